@@ -1,0 +1,304 @@
+// capi.cu -- the extern "C" surface declared in include/dvo_b200.h.
+#include "common.cuh"
+
+#include <cstdio>
+#include <cstring>
+#include <limits>
+
+namespace dvo_b200 {
+
+int set_error(dvo_b200_ctx* ctx, int code, const std::string& msg) {
+  if (ctx) ctx->last_error = msg;
+  return code;
+}
+
+int check_cuda(dvo_b200_ctx* ctx, cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return 0;
+  std::string msg = std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what;
+  cudaGetLastError();
+  return set_error(ctx, e == cudaErrorMemoryAllocation ? DVO_B200_ERR_OUT_OF_MEMORY : DVO_B200_ERR_CUDA, msg);
+}
+
+static cudaEvent_t get_event(dvo_b200_ctx* ctx) {
+  if (!ctx->event_pool.empty()) { cudaEvent_t e = ctx->event_pool.back(); ctx->event_pool.pop_back(); return e; }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+
+ProfScope::ProfScope(dvo_b200_ctx* c, int cls_, int nlaunch) : ctx(c), cls(cls_) {
+  if (!ctx->profile) return;
+  a = get_event(ctx); b = get_event(ctx);
+  cudaEventRecord(a, ctx->stream);
+  ctx->prof_launches[cls] += nlaunch;
+}
+ProfScope::~ProfScope() {
+  if (!a) return;
+  cudaEventRecord(b, ctx->stream);
+  ctx->prof_pending.push_back({cls, {a, b}});
+}
+
+static void drain_profile(dvo_b200_ctx* ctx) {
+  for (auto& e : ctx->prof_pending) {
+    float ms = 0.f;
+    cudaEventSynchronize(e.second.second);
+    cudaEventElapsedTime(&ms, e.second.first, e.second.second);
+    ctx->prof_ms[e.first] += ms;
+    ctx->event_pool.push_back(e.second.first);
+    ctx->event_pool.push_back(e.second.second);
+  }
+  ctx->prof_pending.clear();
+}
+
+namespace {
+
+__global__ void k_convert_raw(const uint8_t* __restrict__ grey, const uint16_t* __restrict__ raw, float scale,
+                              float* __restrict__ I, float* __restrict__ Z, int n) {
+  // benchmark_slam.cpp:58-77: grey u8 -> f32; SurfacePyramid::convertRawDepthImageSse
+  // (surface_pyramid.cpp:65-105): u16 * scale, 0 -> NaN
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  I[i] = (float)grey[i];
+  uint16_t r = raw[i];
+  Z[i] = r == 0 ? __int_as_float(0x7fc00000) : __fmul_rn((float)r, scale);
+}
+
+}  // namespace
+}  // namespace dvo_b200
+
+using namespace dvo_b200;
+
+extern "C" {
+
+int dvo_b200_abi_version(void) { return DVO_B200_ABI_VERSION; }
+
+int dvo_b200_create(int device, void* stream, dvo_b200_ctx** out) {
+  if (!out) return DVO_B200_ERR_INVALID_ARGUMENT;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count) {
+    cudaGetLastError();
+    return DVO_B200_ERR_CUDA;   // no CPU fallback: without a CUDA device there is no engine
+  }
+  if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return DVO_B200_ERR_CUDA; }
+  dvo_b200_ctx* ctx = new dvo_b200_ctx;
+  ctx->device = device;
+  if (stream) { ctx->stream = (cudaStream_t)stream; ctx->own_stream = false; }
+  else {
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); delete ctx; return DVO_B200_ERR_CUDA; }
+    ctx->own_stream = true;
+  }
+  *out = ctx;
+  return 0;
+}
+
+int dvo_b200_destroy(dvo_b200_ctx* ctx) {
+  if (!ctx) return DVO_B200_ERR_INVALID_ARGUMENT;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  drain_profile(ctx);
+  for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
+  Workspace& ws = ctx->ws;
+  cudaFree(ws.d_pair_level); cudaFree(ws.d_state); cudaFree(ws.d_records); cudaFree(ws.d_scale_export);
+  cudaFree(ws.d_tile_base); cudaFree(ws.d_normal_partial); cudaFree(ws.d_active); cudaFree(ws.d_iter_log);
+  if (ws.h_active) cudaFreeHost(ws.h_active);
+  for (auto& kv : ctx->free_slabs) { cudaFree(kv.second->base); delete kv.second; }
+  cudaFree(ctx->d_stage);
+  if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+  if (ctx->h_results) cudaFreeHost(ctx->h_results);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  cudaGetLastError();
+  delete ctx;
+  return 0;
+}
+
+void* dvo_b200_stream(dvo_b200_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+int dvo_b200_synchronize(dvo_b200_ctx* ctx) {
+  if (!ctx) return DVO_B200_ERR_INVALID_ARGUMENT;
+  DVO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+const char* dvo_b200_last_error(dvo_b200_ctx* ctx) { return ctx ? ctx->last_error.c_str() : "null context"; }
+
+void dvo_b200_config_default(dvo_b200_config* cfg) {
+  if (!cfg) return;
+  // dense_tracking_config.cpp:27-42
+  cfg->first_level = 3; cfg->last_level = 1; cfg->max_iterations_per_level = 100; cfg->use_initial_estimate = 0;
+  cfg->precision = 5e-7; cfg->mu = 0.0; cfg->intensity_derivative_threshold = 0.0f; cfg->depth_derivative_threshold = 0.0f;
+}
+
+int64_t dvo_b200_kernel_launches(dvo_b200_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int64_t dvo_b200_h2d_bytes(dvo_b200_ctx* ctx) { return ctx ? ctx->h2d_bytes : 0; }
+int64_t dvo_b200_d2h_bytes(dvo_b200_ctx* ctx) { return ctx ? ctx->d2h_bytes : 0; }
+
+int dvo_b200_pyramid_create_batch(dvo_b200_ctx* ctx, int32_t n, const float* intensity, const float* depth, int32_t width,
+                                  int32_t height, float fx, float fy, float ox, float oy, int32_t levels,
+                                  dvo_b200_pyramid** out) {
+  if (!ctx || !intensity || !depth || !out || n <= 0 || width <= 0 || height <= 0)
+    return set_error(ctx, DVO_B200_ERR_INVALID_ARGUMENT, "pyramid_create: null/invalid argument");
+  cudaSetDevice(ctx->device);
+  size_t img = (size_t)width * height * sizeof(float);
+  int rc = ensure_stage(ctx, 2 * img * n, 0);
+  if (rc) return rc;
+  float* dI = (float*)ctx->d_stage;
+  float* dZ = dI + (size_t)n * width * height;
+  DVO_CUDA(ctx, cudaMemcpyAsync(dI, intensity, img * n, cudaMemcpyHostToDevice, ctx->stream));
+  DVO_CUDA(ctx, cudaMemcpyAsync(dZ, depth, img * n, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->h2d_bytes += 2 * img * n;
+  return pyramid_build_batch(ctx, n, dI, dZ, width, height, fx, fy, ox, oy, levels, 0.f, 0.f, out);
+}
+
+int dvo_b200_pyramid_create(dvo_b200_ctx* ctx, const float* intensity, const float* depth, int32_t width, int32_t height,
+                            float fx, float fy, float ox, float oy, int32_t levels, dvo_b200_pyramid** out) {
+  return dvo_b200_pyramid_create_batch(ctx, 1, intensity, depth, width, height, fx, fy, ox, oy, levels, out);
+}
+
+int dvo_b200_pyramid_create_raw(dvo_b200_ctx* ctx, const uint8_t* grey, const uint16_t* raw_depth, float depth_scale,
+                                int32_t width, int32_t height, float fx, float fy, float ox, float oy, int32_t levels,
+                                dvo_b200_pyramid** out) {
+  if (!ctx || !grey || !raw_depth || !out || width <= 0 || height <= 0)
+    return set_error(ctx, DVO_B200_ERR_INVALID_ARGUMENT, "pyramid_create_raw: null/invalid argument");
+  cudaSetDevice(ctx->device);
+  size_t npx = (size_t)width * height;
+  size_t fbytes = npx * sizeof(float);
+  size_t raw_off = 2 * fbytes;
+  int rc = ensure_stage(ctx, raw_off + npx * 3 + 64, 0);
+  if (rc) return rc;
+  float* dI = (float*)ctx->d_stage;
+  float* dZ = dI + npx;
+  uint16_t* dR = (uint16_t*)((char*)ctx->d_stage + raw_off);
+  uint8_t* dG = (uint8_t*)((char*)ctx->d_stage + raw_off + npx * 2);
+  DVO_CUDA(ctx, cudaMemcpyAsync(dR, raw_depth, npx * 2, cudaMemcpyHostToDevice, ctx->stream));
+  DVO_CUDA(ctx, cudaMemcpyAsync(dG, grey, npx, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->h2d_bytes += npx * 3;
+  k_convert_raw<<<(unsigned)((npx + 255) / 256), 256, 0, ctx->stream>>>(dG, dR, depth_scale, dI, dZ, (int)npx);
+  ctx->launches++;
+  return pyramid_build_batch(ctx, 1, dI, dZ, width, height, fx, fy, ox, oy, levels, 0.f, 0.f, out);
+}
+
+int dvo_b200_pyramid_retain(dvo_b200_pyramid* p) {
+  if (!p) return DVO_B200_ERR_INVALID_ARGUMENT;
+  p->refcount++;
+  return 0;
+}
+
+int dvo_b200_pyramid_release(dvo_b200_pyramid* p) {
+  if (!p) return DVO_B200_ERR_INVALID_ARGUMENT;
+  if (--p->refcount == 0) {
+    // work that reads the planes may still be queued on the stream
+    if (p->ctx) cudaStreamSynchronize(p->ctx->stream);
+    pyramid_free(p);
+  }
+  return 0;
+}
+
+int dvo_b200_pyramid_num_levels(const dvo_b200_pyramid* p) { return p ? p->levels : DVO_B200_ERR_INVALID_ARGUMENT; }
+
+int dvo_b200_pyramid_level_info(const dvo_b200_pyramid* p, int32_t level, int32_t* width, int32_t* height, float K[4]) {
+  if (!p || level < 0 || level >= p->levels) return DVO_B200_ERR_INVALID_ARGUMENT;
+  const LevelInfo& L = p->L[level];
+  if (width) *width = L.w;
+  if (height) *height = L.h;
+  if (K) { K[0] = L.fx; K[1] = L.fy; K[2] = L.ox; K[3] = L.oy; }
+  return 0;
+}
+
+int dvo_b200_pyramid_download(dvo_b200_ctx* ctx, const dvo_b200_pyramid* p, int32_t level, float* planes6) {
+  if (!ctx || !p || !planes6 || level < 0 || level >= p->levels)
+    return set_error(ctx, DVO_B200_ERR_INVALID_ARGUMENT, "pyramid_download: invalid argument");
+  cudaSetDevice(ctx->device);
+  const LevelInfo& L = p->L[level];
+  size_t N = L.n;
+  std::vector<float> tmp(6 * N);
+  DVO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  DVO_CUDA(ctx, cudaMemcpy(tmp.data(), p->planes + L.plane_off, sizeof(float) * 6 * N, cudaMemcpyDeviceToHost));
+  ctx->d2h_bytes += sizeof(float) * 6 * N;
+  for (int pl = 0; pl < 3; ++pl)
+    for (size_t i = 0; i < N; ++i) {
+      planes6[(2 * pl) * N + i] = tmp[pl * 2 * N + 2 * i];
+      planes6[(2 * pl + 1) * N + i] = tmp[pl * 2 * N + 2 * i + 1];
+    }
+  return 0;
+}
+
+int dvo_b200_pyramid_select(dvo_b200_ctx* ctx, dvo_b200_pyramid* p, int32_t level, float intensity_threshold,
+                            float depth_threshold, int64_t* count, uint8_t* mask) {
+  if (!ctx || !p || level < 0 || level >= p->levels)
+    return set_error(ctx, DVO_B200_ERR_INVALID_ARGUMENT, "pyramid_select: invalid argument");
+  cudaSetDevice(ctx->device);
+  int rc = pyramid_reselect(ctx, p, intensity_threshold, depth_threshold);
+  if (rc) return rc;
+  const LevelInfo& L = p->L[level];
+  DVO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  int info[2];
+  DVO_CUDA(ctx, cudaMemcpy(info, p->sel_info + 2 * level, sizeof(info), cudaMemcpyDeviceToHost));
+  if (count) *count = info[0];
+  if (mask) {
+    std::vector<uint32_t> words(L.words);
+    DVO_CUDA(ctx, cudaMemcpy(words.data(), p->sel_mask + L.mask_off, sizeof(uint32_t) * L.words, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < L.n; ++i) mask[i] = (words[i >> 5] >> (i & 31)) & 1u;
+  }
+  return 0;
+}
+
+int dvo_b200_match_batch(dvo_b200_ctx* ctx, const dvo_b200_config* cfg, int32_t n, dvo_b200_pyramid* const* references,
+                         dvo_b200_pyramid* const* currents, const double* T_init, dvo_b200_result* results,
+                         dvo_b200_iteration_stats* iteration_stats, int32_t max_iteration_stats) {
+  if (!ctx || !results) return set_error(ctx, DVO_B200_ERR_INVALID_ARGUMENT, "match_batch: null argument");
+  cudaSetDevice(ctx->device);
+  return tracker_match_batch(ctx, cfg, n, references, currents, T_init, results, nullptr, iteration_stats,
+                             iteration_stats ? max_iteration_stats : 0);
+}
+
+int dvo_b200_match(dvo_b200_ctx* ctx, const dvo_b200_config* cfg, dvo_b200_pyramid* reference, dvo_b200_pyramid* current,
+                   const double* T_init, dvo_b200_result* result) {
+  dvo_b200_pyramid* r[1] = {reference};
+  dvo_b200_pyramid* c[1] = {current};
+  return dvo_b200_match_batch(ctx, cfg, 1, r, c, T_init, result, nullptr, 0);
+}
+
+int dvo_b200_match_batch_device(dvo_b200_ctx* ctx, const dvo_b200_config* cfg, int32_t n,
+                                dvo_b200_pyramid* const* references, dvo_b200_pyramid* const* currents,
+                                const double* T_init, void* d_results) {
+  if (!ctx || !d_results) return set_error(ctx, DVO_B200_ERR_INVALID_ARGUMENT, "match_batch_device: null argument");
+  cudaSetDevice(ctx->device);
+  return tracker_match_batch(ctx, cfg, n, references, currents, T_init, nullptr, d_results, nullptr, 0);
+}
+
+int dvo_b200_residual_image(dvo_b200_ctx* ctx, const dvo_b200_config* cfg, dvo_b200_pyramid* reference,
+                            dvo_b200_pyramid* current, int32_t level, const double* T, float* planes7, int64_t* count) {
+  if (!ctx || !cfg || !planes7) return set_error(ctx, DVO_B200_ERR_INVALID_ARGUMENT, "residual_image: null argument");
+  cudaSetDevice(ctx->device);
+  return tracker_linearize(ctx, cfg, reference, current, level, T, 0, nullptr, count, nullptr, nullptr, nullptr, nullptr, planes7);
+}
+
+int dvo_b200_linearize(dvo_b200_ctx* ctx, const dvo_b200_config* cfg, dvo_b200_pyramid* reference, dvo_b200_pyramid* current,
+                       int32_t level, const double* T, int32_t use_weights, const float* prev_precision, int64_t* count,
+                       float* precision_out, float* ll_out, double* A_out, double* b_out) {
+  if (!ctx || !cfg) return set_error(ctx, DVO_B200_ERR_INVALID_ARGUMENT, "linearize: null argument");
+  cudaSetDevice(ctx->device);
+  return tracker_linearize(ctx, cfg, reference, current, level, T, use_weights, prev_precision, count, precision_out, ll_out,
+                           A_out, b_out, nullptr);
+}
+
+int dvo_b200_profile_enable(dvo_b200_ctx* ctx, int32_t enable) {
+  if (!ctx) return DVO_B200_ERR_INVALID_ARGUMENT;
+  ctx->profile = enable != 0;
+  return 0;
+}
+
+int dvo_b200_profile_read(dvo_b200_ctx* ctx, double ms_out[8], int64_t launches_out[8], int32_t reset) {
+  if (!ctx) return DVO_B200_ERR_INVALID_ARGUMENT;
+  cudaSetDevice(ctx->device);
+  drain_profile(ctx);
+  for (int i = 0; i < 8; ++i) {
+    if (ms_out) ms_out[i] = ctx->prof_ms[i];
+    if (launches_out) launches_out[i] = ctx->prof_launches[i];
+    if (reset) { ctx->prof_ms[i] = 0; ctx->prof_launches[i] = 0; }
+  }
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,187 @@
+// common.cuh -- host/device data model shared by the pyramid and tracker translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/dvo_b200.h"
+#include "se3.cuh"
+
+namespace dvo_b200 {
+
+constexpr int kMaxLevels = DVO_B200_MAX_LEVELS;
+constexpr int kTilePixels = 1024;   // pixels per CTA tile (contiguous in row-major order)
+constexpr int kTileThreads = 256;   // 8 warps x 4 rounds x 32 lanes
+constexpr int kScaleExportFloats = 12;
+constexpr int kNormalPartialFloats = 28;  // ll-sum, 21 upper-triangular A, 6 b
+
+// ---- device image layout --------------------------------------------------------------------
+// Per image, per level l: three float2 planes of h_l*w_l elements, row-major, no row padding:
+//   P0 = (I, Z')   P1 = (Ix, Iy)   P2 = (Zx, Zy)
+// Z' is the depth with NaN wherever ANY of the six channels is NaN at that pixel: a bilinear tap
+// on such a pixel makes the reference reject the point (cmpunord over the 8-vector,
+// dense_tracking_impl.cpp:261) and a reference point there fails isPointOk (point_selection.h:63-66),
+// so one NaN test on the interpolated Z' replaces the reference's test on all lanes.
+// The 8-channel AoS "acceleration" image of the reference (rgbd_image.cpp:534-543) exists only to
+// make CPU gathers contiguous; pairs of channels as float2 give 8-byte gathers and let the
+// reference image be read as two planes (16 B/pixel) and the current as three (24 B/pixel).
+struct LevelInfo {
+  int w, h, n, words;          // words = ceil(n/32) selection-mask words
+  float fx, fy, ox, oy;        // IntrinsicMatrix of this level (intrinsic_matrix.cpp:90-93: whole K * 0.5)
+  size_t plane_off;            // float2 offset of P0 inside dvo_b200_pyramid::planes (P1 = +n, P2 = +2n)
+  size_t mask_off;             // uint32 offset inside sel_mask
+  size_t tmpl_off;             // float offset of tx[w] then ty[h] inside tmpl
+};
+
+struct Slab {                  // one cudaMalloc shared by a batch of pyramids
+  void* base = nullptr;
+  size_t bytes = 0;
+  int refs = 0;
+};
+
+}  // namespace dvo_b200
+
+// opaque handle types of the C ABI
+struct dvo_b200_pyramid {
+  dvo_b200_ctx* ctx = nullptr;
+  int refcount = 1;
+  int levels = 0;
+  dvo_b200::LevelInfo L[dvo_b200::kMaxLevels];
+  dvo_b200::Slab* slab = nullptr;
+  float2* planes = nullptr;      // device
+  uint32_t* sel_mask = nullptr;  // device: selection bitmasks of all levels (default thresholds)
+  int* sel_info = nullptr;       // device: per level {S, last selected linear pixel index}
+  float* tmpl = nullptr;         // device: per level tx[w], ty[h] point-cloud template (rgbd_image.cpp:197-198)
+  float sel_ti = 0.f, sel_td = 0.f;  // thresholds the masks were built with
+  uint64_t id = 0;
+};
+
+namespace dvo_b200 {
+
+// ---- per-pair device state ---------------------------------------------------------------------
+struct PairLevel {              // what one alignment reads at the current level (uploaded per level)
+  const float2* r0; const float2* r1;  // reference P0, P1
+  const uint32_t* rmask;               // reference selection mask
+  const int* rsel;                     // {S, last selected pixel}
+  const float* rtmpl;                  // tx[w], ty[h]
+  const float2* c0; const float2* c1; const float2* c2;  // current P0..P2
+  float cfx, cfy, cox, coy;            // current-image intrinsics (dense_tracking.cpp:212)
+  long long max_valid_pixels;          // PointSelection::getMaximumNumberOfPoints
+};
+
+struct LevelSummary {           // device mirror of dvo_b200_level_stats
+  int id, termination;
+  long long max_valid_pixels, valid_pixels;
+  int num_iterations, has_inc;
+  long long last_n, last_inc_n;
+  double last_inc_nll;
+};
+
+struct PairState {
+  SE3d estimate, estimate_old, initial, initial_old, inc;   // Revertable<SE3d> (util/revertable.h:45-55)
+  double x[6];                  // current increment
+  double error, last_error;     // IterationContext::Error / LastError
+  double A[36], b[6];           // last linearisation (A without mu)
+  double A_done[36];            // EstimateInformation of the last completed iteration on this level (incl. mu)
+  double nll_done, prior_done;  // its TDistributionLogLikelihood / PriorLogLikelihood
+  double nll_cur, prior_cur;
+  int have_done;
+  float precision[4];           // P_k (row-major), also P_{k-1} on entry of an iteration
+  float ll;
+  float kt[12];                 // K * float(estimate)[0:3,:]  (dense_tracking_impl.cpp:142-152)
+  long long n;                  // valid constraints of the current iteration
+  long long n_keep;             // 50*floor(n/50): log-likelihood terms kept (dense_tracking_impl.cpp:413-422)
+  int iteration;                // IterationContext::Iteration
+  int level_active;             // 1 while this pair still iterates on the current level
+  int phase_ok;                 // 1 if the residual stage produced >= 6 constraints (normal stage runs)
+  int termination;
+  int num_levels;
+  int num_iterations_total;
+  int iter_log_count;
+  int pad_;
+  LevelSummary levels[kMaxLevels];
+  double result_T[16], result_info[36], result_ll;
+};
+
+struct ScaleSeg {               // monoid element of the pairwise scale sum (see tracker.cu)
+  int n;
+  float S0[3], S1[3];
+  float wf, wl, ol[3];
+};
+
+struct Workspace {              // per-ctx scratch for a lock-step batch
+  PairLevel* d_pair_level = nullptr;
+  PairState* d_state = nullptr;
+  float* d_records = nullptr;        // per pair 6 planes of N floats {ei, ez, gx, gy, hx, hy}
+  float* d_scale_export = nullptr;   // per pair, per tile: kScaleExportFloats
+  int* d_tile_base = nullptr;        // per pair, per tile: exclusive prefix of valid counts
+  float* d_normal_partial = nullptr; // per pair, per tile: kNormalPartialFloats
+  int* d_active = nullptr;           // number of pairs still active on the level
+  dvo_b200_iteration_stats* d_iter_log = nullptr;
+  int* h_active = nullptr;           // pinned
+  size_t cap_pairs = 0, cap_records = 0, cap_tiles = 0, cap_iter_log = 0;
+};
+
+}  // namespace dvo_b200
+
+struct dvo_b200_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  std::string last_error;
+  int64_t launches = 0, h2d_bytes = 0, d2h_bytes = 0;
+  uint64_t next_pyramid_id = 1;
+  dvo_b200::Workspace ws;
+  // pooled device slabs keyed by size (release -> reuse instead of cudaFree)
+  std::multimap<size_t, dvo_b200::Slab*> free_slabs;
+  // staging for uploads
+  void* d_stage = nullptr; size_t d_stage_bytes = 0;
+  void* h_stage = nullptr; size_t h_stage_bytes = 0;   // pinned bounce buffer for pageable sources
+  void* h_results = nullptr; size_t h_results_bytes = 0;  // pinned
+  // profiling
+  bool profile = false;
+  double prof_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  int64_t prof_launches[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> prof_pending;
+  std::vector<cudaEvent_t> event_pool;
+  std::mutex mu;
+};
+
+namespace dvo_b200 {
+
+int set_error(dvo_b200_ctx* ctx, int code, const std::string& msg);
+int check_cuda(dvo_b200_ctx* ctx, cudaError_t e, const char* what);
+
+#define DVO_CUDA(ctx, call)                                              \
+  do {                                                                   \
+    int rc__ = ::dvo_b200::check_cuda((ctx), (call), #call);             \
+    if (rc__ != 0) return rc__;                                          \
+  } while (0)
+
+// profiling scope: records start/stop events around a kernel class when enabled
+struct ProfScope {
+  dvo_b200_ctx* ctx; int cls; cudaEvent_t a = nullptr, b = nullptr;
+  ProfScope(dvo_b200_ctx* c, int cls_, int nlaunch = 1);
+  ~ProfScope();
+};
+
+// pyramid.cu
+int pyramid_build_batch(dvo_b200_ctx* ctx, int n, const float* d_I, const float* d_Z, int w, int h, float fx, float fy,
+                        float ox, float oy, int levels, float ti, float td, dvo_b200_pyramid** out);
+int pyramid_reselect(dvo_b200_ctx* ctx, dvo_b200_pyramid* p, float ti, float td);
+void pyramid_free(dvo_b200_pyramid* p);
+int ensure_stage(dvo_b200_ctx* ctx, size_t dev_bytes, size_t host_bytes);
+
+// tracker.cu
+int tracker_match_batch(dvo_b200_ctx* ctx, const dvo_b200_config* cfg, int n, dvo_b200_pyramid* const* refs,
+                        dvo_b200_pyramid* const* curs, const double* T_init, dvo_b200_result* h_results,
+                        void* d_results, dvo_b200_iteration_stats* iter_stats, int max_iter_stats);
+int tracker_linearize(dvo_b200_ctx* ctx, const dvo_b200_config* cfg, dvo_b200_pyramid* ref, dvo_b200_pyramid* cur,
+                      int level, const double* T, int use_weights, const float* prev_precision, int64_t* count,
+                      float* precision_out, float* ll_out, double* A_out, double* b_out, float* planes7);
+
+}  // namespace dvo_b200

@@ -1,0 +1,270 @@
+// pyramid.cu -- device image pyramid: replaces RgbdImagePyramid::build (rgbd_image.cpp:156-172),
+// pyrDownMeanSmooth / pyrDownSubsample (rgbd_image.cpp:38-55,127-139), RgbdCameraPyramid::build
+// (rgbd_image.cpp:283-296), calculateDerivativeX/Y (rgbd_image.cpp:419-472, rgbd_image_sse.cpp:241-284),
+// the RgbdCamera point-cloud template (rgbd_image.cpp:186-204) and PointSelection::select with the
+// default predicate (point_selection.cpp:89-152, point_selection.h:63-66).
+#include "common.cuh"
+
+#include <cstdio>
+#include <cstring>
+
+namespace dvo_b200 {
+
+namespace {
+
+__device__ __forceinline__ bool is_nan(float v) { return v != v; }
+
+// level-0 intensity into P0.x (Z slot filled later by the finish pass)
+__global__ void k_pyr_intensity0(const float* __restrict__ I0, float2* __restrict__ planes, size_t planes_per_image,
+                                 size_t plane_off, int n) {
+  int img = blockIdx.y;
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  float2* P0 = planes + img * planes_per_image + plane_off;
+  P0[idx] = make_float2(I0[(size_t)img * n + idx], 0.f);
+}
+
+// level l intensity = ((a+b)+c)+d)/4 of the 2x2 block of level l-1 (rgbd_image.cpp:38-55)
+__global__ void k_pyr_intensity_down(float2* __restrict__ planes, size_t planes_per_image, size_t src_off, int sw,
+                                     size_t dst_off, int dw, int dh) {
+  int img = blockIdx.y;
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= dw * dh) return;
+  int y = idx / dw, x = idx - y * dw;
+  const float2* S = planes + img * planes_per_image + src_off;
+  float2* D = planes + img * planes_per_image + dst_off;
+  const float2* r0 = S + (size_t)(2 * y) * sw + 2 * x;
+  const float2* r1 = r0 + sw;
+  float s = __fadd_rn(r0[0].x, r0[1].x);
+  s = __fadd_rn(s, r1[0].x);
+  s = __fadd_rn(s, r1[1].x);
+  D[idx] = make_float2(s * 0.25f, 0.f);
+}
+
+// gradients (clamped central differences), masked depth, default selection mask for one level.
+// Depth of level l is the pure subsample chain of level 0 (rgbd_image.cpp:127-139): Z_l(y,x) = Z_0(y<<l, x<<l).
+__global__ void k_pyr_finish(const float* __restrict__ Z0, int w0, int n0, float2* __restrict__ planes,
+                             size_t planes_per_image, size_t plane_off, int w, int h, int level,
+                             uint32_t* __restrict__ masks, size_t mask_words_per_image, size_t mask_off,
+                             int* __restrict__ sel_info, int sel_info_per_image, float ti, float td) {
+  int img = blockIdx.y;
+  int n = w * h;
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  bool in = idx < n;
+  bool sel = false;
+  if (in) {
+    int y = idx / w, x = idx - y * w;
+    float2* P0 = planes + img * planes_per_image + plane_off;
+    float2* P1 = P0 + n;
+    float2* P2 = P1 + n;
+    const float* Z = Z0 + (size_t)img * n0;
+    int xp = max(x - 1, 0), xn = min(x + 1, w - 1), yp = max(y - 1, 0), yn = min(y + 1, h - 1);
+    float I = P0[idx].x;
+    float ix = (P0[y * w + xn].x - P0[y * w + xp].x) * 0.5f;
+    float iy = (P0[yn * w + x].x - P0[yp * w + x].x) * 0.5f;
+    float z = Z[(size_t)(y << level) * w0 + (x << level)];
+    float zx = (Z[(size_t)(y << level) * w0 + (xn << level)] - Z[(size_t)(y << level) * w0 + (xp << level)]) * 0.5f;
+    float zy = (Z[(size_t)(yn << level) * w0 + (x << level)] - Z[(size_t)(yp << level) * w0 + (x << level)]) * 0.5f;
+    bool bad = is_nan(I) || is_nan(ix) || is_nan(iy) || is_nan(z) || is_nan(zx) || is_nan(zy);
+    float zm = bad ? __int_as_float(0x7fc00000) : z;
+    P0[idx] = make_float2(I, zm);
+    P1[idx] = make_float2(ix, iy);
+    P2[idx] = make_float2(zx, zy);
+    // ValidPointAndGradientThresholdPredicate::isPointOk (point_selection.h:63-66)
+    sel = !bad && (fabsf(ix) > ti || fabsf(iy) > ti || fabsf(zx) > td || fabsf(zy) > td);
+  }
+  unsigned m = __ballot_sync(0xffffffffu, sel);
+  if ((threadIdx.x & 31) == 0 && idx < ((n + 31) / 32) * 32) {
+    masks[img * mask_words_per_image + mask_off + (idx >> 5)] = m;
+    if (m) {
+      int* info = sel_info + img * sel_info_per_image + 2 * level;
+      atomicAdd(&info[0], __popc(m));
+      atomicMax(&info[1], idx + 31 - __clz(m));
+    }
+  }
+}
+
+// recompute only the selection mask of one level for non-default thresholds
+__global__ void k_reselect(const float2* __restrict__ P0, int n, uint32_t* __restrict__ mask, int* __restrict__ info,
+                           float ti, float td) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  bool sel = false;
+  if (idx < n) {
+    float2 a = P0[idx], b = P0[n + idx], c = P0[2 * (size_t)n + idx];
+    sel = !is_nan(a.y) && (fabsf(b.x) > ti || fabsf(b.y) > ti || fabsf(c.x) > td || fabsf(c.y) > td);
+  }
+  unsigned m = __ballot_sync(0xffffffffu, sel);
+  if ((threadIdx.x & 31) == 0 && idx < ((n + 31) / 32) * 32) {
+    mask[idx >> 5] = m;
+    if (m) {
+      atomicAdd(&info[0], __popc(m));
+      atomicMax(&info[1], idx + 31 - __clz(m));
+    }
+  }
+}
+
+// point-cloud template tx[x] = (x - ox)/fx, ty[y] = (y - oy)/fy (IEEE division, rgbd_image.cpp:197-198)
+// and sel_info initialisation {S = 0, last = -1}
+__global__ void k_template(float* __restrict__ tmpl, size_t tmpl_per_image, size_t off, int w, int h, float fx,
+                           float fy, float ox, float oy, int* __restrict__ sel_info, int sel_info_per_image, int level) {
+  int img = blockIdx.y;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  float* t = tmpl + img * tmpl_per_image + off;
+  if (i < w) t[i] = __fdiv_rn((float)i - ox, fx);
+  else if (i < w + h) t[i] = __fdiv_rn((float)(i - w) - oy, fy);
+  if (i == 0) {
+    sel_info[img * sel_info_per_image + 2 * level] = 0;
+    sel_info[img * sel_info_per_image + 2 * level + 1] = -1;
+  }
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+int ensure_stage(dvo_b200_ctx* ctx, size_t dev_bytes, size_t host_bytes) {
+  if (dev_bytes > ctx->d_stage_bytes) {
+    if (ctx->d_stage) { cudaStreamSynchronize(ctx->stream); cudaFree(ctx->d_stage); ctx->d_stage = nullptr; ctx->d_stage_bytes = 0; }
+    DVO_CUDA(ctx, cudaMalloc(&ctx->d_stage, dev_bytes));
+    ctx->d_stage_bytes = dev_bytes;
+  }
+  if (host_bytes > ctx->h_stage_bytes) {
+    if (ctx->h_stage) { cudaStreamSynchronize(ctx->stream); cudaFreeHost(ctx->h_stage); ctx->h_stage = nullptr; ctx->h_stage_bytes = 0; }
+    DVO_CUDA(ctx, cudaMallocHost(&ctx->h_stage, host_bytes));
+    ctx->h_stage_bytes = host_bytes;
+  }
+  return 0;
+}
+
+static Slab* acquire_slab(dvo_b200_ctx* ctx, size_t bytes) {
+  auto it = ctx->free_slabs.find(bytes);
+  if (it != ctx->free_slabs.end()) {
+    Slab* s = it->second;
+    ctx->free_slabs.erase(it);
+    s->refs = 0;
+    return s;
+  }
+  void* p = nullptr;
+  if (cudaMalloc(&p, bytes) != cudaSuccess) {
+    // drop the pool and retry once
+    for (auto& kv : ctx->free_slabs) { cudaFree(kv.second->base); delete kv.second; }
+    ctx->free_slabs.clear();
+    cudaGetLastError();
+    if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  }
+  Slab* s = new Slab;
+  s->base = p; s->bytes = bytes; s->refs = 0;
+  return s;
+}
+
+void pyramid_free(dvo_b200_pyramid* p) {
+  dvo_b200_ctx* ctx = p->ctx;
+  Slab* s = p->slab;
+  delete p;
+  if (s && --s->refs == 0) {
+    if (ctx) ctx->free_slabs.insert({s->bytes, s});
+    else { cudaFree(s->base); delete s; }
+  }
+}
+
+int pyramid_build_batch(dvo_b200_ctx* ctx, int n, const float* d_I, const float* d_Z, int w, int h, float fx, float fy,
+                        float ox, float oy, int levels, float ti, float td, dvo_b200_pyramid** out) {
+  if (n <= 0 || levels < 1 || levels > kMaxLevels || w < 32 || h < 2)
+    return set_error(ctx, DVO_B200_ERR_INVALID_ARGUMENT, "pyramid: bad geometry");
+  LevelInfo L[kMaxLevels];
+  size_t plane_f2 = 0, mask_words = 0, tmpl_floats = 0;
+  for (int l = 0; l < levels; ++l) {
+    LevelInfo& q = L[l];
+    if (l == 0) { q.w = w; q.h = h; q.fx = fx; q.fy = fy; q.ox = ox; q.oy = oy; }
+    else {
+      q.w = L[l - 1].w / 2; q.h = L[l - 1].h / 2;
+      q.fx = L[l - 1].fx * 0.5f; q.fy = L[l - 1].fy * 0.5f; q.ox = L[l - 1].ox * 0.5f; q.oy = L[l - 1].oy * 0.5f;
+    }
+    if (q.w < 8 || q.h < 2 || (q.w & 1)) return set_error(ctx, DVO_B200_ERR_INVALID_ARGUMENT, "pyramid: level too small / odd width");
+    q.n = q.w * q.h;
+    q.words = (q.n + 31) / 32;
+    q.plane_off = plane_f2; plane_f2 += 3 * (size_t)q.n;
+    q.mask_off = mask_words; mask_words += q.words;
+    q.tmpl_off = tmpl_floats; tmpl_floats += q.w + q.h;
+  }
+  plane_f2 = align_up(plane_f2, 32);          // keep every image 256-byte aligned
+  mask_words = align_up(mask_words, 64);
+  tmpl_floats = align_up(tmpl_floats, 64);
+  const int sel_ints = 2 * kMaxLevels;
+  size_t bytes_planes = (size_t)n * plane_f2 * sizeof(float2);
+  size_t bytes_masks = (size_t)n * mask_words * sizeof(uint32_t);
+  size_t bytes_tmpl = (size_t)n * tmpl_floats * sizeof(float);
+  size_t bytes_sel = align_up((size_t)n * sel_ints * sizeof(int), 256);
+  size_t total = bytes_planes + bytes_masks + bytes_tmpl + bytes_sel;
+  Slab* slab = acquire_slab(ctx, total);
+  if (!slab) return set_error(ctx, DVO_B200_ERR_OUT_OF_MEMORY, "pyramid: cudaMalloc failed");
+  char* base = (char*)slab->base;
+  float2* planes = (float2*)base;
+  uint32_t* masks = (uint32_t*)(base + bytes_planes);
+  float* tmpl = (float*)(base + bytes_planes + bytes_masks);
+  int* sel = (int*)(base + bytes_planes + bytes_masks + bytes_tmpl);
+
+  cudaStream_t st = ctx->stream;
+  {
+    ProfScope prof(ctx, 3, 3 * levels);
+    const int T = 256;
+    for (int l = 0; l < levels; ++l) {
+      const LevelInfo& q = L[l];
+      dim3 gt((q.w + q.h + T - 1) / T, n);
+      k_template<<<gt, T, 0, st>>>(tmpl, tmpl_floats, q.tmpl_off, q.w, q.h, q.fx, q.fy, q.ox, q.oy, sel, sel_ints, l);
+      dim3 g((q.n + T - 1) / T, n);
+      if (l == 0) k_pyr_intensity0<<<g, T, 0, st>>>(d_I, planes, plane_f2, q.plane_off, q.n);
+      else k_pyr_intensity_down<<<g, T, 0, st>>>(planes, plane_f2, L[l - 1].plane_off, L[l - 1].w, q.plane_off, q.w, q.h);
+      ctx->launches += 2;
+    }
+    for (int l = 0; l < levels; ++l) {
+      const LevelInfo& q = L[l];
+      dim3 g((q.words * 32 + T - 1) / T, n);
+      k_pyr_finish<<<g, T, 0, st>>>(d_Z, w, w * h, planes, plane_f2, q.plane_off, q.w, q.h, l, masks, mask_words, q.mask_off,
+                                    sel, sel_ints, ti, td);
+      ctx->launches += 1;
+    }
+  }
+  DVO_CUDA(ctx, cudaGetLastError());
+  for (int i = 0; i < n; ++i) {
+    dvo_b200_pyramid* p = new dvo_b200_pyramid;
+    p->ctx = ctx; p->refcount = 1; p->levels = levels;
+    std::memcpy(p->L, L, sizeof(LevelInfo) * levels);
+    p->slab = slab; slab->refs++;
+    p->planes = planes + (size_t)i * plane_f2;
+    p->sel_mask = masks + (size_t)i * mask_words;
+    p->sel_info = sel + (size_t)i * sel_ints;
+    p->tmpl = tmpl + (size_t)i * tmpl_floats;
+    p->sel_ti = ti; p->sel_td = td;
+    p->id = ctx->next_pyramid_id++;
+    out[i] = p;
+  }
+  return 0;
+}
+
+int pyramid_reselect(dvo_b200_ctx* ctx, dvo_b200_pyramid* p, float ti, float td) {
+  if (p->sel_ti == ti && p->sel_td == td) return 0;
+  cudaStream_t st = ctx->stream;
+  std::vector<int> init(2 * kMaxLevels);
+  for (int l = 0; l < kMaxLevels; ++l) { init[2 * l] = 0; init[2 * l + 1] = -1; }
+  // small synchronous-ish upload through the pinned stage
+  int rc = ensure_stage(ctx, 0, 4096);
+  if (rc) return rc;
+  DVO_CUDA(ctx, cudaStreamSynchronize(st));
+  std::memcpy(ctx->h_stage, init.data(), init.size() * sizeof(int));
+  DVO_CUDA(ctx, cudaMemcpyAsync(p->sel_info, ctx->h_stage, init.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+  ProfScope prof(ctx, 4, p->levels);
+  for (int l = 0; l < p->levels; ++l) {
+    const LevelInfo& q = p->L[l];
+    const int T = 256;
+    k_reselect<<<(q.words * 32 + T - 1) / T, T, 0, st>>>(p->planes + q.plane_off, q.n, p->sel_mask + q.mask_off,
+                                                         p->sel_info + 2 * l, ti, td);
+    ctx->launches += 1;
+  }
+  DVO_CUDA(ctx, cudaGetLastError());
+  DVO_CUDA(ctx, cudaStreamSynchronize(st));  // h_stage reuse safety
+  p->sel_ti = ti; p->sel_td = td;
+  return 0;
+}
+
+}  // namespace dvo_b200
