@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""bench.py -- frame-pair alignments/sec @640x480x5-level (BASELINE.json metric) on N B200s.
+
+A "step" = one pass of the hot path (DenseTracker::match, all levels, all iterations, 6x6 solves)
+over one batch of synthetic frame pairs.  Workload at every N: 512 independent 640x480 pairs PER GPU
+(configs[2]; configs[3] = 4096 pairs over 8 GPUs is the same per-GPU batch -> weak scaling).
+
+  value  : alignments/s with the pyramids already resident in HBM (device time, CUDA events on the
+           engine stream, max over ranks)
+  e2e    : the same metric through the public C-ABI call sequence with HOST buffers: pinned host
+           images -> dvo_b200_pyramid_create_batch (H2D + pyramid build) -> dvo_b200_match_batch ->
+           results on the host (D2H), every step
+  roofline: the two stage kernels of a Gauss-Newton iteration (k_residual + k_normal), algorithmic
+           40 B per pixel-iteration / their device time measured with CUDA events
+  cpu_baseline: the oracle's FAITHFUL restatement of the reference CPU path, match-only, on the
+           box's host cores (bounded sample)
+  --impl reference: the reference's CPU algorithm (oracle FAITHFUL port; the reference itself needs
+           Eigen/OpenCV/Sophus and cannot be built here) from host images: pyramid build + match.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+W, H, LEVELS = 640, 480, 5
+FIRST_LEVEL, LAST_LEVEL, MAX_IT, PRECISION = 4, 0, 50, 1e-4   # benchmark.yaml:3-4 values, 5 levels
+ALGO_BYTES_PER_PIXEL_ITERATION = 40.0
+LEVEL_PIXELS = [(W >> l) * (H >> l) for l in range(LEVELS)]
+METRIC = "frame-pair alignments/sec @640x480x5-level"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=512, help="frame pairs per GPU")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="pairs in the CPU baseline sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md recipe)
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm (oracle = test infrastructure; only this leg of bench.py may execute it)
+# ---------------------------------------------------------------------------------------------
+def cpu_alignments(pairs, include_pyramid: bool, threads: int):
+    """Runs the oracle FAITHFUL match on `pairs` with `threads` host threads; returns (seconds, n)."""
+    from oracle import oracle_py as orc
+    orc.lib()
+    K = pairs[0]["intrinsics"]
+    cfg = orc.config(first_level=FIRST_LEVEL, last_level=LAST_LEVEL, max_iterations_per_level=MAX_IT, precision=PRECISION)
+    mode = orc.mode("faithful")
+    prebuilt = None
+    if not include_pyramid:
+        prebuilt = [(orc.Pyramid(p["I_ref"], p["Z_ref"], K, LEVELS), orc.Pyramid(p["I_cur"], p["Z_cur"], K, LEVELS)) for p in pairs]
+    idx = list(range(len(pairs)))
+    lock = threading.Lock()
+
+    def worker():
+        while True:
+            with lock:
+                if not idx:
+                    return
+                i = idx.pop()
+            if include_pyramid:
+                r = orc.Pyramid(pairs[i]["I_ref"], pairs[i]["Z_ref"], K, LEVELS)
+                c = orc.Pyramid(pairs[i]["I_cur"], pairs[i]["Z_cur"], K, LEVELS)
+            else:
+                r, c = prebuilt[i]
+            orc.match(r, c, cfg, mode, max_iters=8)
+
+    t0 = time.perf_counter()
+    ths = [threading.Thread(target=worker) for _ in range(threads)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    return time.perf_counter() - t0, len(pairs)
+
+
+def host_pairs(seeds, device="cpu"):
+    from dvo_slam_b200 import synth
+    out = []
+    for s in seeds:
+        p = synth.make_pair(s, device=device)
+        out.append({k: (v.cpu().numpy() if hasattr(v, "cpu") else v) for k, v in p.items()})
+    return out
+
+
+def run_reference(args, rank, world):
+    """Reference arm: the reference's CPU algorithm on the host cores (oracle FAITHFUL port)."""
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    per_step = args.cpu_sample or max(cores, min(4 * cores, 64))
+    dev = "cpu"
+    try:
+        import torch
+        if torch.cuda.is_available():
+            dev = "cuda:0"
+    except Exception:
+        pass
+    pairs = host_pairs(range(per_step), device=dev)
+    for _ in range(min(args.warmup, 1)):
+        cpu_alignments(pairs[:cores], True, cores)
+    t_total, n_total = 0.0, 0
+    for _ in range(args.steps):
+        t, n = cpu_alignments(pairs, True, cores)
+        t_total += t
+        n_total += n
+    value = n_total / t_total
+    sample = f"{per_step} pairs/step x {args.steps} steps, oracle FAITHFUL, pyramid build + match from host images, {cores} threads"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "alignments/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{per_step}-pair sample of the batch={args.batch}/GPU 640x480 5-level workload",
+                       "first_level": FIRST_LEVEL, "last_level": LAST_LEVEL, "max_iterations_per_level": MAX_IT, "precision": PRECISION},
+            "cpu_baseline": {"value": value, "unit": "alignments/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "alignments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "reference sources need Eigen3/OpenCV2/Sophus (absent here): timed arm is the oracle's FAITHFUL port"}
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------
+def run_ours(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    from dvo_slam_b200 import synth
+    from dvo_slam_b200.distributed import all_gather_results, results_to_tensor
+    from dvo_slam_b200.engine import Config, Engine, CResult
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    B = args.batch
+    total = B * world
+    eng = Engine(device=local_rank)
+    stream = torch.cuda.ExternalStream(eng.stream, device=dev)
+    cfg = Config(first_level=FIRST_LEVEL, last_level=LAST_LEVEL, max_iterations_per_level=MAX_IT, precision=PRECISION)
+    K = synth.FR1_INTRINSICS
+
+    # ---- synthetic batch: distinct seeded pairs, rendered on the GPU, kept in pinned host memory ----
+    npx = W * H
+    hI = torch.empty((2 * B, H, W), dtype=torch.float32).pin_memory()
+    hZ = torch.empty((2 * B, H, W), dtype=torch.float32).pin_memory()
+    scfg = synth.SceneConfig()
+    for i in range(B):
+        p = synth.make_pair(rank * B + i, scfg, device=dev)
+        hI[i].copy_(p["I_ref"]); hZ[i].copy_(p["Z_ref"])
+        hI[B + i].copy_(p["I_cur"]); hZ[B + i].copy_(p["Z_cur"])
+    torch.cuda.synchronize()
+    h2d_per_step = 2 * (2 * B) * npx * 4
+    d2h_per_step = B * C.sizeof(CResult)
+
+    def build_pyramids():
+        pyrs = eng.pyramid_batch(None, None, K, LEVELS, host_ptrs=(hI.data_ptr(), hZ.data_ptr(), 2 * B, H, W))
+        return pyrs[:B], pyrs[B:]
+
+    refs, curs = build_pyramids()
+    eng.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    last = {}
+
+    def step_resident():
+        last["res"] = eng.match_batch(refs, curs, cfg, raw=True)
+
+    def step_e2e():
+        r, c = build_pyramids()
+        last["res_e2e"] = eng.match_batch(r, c, cfg, raw=True)
+        for p in r + c:
+            p.release()
+
+    # ---- value: resident pyramids ----
+    for _ in range(args.warmup):
+        step_resident()
+    eng.profile_read(reset=True)
+    eng.profile_enable(True)
+    launches0 = eng.kernel_launches()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_total = timed(step_resident, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = eng.kernel_launches() - launches0
+    prof = eng.profile_read(reset=True)
+    eng.profile_enable(False)
+    ms_per_step = ms_total / args.steps
+    value = total / (ms_per_step * 1e-3)
+
+    # pixel-iterations actually executed in one step on this rank (from the results' statistics)
+    res = last["res"]
+    pix_iters = 0
+    it_hist = [0] * LEVELS
+    for i in range(B):
+        for l in range(res[i].num_levels):
+            ls = res[i].levels[l]
+            pix_iters += LEVEL_PIXELS[ls.id] * ls.num_iterations
+            it_hist[ls.id] += ls.num_iterations
+    stage_ms = (prof["residual"]["ms"] + prof["normal"]["ms"]) / args.steps
+    stage_launches = (prof["residual"]["launches"] + prof["normal"]["launches"]) / args.steps
+    algo_bytes = ALGO_BYTES_PER_PIXEL_ITERATION * pix_iters
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = algo_bytes / (stage_ms * 1e-3) / 1e9 if stage_ms > 0 else 0.0
+
+    # ---- e2e: host buffers in, host results out, every step ----
+    for _ in range(max(1, min(args.warmup, 2))):
+        step_e2e()
+    h2d0, d2h0 = eng.h2d_bytes(), eng.d2h_bytes()
+    ms_e2e = timed(step_e2e, args.steps) / args.steps
+    h2d_meas = (eng.h2d_bytes() - h2d0) / args.steps
+    d2h_meas = (eng.d2h_bytes() - d2h0) / args.steps
+    e2e_value = total / (ms_e2e * 1e-3)
+
+    # ---- result gather (one all-gather of fixed-size records, outside the iteration loop) ----
+    gathered = all_gather_results(results_to_tensor(res, dev), total)
+    assert gathered.shape[0] == total
+
+    # ---- single-pair latency (configs[1]) ----
+    lat_ms = None
+    if rank == 0:
+        for _ in range(3):
+            eng.match_batch(refs[:1], curs[:1], cfg, raw=True)
+        t0 = time.perf_counter()
+        for _ in range(10):
+            eng.match_batch(refs[:1], curs[:1], cfg, raw=True)
+        lat_ms = (time.perf_counter() - t0) / 10 * 1e3
+
+    # ---- CPU baseline: oracle FAITHFUL, match only, bounded sample (rank 0, N=1 only) ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        nsample = args.cpu_sample or max(cores, min(4 * cores, 64))
+        hp = [{"I_ref": hI[i].numpy(), "Z_ref": hZ[i].numpy(), "I_cur": hI[B + i].numpy(), "Z_cur": hZ[B + i].numpy(),
+               "intrinsics": K} for i in range(min(nsample, B))]
+        t1, n1 = cpu_alignments(hp[: max(2, min(8, len(hp)))], False, 1)
+        tc, nc = cpu_alignments(hp, False, cores)
+        cpu = {"value": nc / tc, "unit": "alignments/s", "cores": cores, "kind": "port",
+               "sample": f"first {len(hp)} pairs of the batch, oracle FAITHFUL match() on prebuilt pyramids, {cores} threads",
+               "value_1core": n1 / t1}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "alignments/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic",
+                "config": {"workload": f"batch={B} independent 640x480 frame pairs per GPU, 5-level pyramid (FirstLevel=4, LastLevel=0)",
+                           "global_batch": total, "max_iterations_per_level": MAX_IT, "precision": PRECISION, "mu": 0.0,
+                           "parallelism": f"pairs sharded over {world} GPU(s), no data-path collective, one result all-gather",
+                           "l2": "inputs larger than L2: %.1f GB of pyramids per GPU" % (2 * B * sum(LEVEL_PIXELS) * 24 / 1e9),
+                           "iterations_per_level_mean": [it_hist[l] / B for l in range(LEVELS)]},
+                "e2e": {"value": e2e_value, "unit": "alignments/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d_per_step,
+                        "d2h_bytes_per_step": d2h_per_step, "h2d_bytes_counted": h2d_meas, "d2h_bytes_counted": d2h_meas},
+                "gpu_launches": int(launches),
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
+                             "traffic": None, "kernel": "k_residual + k_normal (the two stages of one Gauss-Newton iteration)",
+                             "algorithmic_bytes_per_step": algo_bytes, "kernel_ms_per_step": stage_ms,
+                             "launches_per_step": stage_launches,
+                             "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+                             "kernel_share_of_step": stage_ms / ms_per_step if ms_per_step else None,
+                             "pair_step_ms_per_step": prof["pair_step"]["ms"] / args.steps},
+                "cpu_baseline": cpu, "clocks": clocks, "single_pair_latency_ms": lat_ms}
+        print(json.dumps(line))
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank, local_rank, world)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -102,7 +102,7 @@ int dvo_b200_destroy(dvo_b200_ctx* ctx) {
   cudaFree(ws.d_pair_level); cudaFree(ws.d_state); cudaFree(ws.d_records); cudaFree(ws.d_scale_export);
   cudaFree(ws.d_tile_base); cudaFree(ws.d_normal_partial); cudaFree(ws.d_active); cudaFree(ws.d_iter_log);
   if (ws.h_active) cudaFreeHost(ws.h_active);
-  for (auto& kv : ctx->free_slabs) { cudaFree(kv.second->base); delete kv.second; }
+  for (auto& kv : ctx->free_slabs) { cudaFree(kv.second->base); if (kv.second->ready) cudaEventDestroy(kv.second->ready); delete kv.second; }
   cudaFree(ctx->d_stage);
   if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
   if (ctx->h_results) cudaFreeHost(ctx->h_results);
@@ -187,8 +187,9 @@ int dvo_b200_pyramid_retain(dvo_b200_pyramid* p) {
 int dvo_b200_pyramid_release(dvo_b200_pyramid* p) {
   if (!p) return DVO_B200_ERR_INVALID_ARGUMENT;
   if (--p->refcount == 0) {
-    // work that reads the planes may still be queued on the stream
-    if (p->ctx) cudaStreamSynchronize(p->ctx->stream);
+    // No synchronisation: the slab returns to the owning ctx's pool and is only ever rewritten by
+    // work enqueued later on that ctx's stream (stream order protects queued readers).  A second
+    // ctx that uses this pyramid holds a reference until its (blocking) match call has returned.
     pyramid_free(p);
   }
   return 0;

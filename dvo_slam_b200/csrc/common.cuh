@@ -41,6 +41,7 @@ struct Slab {                  // one cudaMalloc shared by a batch of pyramids
   void* base = nullptr;
   size_t bytes = 0;
   int refs = 0;
+  cudaEvent_t ready = nullptr;   // recorded on the creating stream after the build kernels
 };
 
 }  // namespace dvo_b200

@@ -147,7 +147,7 @@ static Slab* acquire_slab(dvo_b200_ctx* ctx, size_t bytes) {
   void* p = nullptr;
   if (cudaMalloc(&p, bytes) != cudaSuccess) {
     // drop the pool and retry once
-    for (auto& kv : ctx->free_slabs) { cudaFree(kv.second->base); delete kv.second; }
+    for (auto& kv : ctx->free_slabs) { cudaFree(kv.second->base); if (kv.second->ready) cudaEventDestroy(kv.second->ready); delete kv.second; }
     ctx->free_slabs.clear();
     cudaGetLastError();
     if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
@@ -163,7 +163,7 @@ void pyramid_free(dvo_b200_pyramid* p) {
   delete p;
   if (s && --s->refs == 0) {
     if (ctx) ctx->free_slabs.insert({s->bytes, s});
-    else { cudaFree(s->base); delete s; }
+    else { cudaFree(s->base); if (s->ready) cudaEventDestroy(s->ready); delete s; }
   }
 }
 
@@ -226,6 +226,8 @@ int pyramid_build_batch(dvo_b200_ctx* ctx, int n, const float* d_I, const float*
     }
   }
   DVO_CUDA(ctx, cudaGetLastError());
+  if (!slab->ready) DVO_CUDA(ctx, cudaEventCreateWithFlags(&slab->ready, cudaEventDisableTiming));
+  DVO_CUDA(ctx, cudaEventRecord(slab->ready, st));
   for (int i = 0; i < n; ++i) {
     dvo_b200_pyramid* p = new dvo_b200_pyramid;
     p->ctx = ctx; p->refcount = 1; p->levels = levels;

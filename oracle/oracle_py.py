@@ -130,9 +130,12 @@ class Pyramid:
         self.levels = levels
 
     def __del__(self):
-        if getattr(self, "h", None):
-            lib().orc_pyramid_destroy(self.h)
-            self.h = None
+        h, self.h = getattr(self, "h", None), None
+        if h and _lib is not None:   # at interpreter teardown the module globals may already be gone
+            try:
+                _lib.orc_pyramid_destroy(h)
+            except Exception:
+                pass
 
     def level_info(self, level):
         w, h = C.c_int(), C.c_int()

@@ -1,0 +1,283 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle on identical
+inputs.  Tolerances (see DESIGN.md "Parity"):
+  * per pixel / per function at a FIXED transform, against the oracle's MIRROR mode (reference
+    structure incl. the scale pair bug, odd-point drop and LL tail drop; IEEE arithmetic in the
+    kernels' operation order): residual records BIT-EXACT, valid-constraint counts exact,
+    precision / log-likelihood / A / b to 2e-6 relative (summation order only);
+  * whole alignments against the oracle's FAITHFUL mode (the reference's SSE numerics): pose within
+    POSE_TOL_T = 1e-3 m / POSE_TOL_R = 1e-3 rad at 640x480, identical selected-pixel counts.
+"""
+import numpy as np
+import pytest
+
+from helpers import (GOLDEN_LEVELS, GOLDEN_SEEDS, POSE_TOL_R, POSE_TOL_T, golden_images, load_golden, nan_equal,
+                     pose_delta)
+
+pytestmark = pytest.mark.gpu
+
+
+def _cfgs(orc, first, last, **kw):
+    from dvo_slam_b200.engine import Config
+    base = dict(first_level=first, last_level=last, max_iterations_per_level=50, precision=1e-4)
+    base.update(kw)
+    return Config(**base), orc.config(**base)
+
+
+def _golden_pyramids(engine, oracle, g):
+    im = golden_images(g, oracle)
+    gp = (engine.pyramid(im["I_ref"], im["Z_ref"], g["K"], GOLDEN_LEVELS), engine.pyramid(im["I_cur"], im["Z_cur"], g["K"], GOLDEN_LEVELS))
+    op = (oracle.Pyramid(im["I_ref"], im["Z_ref"], g["K"], GOLDEN_LEVELS), oracle.Pyramid(im["I_cur"], im["Z_cur"], g["K"], GOLDEN_LEVELS))
+    return gp, op
+
+
+@pytest.fixture(scope="module")
+def full_pairs(oracle):
+    """Four seeded 640x480 pairs (config 1/2 of BASELINE.json) with oracle pyramids."""
+    from dvo_slam_b200 import synth
+    out = []
+    for seed in range(4):
+        p = synth.make_pair(seed)
+        a = {k: p[k].numpy() for k in ("I_ref", "Z_ref", "I_cur", "Z_cur")}
+        a["K"], a["T_true"], a["xi"] = p["intrinsics"], p["T_true"], p["xi"]
+        a["oref"] = oracle.Pyramid(a["I_ref"], a["Z_ref"], a["K"], 5)
+        a["ocur"] = oracle.Pyramid(a["I_cur"], a["Z_cur"], a["K"], 5)
+        out.append(a)
+    return out
+
+
+@pytest.mark.parametrize("seed", GOLDEN_SEEDS)
+def test_pyramid_bit_exact_and_selection(engine, oracle, seed):
+    g = load_golden(seed)
+    (gref, _), (oref, _) = _golden_pyramids(engine, oracle, g)
+    for lvl in range(GOLDEN_LEVELS):
+        gp, op = gref.download(lvl), oref.planes(lvl)
+        bad = np.isnan(op).any(axis=0)
+        op[1][bad] = np.nan               # device depth is masked where any channel is NaN
+        for c in range(6):
+            assert nan_equal(gp[c], op[c]), (lvl, c)
+        S, mask = gref.select(lvl)
+        So, masko = oracle.select(oref, lvl)
+        assert S == So == int(g[f"sel_l{lvl}"]) and np.array_equal(mask, masko)
+        assert gref.level_info(lvl) == oref.level_info(lvl)
+    # non-default thresholds (DenseTracker::Config::Intensity/DepthDerivativeThreshold)
+    S, mask = gref.select(0, 4.0, 0.02)
+    So, masko = oracle.select(oref, 0, 4.0, 0.02)
+    assert S == So and np.array_equal(mask, masko) and S < int(g["sel_l0"])
+    gref.select(0, 0.0, 0.0)
+
+
+def test_raw_input_conversion(engine, oracle):
+    """N2 row: u8 grey + u16 raw depth in, conversion on the device (surface_pyramid.cpp:65-105)."""
+    g = load_golden(11)
+    im = golden_images(g, oracle)
+    a = engine.pyramid_raw(g["grey_ref"], g["depth_ref"], 1.0 / 5000.0, g["K"], GOLDEN_LEVELS)
+    b = engine.pyramid(im["I_ref"], im["Z_ref"], g["K"], GOLDEN_LEVELS)
+    for lvl in range(GOLDEN_LEVELS):
+        assert nan_equal(a.download(lvl), b.download(lvl))
+
+
+@pytest.mark.parametrize("seed", GOLDEN_SEEDS)
+def test_residual_records_bit_exact_and_linearisation(engine, oracle, seed):
+    g = load_golden(seed)
+    (gref, gcur), (oref, ocur) = _golden_pyramids(engine, oracle, g)
+    mir = oracle.mode("mirror")
+    for lvl in range(GOLDEN_LEVELS):
+        n_g, img_g = engine.residual_image(gref, gcur, lvl, g["kat_T"])
+        n_o, img_o = oracle.residual_image(oref, ocur, lvl, g["kat_T"], mir)
+        assert n_g == n_o and nan_equal(img_g, img_o)
+        for uw in (0, 1):
+            lg = engine.linearize(gref, gcur, lvl, g["kat_T"], bool(uw), g["kat_prev_precision"])
+            key = f"kat_mirror_l{lvl}_w{uw}"
+            assert lg["n"] == int(g[key + "_n"])
+            assert np.allclose(lg["precision"], g[key + "_P"], rtol=2e-6)
+            assert abs(lg["ll"] - float(g[key + "_ll"])) <= 2e-6 * abs(float(g[key + "_ll"])) + 0.5
+            assert np.allclose(lg["A"], g[key + "_A"], rtol=0, atol=2e-6 * np.abs(g[key + "_A"]).max())
+            assert np.allclose(lg["b"], g[key + "_b"], rtol=0, atol=2e-6 * np.abs(g[key + "_b"]).max() + 1e-3)
+
+
+def test_full_resolution_records_and_linearisation(engine, oracle, full_pairs):
+    from dvo_slam_b200 import synth
+    a = full_pairs[0]
+    gref = engine.pyramid(a["I_ref"], a["Z_ref"], a["K"], 5)
+    gcur = engine.pyramid(a["I_cur"], a["Z_cur"], a["K"], 5)
+    T = synth.se3_exp(a["xi"] * 0.9)
+    mir = oracle.mode("mirror")
+    pp = np.array([[2000.0, -30.0], [-30.0, 9000.0]], dtype=np.float32)
+    for lvl in (4, 1, 0):
+        n_g, img_g = engine.residual_image(gref, gcur, lvl, T)
+        n_o, img_o = oracle.residual_image(a["oref"], a["ocur"], lvl, T, mir)
+        assert n_g == n_o and nan_equal(img_g, img_o)
+        for uw in (False, True):
+            lg = engine.linearize(gref, gcur, lvl, T, uw, pp)
+            lo = oracle.linearize(a["oref"], a["ocur"], lvl, T, mir, uw, pp)
+            assert lg["n"] == lo["n"]
+            assert np.allclose(lg["precision"], lo["precision"], rtol=2e-6)
+            assert abs(lg["ll"] - lo["ll"]) <= 2e-6 * abs(lo["ll"]) + 0.5
+            assert np.allclose(lg["A"], lo["A"], rtol=0, atol=2e-6 * np.abs(lo["A"]).max())
+            assert np.allclose(lg["b"], lo["b"], rtol=0, atol=2e-6 * np.abs(lo["b"]).max())
+
+
+def test_match_pose_within_tolerance_of_reference_numerics(engine, oracle, full_pairs):
+    """configs[1]: single 640x480 pair, 5 levels; pose vs the CPU path within the stated SE(3) tolerance."""
+    cfg, ocfg = _cfgs(oracle, 4, 0)
+    exact_tc = 0
+    for a in full_pairs:
+        gref = engine.pyramid(a["I_ref"], a["Z_ref"], a["K"], 5)
+        gcur = engine.pyramid(a["I_cur"], a["Z_cur"], a["K"], 5)
+        r = engine.match(gref, gcur, cfg, with_iterations=True)
+        fa = oracle.match(a["oref"], a["ocur"], ocfg, oracle.mode("faithful"))
+        mi = oracle.match(a["oref"], a["ocur"], ocfg, oracle.mode("mirror"))
+        dt, dr = pose_delta(fa["T"], r.transformation)
+        assert dt < POSE_TOL_T and dr < POSE_TOL_R, (dt, dr)
+        assert [l["valid_pixels"] for l in r.levels] == [l["valid_pixels"] for l in fa["levels"]]
+        assert [l["max_valid_pixels"] for l in r.levels] == [l["max_valid_pixels"] for l in fa["levels"]]
+        assert not r.is_nan()
+        # ground truth: Result.Transformation = inv(T_true)
+        dt, dr = pose_delta(np.linalg.inv(a["T_true"]), r.transformation)
+        assert dt < 3e-3 and dr < 1e-3
+        # against MIRROR the control flow is identical unless an accept test is decided by summation order
+        same = [l["num_iterations"] for l in r.levels] == [l["num_iterations"] for l in mi["levels"]] and \
+               [l["termination"] for l in r.levels] == [l["termination"] for l in mi["levels"]]
+        if same:
+            exact_tc += 1
+            dt, dr = pose_delta(mi["T"], r.transformation)
+            assert dt < 1e-5 and dr < 1e-5
+            assert np.allclose(r.information, mi["information"], rtol=1e-3)
+            assert abs(r.log_likelihood - mi["log_likelihood"]) <= 1e-5 * abs(mi["log_likelihood"])
+            assert [it["n"] for it in r.iterations] == [it["n"] for it in mi["iterations"]]
+    assert exact_tc >= len(full_pairs) - 1
+
+
+@pytest.mark.parametrize("seed", GOLDEN_SEEDS)
+def test_match_against_golden_fixtures(engine, oracle, seed):
+    g = load_golden(seed)
+    (gref, gcur), _ = _golden_pyramids(engine, oracle, g)
+    cfg, _ = _cfgs(oracle, 2, 0)
+    r = engine.match(gref, gcur, cfg)
+    dt, dr = pose_delta(g["faithful_T"], r.transformation)
+    assert dt < 4 * POSE_TOL_T and dr < 4 * POSE_TOL_R      # 160x120: pixels 4x coarser than 640x480
+    assert [l["valid_pixels"] for l in r.levels] == g["mirror_levels"][:, 2].tolist()
+    if [l["num_iterations"] for l in r.levels] == g["mirror_levels"][:, 3].tolist():
+        dt, dr = pose_delta(g["mirror_T"], r.transformation)
+        assert dt < 1e-5 and dr < 1e-5
+
+
+def test_batch_equals_single_and_is_deterministic(engine, oracle, full_pairs):
+    cfg, _ = _cfgs(oracle, 4, 0)
+    refs = engine.pyramid_batch(np.stack([a["I_ref"] for a in full_pairs]), np.stack([a["Z_ref"] for a in full_pairs]), full_pairs[0]["K"], 5)
+    curs = engine.pyramid_batch(np.stack([a["I_cur"] for a in full_pairs]), np.stack([a["Z_cur"] for a in full_pairs]), full_pairs[0]["K"], 5)
+    batch = engine.match_batch(refs, curs, cfg)
+    again = engine.match_batch(refs, curs, cfg)
+    for i in range(len(full_pairs)):
+        single = engine.match(refs[i], curs[i], cfg)
+        assert np.array_equal(batch[i].transformation, single.transformation)      # fixed-order reductions
+        assert np.array_equal(batch[i].transformation, again[i].transformation)
+        assert np.array_equal(batch[i].information, again[i].information)
+        assert batch[i].levels == single.levels
+
+
+def test_inverse_consistency(engine, oracle, full_pairs):
+    """CrossValidationVoter property (constraint_proposal_voter.cpp:73-77): match(a,b) o match(b,a) ~ I."""
+    cfg, _ = _cfgs(oracle, 4, 0)
+    a = full_pairs[1]
+    p = engine.pyramid(a["I_ref"], a["Z_ref"], a["K"], 5)
+    q = engine.pyramid(a["I_cur"], a["Z_cur"], a["K"], 5)
+    fwd, bwd = engine.match_batch([p, q], [q, p], cfg)
+    dt, dr = pose_delta(np.eye(4), fwd.transformation @ bwd.transformation)
+    assert dt < 3e-3 and dr < 1e-3
+
+
+def test_initial_estimate_mu_and_default_levels(engine, oracle, full_pairs):
+    """benchmark.yaml:1-15 style configuration: levels 3..1, use_initial_estimate, mu = 0.05."""
+    a = full_pairs[2]
+    gref = engine.pyramid(a["I_ref"], a["Z_ref"], a["K"], 4)
+    gcur = engine.pyramid(a["I_cur"], a["Z_cur"], a["K"], 4)
+    cfg, ocfg = _cfgs(oracle, 3, 1, use_initial_estimate=1, mu=0.05)
+    from dvo_slam_b200 import synth
+    T0 = synth.se3_exp(a["xi"] * 0.7)          # guess is reference -> current
+    r = engine.match(gref, gcur, cfg, T_init=T0, with_iterations=True)
+    fa = oracle.match(a["oref"], a["ocur"], ocfg, oracle.mode("faithful"), T_init=T0)
+    mi = oracle.match(a["oref"], a["ocur"], ocfg, oracle.mode("mirror"), T_init=T0)
+    dt, dr = pose_delta(fa["T"], r.transformation)
+    assert dt < 2 * POSE_TOL_T and dr < POSE_TOL_R        # stops at level 1 (320x240)
+    assert [l["id"] for l in r.levels] == [3, 2, 1]
+    if [l["num_iterations"] for l in r.levels] == [l["num_iterations"] for l in mi["levels"]]:
+        assert np.allclose([it["prior"] for it in r.iterations], [it["prior"] for it in mi["iterations"]], rtol=1e-3, atol=1e-9)
+        assert np.allclose(r.information, mi["information"], rtol=1e-3)
+
+
+def test_degenerate_inputs(engine, oracle, full_pairs):
+    a = full_pairs[3]
+    cfg, ocfg = _cfgs(oracle, 4, 0)
+    gref = engine.pyramid(a["I_ref"], a["Z_ref"], a["K"], 5)
+    # (1) no valid depth in the current image: n = 0 on every level, increments reverted, NaN information
+    gnan = engine.pyramid(a["I_cur"], np.full_like(a["Z_cur"], np.nan), a["K"], 5)
+    r = engine.match(gref, gnan, cfg)
+    onan = oracle.Pyramid(a["I_cur"], np.full_like(a["Z_cur"], np.nan), a["K"], 5)
+    o = oracle.match(a["oref"], onan, ocfg, oracle.mode("faithful"))
+    assert [l["termination"] for l in r.levels] == [l["termination"] for l in o["levels"]]
+    assert [l["num_iterations"] for l in r.levels] == [1] * 5
+    assert np.allclose(r.transformation, np.eye(4)) and np.isnan(r.information).all() and r.is_nan()
+    # (2) identical frames: identity pose
+    r = engine.match(gref, gref, cfg)
+    dt, dr = pose_delta(np.eye(4), r.transformation)
+    assert dt < 1e-5 and dr < 1e-5
+    # (3) max_iterations = 1: IterationsExceeded everywhere, same as the oracle
+    cfg1, ocfg1 = _cfgs(oracle, 4, 0, max_iterations_per_level=1)
+    gcur = engine.pyramid(a["I_cur"], a["Z_cur"], a["K"], 5)
+    r = engine.match(gref, gcur, cfg1)
+    o = oracle.match(a["oref"], a["ocur"], ocfg1, oracle.mode("mirror"))
+    assert [l["termination"] for l in r.levels] == [l["termination"] for l in o["levels"]] == [0] * 5
+    dt, dr = pose_delta(o["T"], r.transformation)
+    assert dt < 1e-5 and dr < 1e-5
+    # (4) argument errors are status codes, not crashes
+    with pytest.raises(RuntimeError):
+        engine.match(gref, gcur, _cfgs(oracle, 6, 0)[0])       # pyramid has 5 levels
+    with pytest.raises(RuntimeError):
+        engine.match(gref, gcur, _cfgs(oracle, 1, 3)[0])       # FirstLevel < LastLevel (Config::IsSane)
+
+
+def test_statistical_agreement_on_a_batch(engine, oracle):
+    """24 seeded 640x480 pairs: every pose within tolerance of FAITHFUL; control flow identical to
+    MIRROR for the large majority (an accept test decided by fp32 summation order may flip)."""
+    from dvo_slam_b200 import synth
+    cfg, ocfg = _cfgs(oracle, 4, 0)
+    n = 24
+    pairs = [synth.make_pair(100 + s) for s in range(n)]
+    K = pairs[0]["intrinsics"]
+    Ir, Zr = np.stack([p["I_ref"].numpy() for p in pairs]), np.stack([p["Z_ref"].numpy() for p in pairs])
+    Ic, Zc = np.stack([p["I_cur"].numpy() for p in pairs]), np.stack([p["Z_cur"].numpy() for p in pairs])
+    res = engine.match_batch(engine.pyramid_batch(Ir, Zr, K, 5), engine.pyramid_batch(Ic, Zc, K, 5), cfg)
+    same = 0
+    for i in range(n):
+        oref, ocur = oracle.Pyramid(Ir[i], Zr[i], K, 5), oracle.Pyramid(Ic[i], Zc[i], K, 5)
+        fa = oracle.match(oref, ocur, ocfg, oracle.mode("faithful"))
+        mi = oracle.match(oref, ocur, ocfg, oracle.mode("mirror"))
+        dt, dr = pose_delta(fa["T"], res[i].transformation)
+        assert dt < POSE_TOL_T and dr < POSE_TOL_R, (i, dt, dr)
+        if [l["num_iterations"] for l in res[i].levels] == [l["num_iterations"] for l in mi["levels"]]:
+            same += 1
+            dt, dr = pose_delta(mi["T"], res[i].transformation)
+            assert dt < 1e-5 and dr < 1e-5
+    assert same >= int(0.7 * n), same
+
+
+def test_full_size_properties_without_oracle(engine):
+    """BASELINE.json full sizes through size-independent properties: a 64-pair batch where pairs i and
+    i+32 are the same inputs must agree bit for bit, every result is finite and close to ground truth."""
+    from dvo_slam_b200 import synth
+    from dvo_slam_b200.engine import Config
+    cfg = Config(first_level=4, last_level=0, max_iterations_per_level=50, precision=1e-4)
+    pairs = [synth.make_pair(500 + s) for s in range(32)]
+    K = pairs[0]["intrinsics"]
+    Ir = np.stack([p["I_ref"].numpy() for p in pairs] * 2); Zr = np.stack([p["Z_ref"].numpy() for p in pairs] * 2)
+    Ic = np.stack([p["I_cur"].numpy() for p in pairs] * 2); Zc = np.stack([p["Z_cur"].numpy() for p in pairs] * 2)
+    res = engine.match_batch(engine.pyramid_batch(Ir, Zr, K, 5), engine.pyramid_batch(Ic, Zc, K, 5), cfg)
+    for i in range(32):
+        assert np.array_equal(res[i].transformation, res[i + 32].transformation)
+        assert np.array_equal(res[i].information, res[i + 32].information)
+        assert not res[i].is_nan()
+        dt, dr = pose_delta(np.linalg.inv(pairs[i]["T_true"]), res[i].transformation)
+        assert dt < 4e-3 and dr < 1.5e-3, (i, dt, dr)
+        assert np.allclose(res[i].information, res[i].information.T)
+        assert np.linalg.eigvalsh(res[i].information).min() > 0

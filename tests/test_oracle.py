@@ -1,0 +1,176 @@
+"""CPU tests of the oracle (test infrastructure) against its committed fixtures, closed-form
+identities and analytic ground truth.  The reference has no tests or goldens:
+"parity unpinned" -- these pin the oracle itself."""
+import numpy as np
+import pytest
+
+from helpers import GOLDEN_LEVELS, GOLDEN_SEEDS, POSE_TOL_R, POSE_TOL_T, golden_images, load_golden, pose_delta
+
+
+def _pyramids(orc, g):
+    im = golden_images(g, orc)
+    return (orc.Pyramid(im["I_ref"], im["Z_ref"], g["K"], GOLDEN_LEVELS),
+            orc.Pyramid(im["I_cur"], im["Z_cur"], g["K"], GOLDEN_LEVELS))
+
+
+def _cfg(orc, **kw):
+    base = dict(first_level=2, last_level=0, max_iterations_per_level=50, precision=1e-4)
+    base.update(kw)
+    return orc.config(**base)
+
+
+def test_se3_exp_log_roundtrip(oracle):
+    rng = np.random.default_rng(0)
+    for _ in range(50):
+        xi = np.concatenate([rng.uniform(-0.5, 0.5, 3), rng.uniform(-1.0, 1.0, 3)])
+        T = oracle.se3_exp(xi)
+        assert np.allclose(T[:3, :3] @ T[:3, :3].T, np.eye(3), atol=1e-14)
+        assert np.allclose(oracle.se3_log(T), xi, atol=1e-12)
+    assert np.allclose(oracle.se3_exp(np.zeros(6)), np.eye(4))
+    small = np.array([1e-3, -2e-3, 5e-4, 1e-12, -2e-12, 3e-12])
+    assert np.allclose(oracle.se3_log(oracle.se3_exp(small)), small, atol=1e-15)
+
+
+def test_ldlt_solve(oracle):
+    rng = np.random.default_rng(1)
+    for _ in range(20):
+        M = rng.standard_normal((40, 6)) * rng.uniform(0.1, 100, 6)
+        A = M.T @ M
+        b = rng.standard_normal(6)
+        x = oracle.ldlt_solve6(A, b)
+        assert np.allclose(A @ x, b, rtol=1e-8, atol=1e-8 * np.abs(b).max())
+
+
+def test_convert_raw_depth(oracle):
+    raw = np.array([[0, 5000, 1], [65535, 0, 12345]], dtype=np.uint16)
+    out = oracle.convert_raw_depth(raw, 1.0 / 5000.0)
+    assert np.isnan(out[0, 0]) and np.isnan(out[1, 1])
+    assert out[0, 1] == np.float32(5000) * np.float32(1.0 / 5000.0)
+    assert out[1, 2] == np.float32(12345) * np.float32(1.0 / 5000.0)
+
+
+@pytest.mark.parametrize("seed", GOLDEN_SEEDS)
+def test_pyramid_checksums_and_selection(oracle, seed):
+    g = load_golden(seed)
+    ref, _ = _pyramids(oracle, g)
+    for lvl in range(GOLDEN_LEVELS):
+        pl = ref.planes(lvl)
+        sums = np.array([np.nansum(pl[c].astype(np.float64)) for c in range(6)])
+        nans = np.array([int(np.isnan(pl[c]).sum()) for c in range(6)])
+        assert np.array_equal(nans, g[f"pyr_l{lvl}_nan"])
+        assert np.allclose(sums, g[f"pyr_l{lvl}_sum"], rtol=0, atol=0)
+        assert oracle.select(ref, lvl)[0] == int(g[f"sel_l{lvl}"])
+    # level geometry: K scaled as a whole by 0.5 per level (intrinsic_matrix.cpp:90-93)
+    w, h, K = ref.level_info(1)
+    assert (w, h) == (80, 60) and np.allclose(K, np.array(g["K"]) * 0.5)
+
+
+@pytest.mark.parametrize("seed", GOLDEN_SEEDS)
+@pytest.mark.parametrize("mname", ["mirror", "exact"])
+def test_match_reproduces_golden_ieee_modes(oracle, seed, mname):
+    """MIRROR / EXACT use only IEEE operations: outputs must reproduce the fixture exactly."""
+    g = load_golden(seed)
+    ref, cur = _pyramids(oracle, g)
+    r = oracle.match(ref, cur, _cfg(oracle), oracle.mode(mname))
+    lv = np.array([[l["id"], l["termination"], l["valid_pixels"], l["num_iterations"]] for l in r["levels"]])
+    assert np.array_equal(lv, g[f"{mname}_levels"])
+    assert np.array_equal(np.array([it["n"] for it in r["iterations"]]), g[f"{mname}_iter_n"])
+    assert np.allclose(r["T"], g[f"{mname}_T"], atol=1e-12)
+    assert np.allclose(r["information"], g[f"{mname}_information"], rtol=1e-9)
+    assert np.allclose([it["nll"] for it in r["iterations"]], g[f"{mname}_iter_nll"], rtol=1e-12)
+
+
+@pytest.mark.parametrize("seed", GOLDEN_SEEDS)
+def test_match_faithful_within_tolerance_of_golden(oracle, seed):
+    """FAITHFUL uses _mm_rcp_ps whose value is CPU-vendor specific: tolerance, not equality."""
+    g = load_golden(seed)
+    ref, cur = _pyramids(oracle, g)
+    r = oracle.match(ref, cur, _cfg(oracle), oracle.mode("faithful"))
+    dt, dr = pose_delta(g["faithful_T"], r["T"])
+    assert dt < 4 * POSE_TOL_T and dr < 4 * POSE_TOL_R
+    assert [l["valid_pixels"] for l in r["levels"]] == g["faithful_levels"][:, 2].tolist()
+
+
+@pytest.mark.parametrize("seed", GOLDEN_SEEDS)
+def test_all_modes_recover_ground_truth_and_agree(oracle, seed):
+    g = load_golden(seed)
+    ref, cur = _pyramids(oracle, g)
+    Ts = {}
+    for mname in ("faithful", "exact", "mirror"):
+        r = oracle.match(ref, cur, _cfg(oracle), oracle.mode(mname))
+        Ts[mname] = r["T"]
+        # Result.Transformation = estimate^-1 = inv(T_true) (dense_tracking.cpp:371); 160x120 quantised scene
+        dt, dr = pose_delta(np.linalg.inv(g["T_true"]), r["T"])
+        assert dt < 6e-3 and dr < 3e-3, (mname, dt, dr)
+    for a in ("exact", "mirror"):
+        dt, dr = pose_delta(Ts["faithful"], Ts[a])
+        assert dt < 4 * POSE_TOL_T and dr < 4 * POSE_TOL_R, (a, dt, dr)   # 160x120: pixels 4x coarser than 640x480
+
+
+@pytest.mark.parametrize("seed", GOLDEN_SEEDS)
+def test_linearize_kats(oracle, seed):
+    g = load_golden(seed)
+    ref, cur = _pyramids(oracle, g)
+    for lvl in range(GOLDEN_LEVELS):
+        for uw in (0, 1):
+            lin = oracle.linearize(ref, cur, lvl, g["kat_T"], oracle.mode("mirror"), bool(uw), g["kat_prev_precision"])
+            key = f"kat_mirror_l{lvl}_w{uw}"
+            assert lin["n"] == int(g[key + "_n"])
+            assert np.array_equal(lin["precision"], g[key + "_P"])
+            assert lin["ll"] == float(g[key + "_ll"])
+            assert np.allclose(lin["A"], g[key + "_A"], rtol=1e-12) and np.allclose(lin["b"], g[key + "_b"], rtol=1e-12)
+            # FAITHFUL differs from MIRROR only by numerical noise at a fixed linearisation point
+            fa = oracle.linearize(ref, cur, lvl, g["kat_T"], oracle.mode("faithful"), bool(uw), g["kat_prev_precision"])
+            assert abs(fa["n"] - lin["n"]) <= max(3, lin["n"] // 200)
+            # (no comparison of P or A between FAITHFUL and MIRROR: the bugged pairwise scale sum uses only
+            # the pair leaders, so one extra/missing valid point -- or the 0.2 px rcp jitter on a heavy-tailed
+            # residual -- changes P by 5 % .. 4x at a fixed transform; the two are compared at the pose level)
+
+
+def test_scale_pair_bug_is_structural(oracle):
+    """computeScaleSse's pair bug (dense_tracking_impl.cpp:614-615) changes Result.Information by far
+    more than numerical noise does; the GPU path must reproduce it (MIRROR keeps it on)."""
+    ratios = []
+    for seed in GOLDEN_SEEDS:
+        g = load_golden(seed)
+        ref, cur = _pyramids(oracle, g)
+        m = oracle.mode("mirror")
+        m.scale_pair_bug = 0
+        off = oracle.match(ref, cur, _cfg(oracle), m)
+        ratios.append(off["information"][0, 0] / g["mirror_information"][0, 0])
+    assert max(ratios) > 3.0, ratios
+
+
+def test_identical_frames_give_identity(oracle):
+    g = load_golden(12)
+    im = golden_images(g, oracle)
+    a = oracle.Pyramid(im["I_ref"], im["Z_ref"], g["K"], GOLDEN_LEVELS)
+    b = oracle.Pyramid(im["I_ref"], im["Z_ref"], g["K"], GOLDEN_LEVELS)
+    r = oracle.match(a, b, _cfg(oracle), oracle.mode("faithful"))
+    dt, dr = pose_delta(np.eye(4), r["T"])
+    assert dt < 1e-5 and dr < 1e-5
+
+
+def test_too_few_constraints_gives_nan_information(oracle):
+    g = load_golden(12)
+    im = golden_images(g, oracle)
+    Z = np.full_like(im["Z_cur"], np.nan)
+    a = oracle.Pyramid(im["I_ref"], im["Z_ref"], g["K"], GOLDEN_LEVELS)
+    b = oracle.Pyramid(im["I_cur"], Z, g["K"], GOLDEN_LEVELS)
+    r = oracle.match(a, b, _cfg(oracle), oracle.mode("faithful"))
+    # n < 6 breaks the loop with TooFewConstraints, but x = log(inc) = 0 <= Precision, so the post-loop
+    # check overwrites it with IncrementTooSmall (dense_tracking.cpp:276-284, 359-360)
+    assert all(l["termination"] == 1 and l["num_iterations"] == 1 for l in r["levels"])
+    assert all(it["n"] == 0 for it in r["iterations"])
+    assert np.isnan(r["information"]).all()                          # defined behaviour for SURVEY Q24
+    assert np.allclose(r["T"], np.eye(4))                            # every increment reverted
+
+
+def test_initial_estimate_and_mu(oracle):
+    g = load_golden(13)
+    ref, cur = _pyramids(oracle, g)
+    T0 = np.linalg.inv(g["faithful_T"])   # input guess is reference->current
+    r = oracle.match(ref, cur, _cfg(oracle, use_initial_estimate=1, mu=0.05), oracle.mode("faithful"), T_init=T0)
+    dt, dr = pose_delta(g["faithful_T"], r["T"])
+    assert dt < 4 * POSE_TOL_T and dr < 4 * POSE_TOL_R
+    assert all(np.isfinite(it["prior"]) for it in r["iterations"])
