@@ -57,38 +57,55 @@ def parse_args():
 # clocks sampling (B200_PROFILING.md recipe)
 # ---------------------------------------------------------------------------------------------
 class ClockSampler:
+    """Polls nvidia-smi every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
     def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.stop_flag, self.thread = index, [], threading.Event(), None
+
+    def _loop(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.splitlines()[0].split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
 
     def start(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+        self.thread = threading.Thread(target=self._loop, daemon=True)
+        self.thread.start()
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        sm, mx, reasons = [], [], set()
+        self.stop_flag.set()
+        if self.thread:
+            self.thread.join(timeout=10)
+        sm, mx, pw, reasons = [], [], [], set()
         for r in self.rows:
             try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
+                sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
             except Exception:
                 continue
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def usable_cores() -> int:
+    """Host threads this process may really use: min(visible CPUs, cgroup CPU quota)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except Exception:
+        pass
+    return n
 
 
 # ---------------------------------------------------------------------------------------------
@@ -142,7 +159,7 @@ def run_reference(args, rank, world):
     """Reference arm: the reference's CPU algorithm on the host cores (oracle FAITHFUL port)."""
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     per_step = args.cpu_sample or max(cores, min(4 * cores, 64))
     dev = "cpu"
     try:
@@ -306,7 +323,7 @@ def run_ours(args, rank, local_rank, world):
     # ---- CPU baseline: oracle FAITHFUL, match only, bounded sample (rank 0, N=1 only) ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
+        cores = usable_cores()
         nsample = args.cpu_sample or max(cores, min(4 * cores, 64))
         hp = [{"I_ref": hI[i].numpy(), "Z_ref": hZ[i].numpy(), "I_cur": hI[B + i].numpy(), "Z_cur": hZ[B + i].numpy(),
                "intrinsics": K} for i in range(min(nsample, B))]

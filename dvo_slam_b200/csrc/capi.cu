@@ -100,7 +100,7 @@ int dvo_b200_destroy(dvo_b200_ctx* ctx) {
   for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
   Workspace& ws = ctx->ws;
   cudaFree(ws.d_pair_level); cudaFree(ws.d_state); cudaFree(ws.d_records); cudaFree(ws.d_scale_export);
-  cudaFree(ws.d_tile_base); cudaFree(ws.d_normal_partial); cudaFree(ws.d_active); cudaFree(ws.d_iter_log);
+  cudaFree(ws.d_tile_base); cudaFree(ws.d_normal_partial); cudaFree(ws.d_active); cudaFree(ws.d_iter_log); cudaFree(ws.d_squads);
   if (ws.h_active) cudaFreeHost(ws.h_active);
   for (auto& kv : ctx->free_slabs) { cudaFree(kv.second->base); if (kv.second->ready) cudaEventDestroy(kv.second->ready); delete kv.second; }
   cudaFree(ctx->d_stage);

@@ -124,13 +124,15 @@ struct Workspace {              // per-ctx scratch for a lock-step batch
   int* d_active = nullptr;           // number of pairs still active on the level
   dvo_b200_iteration_stats* d_iter_log = nullptr;
   int* h_active = nullptr;           // pinned
-  size_t cap_pairs = 0, cap_records = 0, cap_tiles = 0, cap_iter_log = 0;
+  char* d_squads = nullptr;          // persistent kernel: SquadState[nsquads] + {queue head, error flag}
+  size_t cap_pairs = 0, cap_records = 0, cap_export = 0, cap_segbase = 0, cap_partial = 0, cap_squads = 0, cap_iter_log = 0;
 };
 
 }  // namespace dvo_b200
 
 struct dvo_b200_ctx {
   int device = 0;
+  int num_sms = 0, ctas_per_sm = 0;   // persistent-kernel grid geometry (queried once)
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   std::string last_error;

@@ -1,0 +1,456 @@
+// stages.cuh -- the two data-parallel stages of one Gauss-Newton iteration of
+// dvo::DenseTracker::match() as warp-level device functions (used by every kernel in tracker.cu).
+//
+//   stage A (stage_a_segment): computeResidualsSse + computeWeightsSse + computeScaleSse
+//                              (dense_tracking_impl.cpp:133-393, 657-707, 590-638)
+//   stage B (stage_b_segment): computeCompleteDataLogLikelihood + Jacobians + normal equations
+//                              (dense_tracking_impl.cpp:406-425, dense_tracking.cpp:333-342, 448-476,
+//                               least_squares.cpp:58-64)
+//
+// A warp owns a contiguous run of pixels (a "segment", row-major order) and walks it 32 pixels at a
+// time.  All arithmetic that decides validity is explicit round-to-nearest fp32 in a fixed order
+// (packed f32x2 where two channels share an operation), mirrored bit for bit by the oracle's MIRROR
+// mode; sums use whatever contraction the compiler picks.
+#pragma once
+#include "common.cuh"
+#include "f32x2.cuh"
+
+namespace dvo_b200 {
+
+constexpr unsigned kFullMask = 0xffffffffu;
+constexpr int kSegmentPixels = 256;     // pixels per warp segment (8 rounds of 32)
+constexpr int kSegmentsPerTile = 4;     // a 128-thread CTA covers 4 consecutive segments = 1024 pixels
+
+// record planes of one pair at one level (scratch): E = (e.i, e.z), G = (e.idx, e.idy), H = (e.zdx, e.zdy), W = weight
+struct RecordPlanes {
+  float2* E; float2* G; float2* H; float* W;
+};
+__host__ __device__ __forceinline__ RecordPlanes record_planes(float* base, size_t n) {
+  RecordPlanes r;
+  r.E = reinterpret_cast<float2*>(base);
+  r.G = r.E + n;
+  r.H = r.G + n;
+  r.W = reinterpret_cast<float*>(r.H + n);
+  return r;
+}
+constexpr int kRecordFloatsPerPixel = 7;
+
+// ---- per pair-iteration constants ---------------------------------------------------------------
+struct StageConsts {
+  f2 k0, k1, k2, k3;          // (kt[0],kt[4]) (kt[1],kt[5]) (kt[2],kt[6]) (kt[3],kt[7]): rows X and Y of K*T
+  float k8, k9, k10, k11;     // row Z
+  f2 Pa, Pb;                  // precision used for the weights: (P00,P01), (P10,P11)
+  f2 cg, fxy;                 // (0.5 fx/255, 0.5 fy/255), (fx, fy)   (dense_tracking.cpp:215-220)
+  float c_i, ubx, uby;
+  int first_iteration;
+  int drop_idx;               // linear index of the odd selected point that is skipped, or -1
+};
+
+__device__ __forceinline__ void load_stage_consts(const PairState& st, const PairLevel& pl, int w, int h, StageConsts& c) {
+  // PairState is rewritten between stages by another SM (persistent kernel): read it through L2 (ld.cg)
+  float kt[12], P[4];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) kt[i] = __ldcg(&st.kt[i]);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) P[i] = __ldcg(&st.precision[i]);
+  c.k0 = pk(kt[0], kt[4]); c.k1 = pk(kt[1], kt[5]); c.k2 = pk(kt[2], kt[6]); c.k3 = pk(kt[3], kt[7]);
+  c.k8 = kt[8]; c.k9 = kt[9]; c.k10 = kt[10]; c.k11 = kt[11];
+  c.Pa = pk(P[0], P[1]); c.Pb = pk(P[2], P[3]);
+  c.cg = pk(__fdiv_rn(__fmul_rn(0.5f, pl.cfx), 255.0f), __fdiv_rn(__fmul_rn(0.5f, pl.cfy), 255.0f));
+  c.fxy = pk(pl.cfx, pl.cfy);
+  c.c_i = 1.0f / 255.0f;
+  c.ubx = (float)(w - 2); c.uby = (float)(h - 2);
+  c.first_iteration = __ldcg(&st.iteration) == 0;
+  int S = pl.rsel[0];
+  c.drop_idx = (S & 1) ? pl.rsel[1] : -1;   // odd S: last selected point skipped (dense_tracking_impl.cpp:169)
+}
+
+// Reference-side inputs of one pixel, loaded one round ahead of their use.
+struct RefPixel {
+  f2 a;        // (I_r, Z_r)
+  f2 g;        // (Ix_r, Iy_r)
+  float tx, ty;
+};
+
+__device__ __forceinline__ RefPixel load_ref_pixel(const PairLevel& pl, int idx, int w, unsigned wmagic, int n) {
+  RefPixel r;
+  const int i = min(idx, n - 1);                   // lanes past the end of the image read a valid address
+  r.a = ldg_f2(pl.r0 + i);
+  r.g = ldg_f2(pl.r1 + i);
+  const int y = (int)__umulhi((unsigned)i, wmagic);   // i / w (exact for i*w < 2^32)
+  const int x = i - y * w;
+  r.tx = __ldg(pl.rtmpl + x);
+  r.ty = __ldg(pl.rtmpl + w + y);
+  return r;
+}
+
+// The residual record of one reference pixel (computeResidualsSse, dense_tracking_impl.cpp:133-393):
+//   point (x,y,z) = (tx*z, ty*z, z); (X,Y,Z') = fma chains over the rows of K*T; (u,v) = (X,Y)*rcp_rn(Z')
+//   bounds 0<=u<=w-2, 0<=v<=h-2; truncation; bilinear blend of the six channels (three float2 planes)
+//   residual weights of dense_tracking.cpp:215-220; occlusion test of line 275.
+// Branch-free: every lane issues its twelve tap loads at once (a rejected point reads tap 0), the
+// verdict is returned.  E = (e.i, e.z), G = (e.idx, e.idy), H = (e.zdx, e.zdy).
+__device__ __forceinline__ bool pixel_record(const RefPixel& r, bool selected, int w, const PairLevel& pl, const StageConsts& c,
+                                             f2& E, f2& G, f2& H) {
+  const float z = hi(r.a);
+  const f2 pxy = mul2(pk(r.tx, r.ty), bc(z));
+  const float px = lo(pxy), py = hi(pxy);
+  const f2 XY = fma2(c.k0, bc(px), fma2(c.k1, bc(py), fma2(c.k2, bc(z), c.k3)));
+  const float Zt = __fmaf_rn(c.k8, px, __fmaf_rn(c.k9, py, __fmaf_rn(c.k10, z, c.k11)));
+  f2 uv = mul2(XY, bc(rcp_rn(Zt)));
+  const float u = lo(uv), v = hi(uv);
+  const bool inb = selected && u >= 0.f && u <= c.ubx && v >= 0.f && v <= c.uby;   // NaN compares false
+  uv = inb ? uv : 0ull;
+  // truncation without conversions: for 0 <= t < 2^23, RZ(t + 2^23) carries floor(t) in its mantissa
+  const f2 t = add2_rz(uv, bc(8388608.0f));
+  const f2 f = sub2(uv, sub2(t, bc(8388608.0f)));   // (fu, fv)
+  const f2 gq = sub2(bc(1.0f), f);                   // (gu, gv)
+  const int u0 = __float_as_int(lo(t)) - 0x4b000000, v0 = __float_as_int(hi(t)) - 0x4b000000;
+  const float fu = lo(f), fv = hi(f), gu = lo(gq), gv = hi(gq);
+  const int b = v0 * w + u0;
+  const f2 p00 = ldg_f2(pl.c0 + b), p10 = ldg_f2(pl.c0 + b + 1), p01 = ldg_f2(pl.c0 + b + w), p11 = ldg_f2(pl.c0 + b + w + 1);
+  const f2 q00 = ldg_f2(pl.c1 + b), q10 = ldg_f2(pl.c1 + b + 1), q01 = ldg_f2(pl.c1 + b + w), q11 = ldg_f2(pl.c1 + b + w + 1);
+  const f2 s00 = ldg_f2(pl.c2 + b), s10 = ldg_f2(pl.c2 + b + 1), s01 = ldg_f2(pl.c2 + b + w), s11 = ldg_f2(pl.c2 + b + w + 1);
+#define DVO_BLEND2(c00, c10, c01, c11) \
+  fma2(bc(fv), fma2(bc(fu), c11, mul2(bc(gu), c01)), mul2(bc(gv), fma2(bc(fu), c10, mul2(bc(gu), c00))))
+  const f2 IZ = DVO_BLEND2(p00, p10, p01, p11);
+  const f2 Gc = DVO_BLEND2(q00, q10, q01, q11);
+  const f2 Hc = DVO_BLEND2(s00, s10, s01, s11);
+#undef DVO_BLEND2
+  const float Zc = hi(IZ);
+  const float ez = __fsub_rn(Zc, Zt);
+  const float s = __fsub_rn(z, 0.4f);
+  const float sig = __fmaf_rn(__fmul_rn(0.0019f, s), s, 0.0012f);    // depthStdDevZ (lines 122-128)
+  const float ei = __fmaf_rn(c.c_i, lo(IZ), __fmul_rn(-c.c_i, lo(r.a)));
+  E = pk(ei, ez);
+  G = fma2(c.cg, Gc, mul2(c.cg, r.g));
+  H = mul2(c.fxy, Hc);
+  // masked depth NaN = any NaN lane of the reference's 8-vector (line 261); occlusion test (line 275)
+  return inb && Zc == Zc && ez > __fmul_rn(-20.0f, sig);
+}
+
+// ---- pairwise scale sum ---------------------------------------------------------------------------
+// computeScaleSse (dense_tracking_impl.cpp:590-638) walks the compacted residual list two at a time
+// and, because lines 614-615 re-use the low half of the register, adds (w_{2j} + w_{2j+1}) r_{2j} r_{2j}^T
+// for every pair plus w_n r_n r_n^T for an odd tail.  That needs, per valid point, the parity of its
+// rank in row-major order and the weight of the next valid point.  A contiguous run of pixels is
+// summarised by a segment record: the sums under both hypotheses for the parity of its first point
+// (S0: the first valid point is a pair leader, S1: it is a follower), its first valid weight and its
+// last valid point (a leader whose partner lies in the next run).  Runs combine associatively.
+template <typename T>
+struct SegT {
+  long long n;
+  T S0[3], S1[3];
+  T wf, wl, ol[3];
+};
+
+template <typename T, typename A, typename B>
+__host__ __device__ __forceinline__ SegT<T> combine_seg(const A& a, const B& b) {
+  SegT<T> r;
+  r.n = (long long)a.n + (long long)b.n;
+  int hb0 = (int)(a.n & 1), hb1 = (int)((a.n + 1) & 1);
+  bool link0 = a.n > 0 && b.n > 0 && (((a.n - 1) & 1) == 0);   // hypothesis 0: last point of a is a leader
+  bool link1 = a.n > 0 && b.n > 0 && ((a.n & 1) == 0);         // hypothesis 1
+  for (int k = 0; k < 3; ++k) {
+    T bs0 = hb0 ? (T)b.S1[k] : (T)b.S0[k];
+    T bs1 = hb1 ? (T)b.S1[k] : (T)b.S0[k];
+    r.S0[k] = (T)a.S0[k] + bs0 + (link0 ? ((T)a.wl + (T)b.wf) * (T)a.ol[k] : (T)0);
+    r.S1[k] = (T)a.S1[k] + bs1 + (link1 ? ((T)a.wl + (T)b.wf) * (T)a.ol[k] : (T)0);
+  }
+  r.wf = a.n > 0 ? (T)a.wf : (T)b.wf;
+  if (b.n > 0) { r.wl = (T)b.wl; for (int k = 0; k < 3; ++k) r.ol[k] = (T)b.ol[k]; }
+  else         { r.wl = (T)a.wl; for (int k = 0; k < 3; ++k) r.ol[k] = (T)a.ol[k]; }
+  return r;
+}
+
+constexpr int kSegExportFloats = 12;   // n (as int bits), S0[3], S1[3], wf, wl, ol[3]
+constexpr int kCtaExportFloats = 16;   // the CTA's four warp summaries combined (12) + the four warp counts (int bits)
+
+__device__ __forceinline__ SegT<double> load_seg_export(const float* e) {
+  SegT<double> s;
+  // written by other SMs in the same kernel (persistent path): read through L2
+  float v[kSegExportFloats];
+#pragma unroll
+  for (int i = 0; i < kSegExportFloats; ++i) v[i] = __ldcg(e + i);
+  s.n = __float_as_int(v[0]);
+  s.S0[0] = v[1]; s.S0[1] = v[2]; s.S0[2] = v[3];
+  s.S1[0] = v[4]; s.S1[1] = v[5]; s.S1[2] = v[6];
+  s.wf = v[7]; s.wl = v[8]; s.ol[0] = v[9]; s.ol[1] = v[10]; s.ol[2] = v[11];
+  return s;
+}
+
+// Thread 0 of a CTA folds the four warp summaries (shared memory, in pixel order) into one CTA export.
+__device__ __forceinline__ void cta_export_segments(const float (*sm_exp)[kSegExportFloats], float* out) {
+  SegT<float> acc;
+  {
+    const float* e = sm_exp[0];
+    acc.n = __float_as_int(e[0]);
+    for (int k = 0; k < 3; ++k) { acc.S0[k] = e[1 + k]; acc.S1[k] = e[4 + k]; acc.ol[k] = e[9 + k]; }
+    acc.wf = e[7]; acc.wl = e[8];
+  }
+  for (int q = 1; q < kSegmentsPerTile; ++q) {
+    const float* e = sm_exp[q];
+    SegT<float> b;
+    b.n = __float_as_int(e[0]);
+    for (int k = 0; k < 3; ++k) { b.S0[k] = e[1 + k]; b.S1[k] = e[4 + k]; b.ol[k] = e[9 + k]; }
+    b.wf = e[7]; b.wl = e[8];
+    acc = combine_seg<float>(acc, b);
+  }
+  out[0] = __int_as_float((int)acc.n);
+  for (int k = 0; k < 3; ++k) { out[1 + k] = acc.S0[k]; out[4 + k] = acc.S1[k]; out[9 + k] = acc.ol[k]; }
+  out[7] = acc.wf; out[8] = acc.wl;
+  for (int q = 0; q < kSegmentsPerTile; ++q) out[12 + q] = sm_exp[q][0];
+}
+
+// Student-t weight of computeWeightsSse (dense_tracking_impl.cpp:657-707): w = 7 / (5 + r^T P r), nu = 5;
+// w = 1 on the first iteration of a level (dense_tracking.cpp:286-289).
+__device__ __forceinline__ float student_weight(const StageConsts& c, float ei, float ez) {
+  if (c.first_iteration) return 1.0f;
+  const f2 q = fma2(bc(ez), c.Pb, mul2(bc(ei), c.Pa));        // (ei P00 + ez P10, ei P01 + ez P11)
+  const float d = fmaf(lo(q), ei, hi(q) * ez);
+  return 7.0f * rcp_fast(5.0f + d);
+}
+
+__device__ __forceinline__ void store_record(const RecordPlanes& rec, int idx, int n, bool valid, f2 E, f2 G, f2 H, float wgt) {
+  if (idx < n) {
+    if (valid) {
+      rec.E[idx] = make_float2(lo(E), hi(E));
+      rec.G[idx] = make_float2(lo(G), hi(G));
+      rec.H[idx] = make_float2(lo(H), hi(H));
+      rec.W[idx] = wgt;
+    } else {
+      const float nanf_ = __int_as_float(0x7fc00000);
+      rec.E[idx] = make_float2(nanf_, nanf_);
+    }
+  }
+}
+
+// Stage A over the pixels [begin, end) of one pair (begin a multiple of 32): writes the residual
+// records and the segment summary (kSegExportFloats floats at `seg_out`).  The warp walks 64 pixels
+// per round, two per lane (base + lane and base + 32 + lane), with the reference-side loads of the
+// next round issued before the current round's taps are consumed.
+__device__ __forceinline__ void stage_a_segment(const PairLevel& pl, const StageConsts& c, int w, unsigned wmagic, int n,
+                                                int begin, int end, const RecordPlanes& rec, float* seg_out) {
+  const int lane = threadIdx.x & 31;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  float sall0 = 0.f, sall1 = 0.f, sall2 = 0.f, salt0 = 0.f, salt1 = 0.f, salt2 = 0.f;
+  // the last valid lane seen so far keeps its own point as "pending leader" until the next valid weight is known
+  bool pend = false;
+  float pw = 0.f, po0 = 0.f, po1 = 0.f, po2 = 0.f;
+  int psign = 0;
+  int cnt = 0;
+  float wfirst = 0.f;
+  if (begin < end) {
+    RefPixel r0 = load_ref_pixel(pl, begin + lane, w, wmagic, n);
+    RefPixel r1 = load_ref_pixel(pl, begin + 32 + lane, w, wmagic, n);
+    unsigned sel0 = __ldg(pl.rmask + (begin >> 5));
+    unsigned sel1 = begin + 32 < end ? __ldg(pl.rmask + (begin >> 5) + 1) : 0u;
+#pragma unroll 1
+    for (int base = begin; base < end; base += 64) {
+      const int i0 = base + lane, i1 = base + 32 + lane;
+      const RefPixel c0 = r0, c1 = r1;
+      const bool s0 = ((sel0 >> lane) & 1u) && i0 != c.drop_idx;
+      const bool s1 = ((sel1 >> lane) & 1u) && i1 != c.drop_idx;
+      const int nb = base + 64;
+      if (nb < end) {   // warp-uniform: prefetch the next round's reference data
+        r0 = load_ref_pixel(pl, nb + lane, w, wmagic, n);
+        r1 = load_ref_pixel(pl, nb + 32 + lane, w, wmagic, n);
+        sel0 = __ldg(pl.rmask + (nb >> 5));
+        sel1 = nb + 32 < end ? __ldg(pl.rmask + (nb >> 5) + 1) : 0u;
+      }
+      f2 E0, G0, H0, E1, G1, H1;
+      const bool v0 = pixel_record(c0, s0, w, pl, c, E0, G0, H0);
+      const bool v1 = pixel_record(c1, s1, w, pl, c, E1, G1, H1);
+      const float ei0 = lo(E0), ez0 = hi(E0), ei1 = lo(E1), ez1 = hi(E1);
+      const float w0 = student_weight(c, ei0, ez0), w1 = student_weight(c, ei1, ez1);
+      store_record(rec, i0, end, v0, E0, G0, H0, w0);   // end <= n: never touch another warp's pixels
+      store_record(rec, i1, end, v1, E1, G1, H1, w1);
+
+      // ---- pairwise scale sums over the 64 points of this round (bit i of m0 = pixel base+i, of m1 = base+32+i) ----
+      const unsigned m0 = __ballot_sync(kFullMask, v0), m1 = __ballot_sync(kFullMask, v1);
+      if (m0 | m1) {
+        const float w1_first = __shfl_sync(kFullMask, w1, m1 ? __ffs(m1) - 1 : 0);        // first valid weight of the upper half
+        const float w_first = m0 ? __shfl_sync(kFullMask, w0, __ffs(m0) - 1) : w1_first;   // first valid weight of the round
+        if (cnt == 0) wfirst = w_first;
+        // the pending leader of an earlier round pairs with the first valid point of this round
+        {
+          const float s = pend ? pw + w_first : 0.f;
+          const float sa = __int_as_float(__float_as_int(s) ^ psign);
+          sall0 = fmaf(s, po0, sall0); sall1 = fmaf(s, po1, sall1); sall2 = fmaf(s, po2, sall2);
+          salt0 = fmaf(sa, po0, salt0); salt1 = fmaf(sa, po1, salt1); salt2 = fmaf(sa, po2, salt2);
+        }
+        const unsigned above0 = (m0 >> lane) >> 1, above1 = (m1 >> lane) >> 1;
+        float wn0 = __shfl_sync(kFullMask, w0, above0 ? lane + __ffs(above0) : lane);
+        const float wn1 = __shfl_sync(kFullMask, w1, above1 ? lane + __ffs(above1) : lane);
+        wn0 = above0 ? wn0 : w1_first;
+        const bool next0 = above0 != 0u || m1 != 0u, next1 = above1 != 0u;
+        const int c0n = __popc(m0);
+        const int sg0 = ((cnt + __popc(m0 & lt_mask)) & 1) << 31;          // sign bit set for odd rank
+        const int sg1 = ((cnt + c0n + __popc(m1 & lt_mask)) & 1) << 31;
+        // rejected points carry garbage (possibly NaN) residuals: zero them so that 0 * outer stays 0
+        const float xi0 = v0 ? ei0 : 0.f, xz0 = v0 ? ez0 : 0.f, xi1 = v1 ? ei1 : 0.f, xz1 = v1 ? ez1 : 0.f;
+        const float a0 = xi0 * xi0, a1 = xi0 * xz0, a2 = xz0 * xz0;
+        const float b0 = xi1 * xi1, b1 = xi1 * xz1, b2 = xz1 * xz1;
+        {
+          const float s = (v0 && next0) ? w0 + wn0 : 0.f;
+          const float sa = __int_as_float(__float_as_int(s) ^ sg0);
+          sall0 = fmaf(s, a0, sall0); sall1 = fmaf(s, a1, sall1); sall2 = fmaf(s, a2, sall2);
+          salt0 = fmaf(sa, a0, salt0); salt1 = fmaf(sa, a1, salt1); salt2 = fmaf(sa, a2, salt2);
+        }
+        {
+          const float s = (v1 && next1) ? w1 + wn1 : 0.f;
+          const float sa = __int_as_float(__float_as_int(s) ^ sg1);
+          sall0 = fmaf(s, b0, sall0); sall1 = fmaf(s, b1, sall1); sall2 = fmaf(s, b2, sall2);
+          salt0 = fmaf(sa, b0, salt0); salt1 = fmaf(sa, b1, salt1); salt2 = fmaf(sa, b2, salt2);
+        }
+        // new pending leader: the last valid point of the round
+        const bool np1 = v1 && !next1, np0 = v0 && !next0;
+        pend = np0 || np1;
+        pw = np1 ? w1 : (np0 ? w0 : pw);
+        po0 = np1 ? b0 : (np0 ? a0 : po0); po1 = np1 ? b1 : (np0 ? a1 : po1); po2 = np1 ? b2 : (np0 ? a2 : po2);
+        psign = np1 ? sg1 : (np0 ? sg0 : psign);
+        cnt += c0n + __popc(m1);
+      }
+    }
+  }
+  // leaders at even local rank belong to hypothesis 0, odd to hypothesis 1: S0 = (all + alt)/2, S1 = (all - alt)/2
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    sall0 += __shfl_xor_sync(kFullMask, sall0, off); sall1 += __shfl_xor_sync(kFullMask, sall1, off);
+    sall2 += __shfl_xor_sync(kFullMask, sall2, off); salt0 += __shfl_xor_sync(kFullMask, salt0, off);
+    salt1 += __shfl_xor_sync(kFullMask, salt1, off); salt2 += __shfl_xor_sync(kFullMask, salt2, off);
+  }
+  if (lane == 0) {
+    seg_out[0] = __int_as_float(cnt);
+    seg_out[1] = 0.5f * (sall0 + salt0); seg_out[2] = 0.5f * (sall1 + salt1); seg_out[3] = 0.5f * (sall2 + salt2);
+    seg_out[4] = 0.5f * (sall0 - salt0); seg_out[5] = 0.5f * (sall1 - salt1); seg_out[6] = 0.5f * (sall2 - salt2);
+    seg_out[7] = wfirst;
+    if (cnt == 0) { seg_out[8] = 0.f; seg_out[9] = 0.f; seg_out[10] = 0.f; seg_out[11] = 0.f; }
+  }
+  if (pend) {   // exactly one lane when cnt > 0: the last valid point of the segment
+    seg_out[8] = pw; seg_out[9] = po0; seg_out[10] = po1; seg_out[11] = po2;
+  }
+}
+
+// ---- stage B -----------------------------------------------------------------------------------------
+struct StageBConsts {
+  float P00, P01, P10, P11;   // P_k
+  float l, wd0, wd1;          // P_k = [1 l; 0 1]^T-style factors, see stage_b_segment
+};
+
+constexpr int kNormalValues = 28;   // log-likelihood sum, 21 upper-triangular A (row-major), 6 b
+
+// Accumulators of stage B for one thread.  A is kept as pairs of adjacent columns of one row
+// (A[r][2c], A[r][2c+1]); rows 1, 3 and 5 carry one redundant lower-triangle entry so that every
+// update is a packed FMA of a broadcast row factor with a column pair.
+struct StageBAcc {
+  f2 r0[3], r1[3], r2[2], r3[2], r4, r5;   // 12 pairs
+  f2 b[3];
+  float prod;      // running product of (1 + 0.2 r^T P r) over this thread's kept points
+  float llsum;     // sum of logs flushed so far
+};
+
+__device__ __forceinline__ void stage_b_init(StageBAcc& a) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { a.r0[i] = 0; a.r1[i] = 0; a.b[i] = 0; }
+  a.r2[0] = a.r2[1] = a.r3[0] = a.r3[1] = a.r4 = a.r5 = 0;
+  a.prod = 1.0f; a.llsum = 0.f;
+}
+
+// A += u v^T (upper triangle, column pairs) and b += u * s for one 6-vector given as three pairs V,
+// with u = V * wd.
+__device__ __forceinline__ void stage_b_rank1(StageBAcc& acc, const f2 V[3], float wd, float s) {
+  const f2 U0 = mul2(V[0], bc(wd)), U1 = mul2(V[1], bc(wd)), U2 = mul2(V[2], bc(wd));
+  const float u0 = lo(U0), u1 = hi(U0), u2 = lo(U1), u3 = hi(U1), u4 = lo(U2), u5 = hi(U2);
+  acc.r0[0] = fma2(bc(u0), V[0], acc.r0[0]); acc.r0[1] = fma2(bc(u0), V[1], acc.r0[1]); acc.r0[2] = fma2(bc(u0), V[2], acc.r0[2]);
+  acc.r1[0] = fma2(bc(u1), V[0], acc.r1[0]); acc.r1[1] = fma2(bc(u1), V[1], acc.r1[1]); acc.r1[2] = fma2(bc(u1), V[2], acc.r1[2]);
+  acc.r2[0] = fma2(bc(u2), V[1], acc.r2[0]); acc.r2[1] = fma2(bc(u2), V[2], acc.r2[1]);
+  acc.r3[0] = fma2(bc(u3), V[1], acc.r3[0]); acc.r3[1] = fma2(bc(u3), V[2], acc.r3[1]);
+  acc.r4 = fma2(bc(u4), V[2], acc.r4);
+  acc.r5 = fma2(bc(u5), V[2], acc.r5);
+  acc.b[0] = fma2(U0, bc(s), acc.b[0]); acc.b[1] = fma2(U1, bc(s), acc.b[1]); acc.b[2] = fma2(U2, bc(s), acc.b[2]);
+}
+
+// Stage B over the pixels [begin, end): log-likelihood terms and normal equations with W = w * P_k.
+// rank_base: number of valid points before `begin` in row-major order; points with rank >= n_keep are
+// the dropped tail of computeCompleteDataLogLikelihood (dense_tracking_impl.cpp:413-422).
+//
+// With l = P01/P00, d0 = P00, d1 = P11 - P01^2/P00:
+//   J^T P J = d0 j0' j0'^T + d1 J1 J1^T,  j0' = J0 + l J1,     J^T P r = d0 j0' (r0 + l r1) + d1 J1 r1
+// so each point contributes two rank-1 updates.  J rows at the untransformed reference point
+// (dense_tracking.cpp:448-476): J0 = gx a + gy b, J1 = hx a + hy b - c with
+//   a = [1/z, 0, -x/z^2, a2 y, 1 - a2 x, -y/z], b = [0, 1/z, -y/z^2, b2 y - 1, -a3, x/z], c = [0, 0, 1, y, -x, 0].
+__device__ __forceinline__ void stage_b_segment(const PairLevel& pl, const StageBConsts& c, int w, unsigned wmagic, int n,
+                                                int begin, int end, const RecordPlanes& rec, long long rank_base,
+                                                long long n_keep, bool need_rank, StageBAcc& acc) {
+  const int lane = threadIdx.x & 31;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  int seen = 0;
+#pragma unroll 2
+  for (int base = begin; base < end; base += 32) {
+    const int idx = base + lane;
+    float2 e = idx < n ? rec.E[idx] : make_float2(__int_as_float(0x7fc00000), 0.f);
+    const bool valid = e.x == e.x;
+    bool keep = valid;
+    if (need_rank) {   // warp-uniform: only the segments that contain the tail of the point list
+      const unsigned m = __ballot_sync(kFullMask, valid);
+      keep = valid && (rank_base + seen + __popc(m & lt_mask)) < n_keep;
+      seen += __popc(m);
+    }
+    if (!valid) continue;
+    const float2 g2 = rec.G[idx], h2 = rec.H[idx];
+    const float wgt = rec.W[idx];
+    const float ei = e.x, ez = e.y;
+    // log-likelihood term: log(1 + 0.2 r^T P r), accumulated as a product
+    const float d = (ei * c.P00 + ez * c.P10) * ei + (ei * c.P01 + ez * c.P11) * ez;
+    if (keep) {
+      acc.prod *= fmaf(0.2f, d, 1.0f);
+      if (acc.prod > 1e18f) { acc.llsum += __logf(acc.prod); acc.prod = 1.0f; }   // keep the product in range
+    }
+    const int y = (int)__umulhi((unsigned)idx, wmagic);
+    const int x = idx - y * w;
+    const float z = __ldg(pl.r0 + idx).y;
+    const float px = __ldg(pl.rtmpl + x) * z, py = __ldg(pl.rtmpl + w + y) * z;
+    const float zi = rcp_fast(z), zs = zi * zi;
+    const float a2 = -px * zs, b2 = -py * zs;
+    const float a3 = a2 * py;
+    const f2 A23 = pk(a2, a3), B23 = pk(b2, fmaf(b2, py, -1.0f));
+    const f2 A45 = pk(fmaf(-a2, px, 1.0f), -py * zi), B45 = pk(-a3, px * zi);
+    const f2 NC23 = pk(-1.0f, -py), NC45 = pk(px, 0.0f);     // -c[2..3], -c[4..5]
+    const f2 G = pk(g2.x, g2.y), H = pk(h2.x, h2.y);
+    const f2 Gp = fma2(bc(c.l), H, G);                        // (gx + l hx, gy + l hy)
+    const float gx = lo(Gp), gy = hi(Gp);
+    f2 V0[3], V1[3];
+    V0[0] = mul2(Gp, bc(zi));
+    V0[1] = fma2(bc(gx), A23, fma2(bc(gy), B23, mul2(bc(c.l), NC23)));
+    V0[2] = fma2(bc(gx), A45, fma2(bc(gy), B45, mul2(bc(c.l), NC45)));
+    V1[0] = mul2(H, bc(zi));
+    V1[1] = fma2(bc(h2.x), A23, fma2(bc(h2.y), B23, NC23));
+    V1[2] = fma2(bc(h2.x), A45, fma2(bc(h2.y), B45, NC45));
+    // b -= J^T W r
+    stage_b_rank1(acc, V0, wgt * c.wd0, -fmaf(c.l, ez, ei));
+    stage_b_rank1(acc, V1, wgt * c.wd1, -ez);
+  }
+}
+
+// flush the product of the pending log-likelihood terms and unpack: out[0] = ll sum,
+// out[1..21] = A upper triangle (row-major), out[22..27] = b
+__device__ __forceinline__ void stage_b_values(const StageBAcc& acc, float out[kNormalValues]) {
+  out[0] = acc.llsum + __logf(acc.prod);
+  out[1] = lo(acc.r0[0]); out[2] = hi(acc.r0[0]); out[3] = lo(acc.r0[1]); out[4] = hi(acc.r0[1]); out[5] = lo(acc.r0[2]); out[6] = hi(acc.r0[2]);
+  out[7] = hi(acc.r1[0]); out[8] = lo(acc.r1[1]); out[9] = hi(acc.r1[1]); out[10] = lo(acc.r1[2]); out[11] = hi(acc.r1[2]);
+  out[12] = lo(acc.r2[0]); out[13] = hi(acc.r2[0]); out[14] = lo(acc.r2[1]); out[15] = hi(acc.r2[1]);
+  out[16] = hi(acc.r3[0]); out[17] = lo(acc.r3[1]); out[18] = hi(acc.r3[1]);
+  out[19] = lo(acc.r4); out[20] = hi(acc.r4);
+  out[21] = hi(acc.r5);
+  out[22] = lo(acc.b[0]); out[23] = hi(acc.b[0]); out[24] = lo(acc.b[1]); out[25] = hi(acc.b[1]); out[26] = lo(acc.b[2]); out[27] = hi(acc.b[2]);
+}
+
+__device__ __forceinline__ void load_stage_b_consts(const PairState& st, StageBConsts& c) {
+  c.P00 = __ldcg(&st.precision[0]); c.P01 = __ldcg(&st.precision[1]); c.P10 = __ldcg(&st.precision[2]); c.P11 = __ldcg(&st.precision[3]);
+  c.l = c.P01 / c.P00;
+  c.wd0 = c.P00;
+  c.wd1 = c.P11 - c.P01 * c.l;
+}
+
+}  // namespace dvo_b200

@@ -11,11 +11,14 @@
 // with one tiny per-pair kernel after each (k_pair_mid: P_k; k_pair_end: accept test, 6x6 LDL^T solve,
 // SE(3) update, termination logic).
 #include "common.cuh"
+#include "stages.cuh"
 
 #include <cstdio>
 #include <cstring>
 #include <limits>
 #include <cmath>
+#include <cstdlib>
+#include <algorithm>
 
 namespace dvo_b200 {
 
@@ -24,7 +27,9 @@ namespace {
 constexpr unsigned kFull = 0xffffffffu;
 
 struct LevelLaunch {
-  int w, h, n, ntiles;
+  int w, h, n, ntiles;   // ntiles = CTAs of a stage launch (4 segments each)
+  int nseg;              // warp segments of kSegmentPixels pixels
+  unsigned wmagic;       // floor(2^32 / w) + 1: idx / w == __umulhi(idx, wmagic) for idx * w < 2^32
   int level_index;   // position in Result.Statistics.Levels
   int level_id;      // pyramid level
   int max_iterations;
@@ -103,252 +108,63 @@ __global__ void k_level_begin(PairState* states, const PairLevel* pls, const dou
 }
 
 // ------------------------------------------------------------------------------------------------
-// stage A
+// stage A kernel: one warp per 256-pixel segment, four segments per CTA
 // ------------------------------------------------------------------------------------------------
-struct TileConsts {
-  float kt[12];
-  float P[4];
-  float c_i, c_gx, c_gy, fx, fy, ubx, uby;
-  int first_iteration;
-  int S, last_sel;
-};
-
-struct PixelOut {
-  float ei, ez, gx, gy, hx, hy;
-};
-
-// The residual record of one reference pixel: computeResidualsSse (dense_tracking_impl.cpp:133-393).
-// Every fp32 operation is an explicit round-to-nearest intrinsic so that the value is defined bit
-// for bit (the oracle's MIRROR mode restates exactly this sequence on the CPU):
-//   point (x,y,z) = (tx*z, ty*z, z); (X,Y,Z') = fma chains of KT rows; (u,v) = (X,Y) * rcp_rn(Z')
-//   bounds 0<=u<=w-2, 0<=v<=h-2; truncation; bilinear blend of the six channels
-//   residual record with the weights of dense_tracking.cpp:215-220; occlusion test (line 275)
-__device__ __forceinline__ bool pixel_record(int idx, int x, int y, int w, const PairLevel& pl, const TileConsts& tc,
-                                             PixelOut& o) {
-  float2 a = __ldg(pl.r0 + idx);   // (I_r, Z_r)
-  float2 g = __ldg(pl.r1 + idx);   // (Ix_r, Iy_r)
-  float z = a.y;
-  float tx = __ldg(pl.rtmpl + x), ty = __ldg(pl.rtmpl + w + y);
-  float px = __fmul_rn(tx, z), py = __fmul_rn(ty, z);
-  float X = __fmaf_rn(tc.kt[0], px, __fmaf_rn(tc.kt[1], py, __fmaf_rn(tc.kt[2], z, tc.kt[3])));
-  float Y = __fmaf_rn(tc.kt[4], px, __fmaf_rn(tc.kt[5], py, __fmaf_rn(tc.kt[6], z, tc.kt[7])));
-  float Zt = __fmaf_rn(tc.kt[8], px, __fmaf_rn(tc.kt[9], py, __fmaf_rn(tc.kt[10], z, tc.kt[11])));
-  float rz = __frcp_rn(Zt);
-  float u = __fmul_rn(X, rz), v = __fmul_rn(Y, rz);
-  if (!(u >= 0.f && u <= tc.ubx && v >= 0.f && v <= tc.uby)) return false;
-  int u0 = __float2int_rz(u), v0 = __float2int_rz(v);
-  float fu = __fsub_rn(u, (float)u0), fv = __fsub_rn(v, (float)v0);
-  float gu = __fsub_rn(1.0f, fu), gv = __fsub_rn(1.0f, fv);
-  int b = v0 * w + u0;
-  float2 p00 = __ldg(pl.c0 + b), p10 = __ldg(pl.c0 + b + 1), p01 = __ldg(pl.c0 + b + w), p11 = __ldg(pl.c0 + b + w + 1);
-#define DVO_BLEND(c00, c10, c01, c11) \
-  __fmaf_rn(fv, __fmaf_rn(fu, c11, __fmul_rn(gu, c01)), __fmul_rn(gv, __fmaf_rn(fu, c10, __fmul_rn(gu, c00))))
-  float Zc = DVO_BLEND(p00.y, p10.y, p01.y, p11.y);
-  if (Zc != Zc) return false;     // masked depth: any NaN lane of the reference's 8-vector
-  float Ic = DVO_BLEND(p00.x, p10.x, p01.x, p11.x);
-  o.ez = __fsub_rn(Zc, Zt);
-  float s = __fsub_rn(z, 0.4f);
-  float sig = __fmaf_rn(__fmul_rn(0.0019f, s), s, 0.0012f);   // depthStdDevZ (dense_tracking_impl.cpp:122-128)
-  if (!(o.ez > __fmul_rn(-20.0f, sig))) return false;         // occlusion test
-  o.ei = __fmaf_rn(tc.c_i, Ic, __fmul_rn(-tc.c_i, a.x));
-  float2 q00 = __ldg(pl.c1 + b), q10 = __ldg(pl.c1 + b + 1), q01 = __ldg(pl.c1 + b + w), q11 = __ldg(pl.c1 + b + w + 1);
-  float Ixc = DVO_BLEND(q00.x, q10.x, q01.x, q11.x);
-  float Iyc = DVO_BLEND(q00.y, q10.y, q01.y, q11.y);
-  o.gx = __fmaf_rn(tc.c_gx, Ixc, __fmul_rn(tc.c_gx, g.x));
-  o.gy = __fmaf_rn(tc.c_gy, Iyc, __fmul_rn(tc.c_gy, g.y));
-  float2 s00 = __ldg(pl.c2 + b), s10 = __ldg(pl.c2 + b + 1), s01 = __ldg(pl.c2 + b + w), s11 = __ldg(pl.c2 + b + w + 1);
-  float Zxc = DVO_BLEND(s00.x, s10.x, s01.x, s11.x);
-  float Zyc = DVO_BLEND(s00.y, s10.y, s01.y, s11.y);
-#undef DVO_BLEND
-  o.hx = __fmul_rn(tc.fx, Zxc);
-  o.hy = __fmul_rn(tc.fy, Zyc);
-  return true;
-}
-
-__device__ __forceinline__ void load_tile_consts(const PairState& st, const PairLevel& pl, int w, int h, TileConsts& tc) {
-#pragma unroll
-  for (int i = 0; i < 12; ++i) tc.kt[i] = st.kt[i];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) tc.P[i] = st.precision[i];
-  tc.c_i = 1.0f / 255.0f;
-  tc.c_gx = __fdiv_rn(__fmul_rn(0.5f, pl.cfx), 255.0f);
-  tc.c_gy = __fdiv_rn(__fmul_rn(0.5f, pl.cfy), 255.0f);
-  tc.fx = pl.cfx; tc.fy = pl.cfy;
-  tc.ubx = (float)(w - 2); tc.uby = (float)(h - 2);
-  tc.first_iteration = st.iteration == 0;
-  tc.S = pl.rsel[0]; tc.last_sel = pl.rsel[1];
-}
-
-// Pairwise scale sum (computeScaleSse, dense_tracking_impl.cpp:590-638).  The reference walks the
-// compacted residual list two at a time and, because lines 614-615 re-use the low half of the
-// register, adds (w_{2j} + w_{2j+1}) * r_{2j} r_{2j}^T for every pair and w_n r_n r_n^T for an odd
-// tail.  Reproducing that needs, for every valid point, the parity of its rank in row-major order
-// and the weight of the next valid point.  A contiguous run of pixels is summarised by a ScaleSeg:
-// sums under both hypotheses for the parity of its first point (S0: first point is a pair leader,
-// S1: it is a follower), its first valid weight and its last valid point (a leader whose partner
-// lies in the next run).  Runs combine associatively (combine_seg), so warps, tiles and finally the
-// whole image are reduced in a fixed order.
-template <typename T>
-struct SegT {
-  long long n;
-  T S0[3], S1[3];
-  T wf, wl, ol[3];
-};
-
-template <typename T, typename A, typename B>
-__host__ __device__ __forceinline__ SegT<T> combine_seg(const A& a, const B& b) {
-  SegT<T> r;
-  r.n = (long long)a.n + (long long)b.n;
-  int hb0 = (int)(a.n & 1), hb1 = (int)((a.n + 1) & 1);
-  bool link0 = a.n > 0 && b.n > 0 && (((a.n - 1) & 1) == 0);       // h = 0: last point of a is a leader
-  bool link1 = a.n > 0 && b.n > 0 && (((a.n - 1 + 1) & 1) == 0);   // h = 1
-  for (int k = 0; k < 3; ++k) {
-    T bs0 = hb0 ? (T)b.S1[k] : (T)b.S0[k];
-    T bs1 = hb1 ? (T)b.S1[k] : (T)b.S0[k];
-    r.S0[k] = (T)a.S0[k] + bs0 + (link0 ? ((T)a.wl + (T)b.wf) * (T)a.ol[k] : (T)0);
-    r.S1[k] = (T)a.S1[k] + bs1 + (link1 ? ((T)a.wl + (T)b.wf) * (T)a.ol[k] : (T)0);
-  }
-  r.wf = a.n > 0 ? (T)a.wf : (T)b.wf;
-  if (b.n > 0) { r.wl = (T)b.wl; for (int k = 0; k < 3; ++k) r.ol[k] = (T)b.ol[k]; }
-  else         { r.wl = (T)a.wl; for (int k = 0; k < 3; ++k) r.ol[k] = (T)a.ol[k]; }
-  return r;
-}
-
-__global__ void __launch_bounds__(kTileThreads)
+__global__ void __launch_bounds__(kSegmentsPerTile * 32)
 k_residual(const PairState* __restrict__ states, const PairLevel* __restrict__ pls, float* __restrict__ records,
-           float* __restrict__ scale_export, int w, int h, int n, int ntiles) {
-  const int pair = blockIdx.y, tile = blockIdx.x;
+           float* __restrict__ seg_export, LevelLaunch lp) {
+  const int pair = blockIdx.y;
   const PairState& st = states[pair];
   if (!st.level_active) return;
   const PairLevel pl = pls[pair];
-  TileConsts tc;
-  load_tile_consts(st, pl, w, h, tc);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float* rec = records + (size_t)pair * 7 * n;
-  const bool drop_last = (tc.S & 1) != 0;  // odd number of selected points: last one skipped (dense_tracking_impl.cpp:169)
-
-  float S0[3] = {0.f, 0.f, 0.f}, S1[3] = {0.f, 0.f, 0.f};
-  bool pend = false;
-  float pw = 0.f, po0 = 0.f, po1 = 0.f, po2 = 0.f;
-  int ppar = 0, cnt = 0;
-  float wfirst = 0.f;
-
-  const int seg_base = tile * kTilePixels + warp * 128;
-#pragma unroll 1
-  for (int r = 0; r < 4; ++r) {
-    const int base = seg_base + r * 32;
-    if (base >= n) break;
-    const int idx = base + lane;
-    bool valid = false;
-    PixelOut o;
-    float wgt = 1.0f;
-    unsigned selw = __ldg(pl.rmask + (base >> 5));
-    if ((selw >> lane) & 1u) {
-      if (!(drop_last && idx == tc.last_sel)) {
-        int y = idx / w, x = idx - y * w;
-        valid = pixel_record(idx, x, y, w, pl, tc, o);
-      }
-    }
-    if (valid && !tc.first_iteration) {
-      // computeWeightsSse (dense_tracking_impl.cpp:657-707): w = 7 / (5 + r^T P r), nu = 5
-      float d = (o.ei * tc.P[0] + o.ez * tc.P[2]) * o.ei + (o.ei * tc.P[1] + o.ez * tc.P[3]) * o.ez;
-      wgt = __fdividef(7.0f, 5.0f + d);
-    }
-    if (idx < n) {
-      const float nanf_ = __int_as_float(0x7fc00000);
-      rec[idx] = valid ? o.ei : nanf_;
-      if (valid) {
-        rec[(size_t)n + idx] = o.ez; rec[2 * (size_t)n + idx] = o.gx; rec[3 * (size_t)n + idx] = o.gy;
-        rec[4 * (size_t)n + idx] = o.hx; rec[5 * (size_t)n + idx] = o.hy; rec[6 * (size_t)n + idx] = wgt;
-      }
-    }
-    unsigned m = __ballot_sync(kFull, valid);
-    if (m) {
-      int first = __ffs(m) - 1, last = 31 - __clz(m);
-      float w_first = __shfl_sync(kFull, wgt, first);
-      if (cnt == 0) wfirst = w_first;
-      if (pend && lane == 0) {
-        float s = pw + w_first;
-        if (ppar) { S1[0] += s * po0; S1[1] += s * po1; S1[2] += s * po2; }
-        else      { S0[0] += s * po0; S0[1] += s * po1; S0[2] += s * po2; }
-      }
-      unsigned above = lane == 31 ? 0u : (m >> (lane + 1));
-      int nxt = above ? lane + __ffs(above) : lane;
-      float w_next = __shfl_sync(kFull, wgt, nxt);
-      float o0 = valid ? o.ei * o.ei : 0.f, o1 = valid ? o.ei * o.ez : 0.f, o2 = valid ? o.ez * o.ez : 0.f;
-      if (valid && above) {
-        int rank = cnt + __popc(m & ((1u << lane) - 1u));
-        float s = wgt + w_next;
-        if (rank & 1) { S1[0] += s * o0; S1[1] += s * o1; S1[2] += s * o2; }
-        else          { S0[0] += s * o0; S0[1] += s * o1; S0[2] += s * o2; }
-      }
-      pw = __shfl_sync(kFull, wgt, last);
-      po0 = __shfl_sync(kFull, o0, last); po1 = __shfl_sync(kFull, o1, last); po2 = __shfl_sync(kFull, o2, last);
-      cnt += __popc(m);
-      ppar = (cnt - 1) & 1;
-      pend = true;
-    }
-  }
-  // warp reduction of the six sums, then the 8 warp segments of the tile are combined in order
-#pragma unroll
-  for (int k = 0; k < 3; ++k) {
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      S0[k] += __shfl_xor_sync(kFull, S0[k], off);
-      S1[k] += __shfl_xor_sync(kFull, S1[k], off);
-    }
-  }
-  __shared__ SegT<float> segs[kTileThreads / 32];
-  if (lane == 0) {
-    SegT<float>& s = segs[warp];
-    s.n = cnt;
-    for (int k = 0; k < 3; ++k) { s.S0[k] = S0[k]; s.S1[k] = S1[k]; }
-    s.wf = wfirst; s.wl = pw; s.ol[0] = po0; s.ol[1] = po1; s.ol[2] = po2;
-  }
+  StageConsts c;
+  load_stage_consts(st, pl, lp.w, lp.h, c);
+  const int warp = threadIdx.x >> 5;
+  const int seg = blockIdx.x * kSegmentsPerTile + warp;
+  const int begin = min(seg * kSegmentPixels, lp.n);
+  const int end = min(begin + kSegmentPixels, lp.n);
+  const RecordPlanes rec = record_planes(records + (size_t)pair * kRecordFloatsPerPixel * lp.n, lp.n);
+  __shared__ float sm_exp[kSegmentsPerTile][kSegExportFloats];
+  stage_a_segment(pl, c, lp.w, lp.wmagic, lp.n, begin, end, rec, sm_exp[warp]);
   __syncthreads();
-  if (threadIdx.x == 0) {
-    SegT<float> acc = segs[0];
-    for (int k = 1; k < kTileThreads / 32; ++k) acc = combine_seg<float>(acc, segs[k]);
-    float* e = scale_export + ((size_t)pair * ntiles + tile) * kScaleExportFloats;
-    e[0] = __int_as_float((int)acc.n);
-    e[1] = acc.S0[0]; e[2] = acc.S0[1]; e[3] = acc.S0[2];
-    e[4] = acc.S1[0]; e[5] = acc.S1[1]; e[6] = acc.S1[2];
-    e[7] = acc.wf; e[8] = acc.wl; e[9] = acc.ol[0]; e[10] = acc.ol[1]; e[11] = acc.ol[2];
-  }
+  if (threadIdx.x == 0) cta_export_segments(sm_exp, seg_export + ((size_t)pair * lp.ntiles + blockIdx.x) * kCtaExportFloats);
 }
 
-__device__ __forceinline__ SegT<double> load_seg(const float* e) {
-  SegT<double> s;
-  s.n = __float_as_int(e[0]);
-  s.S0[0] = e[1]; s.S0[1] = e[2]; s.S0[2] = e[3];
-  s.S1[0] = e[4]; s.S1[1] = e[5]; s.S1[2] = e[6];
-  s.wf = e[7]; s.wl = e[8]; s.ol[0] = e[9]; s.ol[1] = e[10]; s.ol[2] = e[11];
-  return s;
-}
+struct PairMidSmem {
+  SegT<double> lanes[32];
+  long long lane_base[32];
+};
 
-// one warp per pair: combine tile summaries in order -> covariance -> P_k (dense_tracking.cpp:276-295)
-__global__ void k_pair_mid(PairState* states, const float* __restrict__ scale_export, int* __restrict__ tile_base,
-                           int ntiles, int* active, LevelLaunch lp, dvo_b200_iteration_stats* ilog, int max_log) {
-  const int pair = blockIdx.x, lane = threadIdx.x;
-  PairState& st = states[pair];
-  if (!st.level_active) return;
-  const float* e = scale_export + (size_t)pair * ntiles * kScaleExportFloats;
+// one warp per pair: combine the segment summaries in order -> covariance -> P_k (dense_tracking.cpp:276-295).
+// e: this pair's nseg segment exports; seg_base: this pair's exclusive prefix of valid counts (output).
+__device__ __noinline__ void pair_mid_warp(PairState& st, int pair, const float* e, int* seg_base, int ntiles, int* active,
+                              const LevelLaunch& lp, dvo_b200_iteration_stats* ilog, int max_log, PairMidSmem& sm) {
+  const int lane = threadIdx.x & 31;
+  SegT<double>* lanes = sm.lanes;
+  long long* lane_base = sm.lane_base;
   int chunk = (ntiles + 31) / 32;
   int t0 = lane * chunk, t1 = min(t0 + chunk, ntiles);
   SegT<double> acc;
   acc.n = 0; acc.wf = acc.wl = 0;
   for (int k = 0; k < 3; ++k) acc.S0[k] = acc.S1[k] = acc.ol[k] = 0;
-  for (int t = t0; t < t1; ++t) acc = combine_seg<double>(acc, load_seg(e + (size_t)t * kScaleExportFloats));
-  __shared__ SegT<double> lanes[32];
-  __shared__ long long lane_base[32];
+  for (int t = t0; t < t1; ++t) acc = combine_seg<double>(acc, load_seg_export(e + (size_t)t * kCtaExportFloats));
   lanes[lane] = acc;
+  {   // exclusive prefix of the lane counts
+    long long incl = acc.n;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      long long v = __shfl_up_sync(kFull, incl, off);
+      if (lane >= off) incl += v;
+    }
+    lane_base[lane] = incl - acc.n;
+  }
   __syncwarp();
+  for (int off = 1; off < 32; off <<= 1) {   // in-order tree combine
+    if ((lane & (2 * off - 1)) == 0) lanes[lane] = combine_seg<double>(lanes[lane], lanes[lane + off]);
+    __syncwarp();
+  }
   if (lane == 0) {
     SegT<double> all = lanes[0];
-    long long run = 0;
-    lane_base[0] = 0;
-    run = lanes[0].n;
-    for (int k = 1; k < 32; ++k) { lane_base[k] = run; run += lanes[k].n; all = combine_seg<double>(all, lanes[k]); }
     long long n = all.n;
     st.n = n;
     st.n_keep = (n / 50) * 50;
@@ -373,7 +189,7 @@ __global__ void k_pair_mid(PairState* states, const float* __restrict__ scale_ex
       if (st.termination != DVO_B200_TERM_TOO_FEW_CONSTRAINTS) ls.has_inc = ls.num_iterations >= 1;
       st.have_done = (st.termination == DVO_B200_TERM_TOO_FEW_CONSTRAINTS) ? -1 : st.have_done;
       st.level_active = 0;
-      atomicSub(active, 1);
+      if (active) atomicSub(active, 1);
     } else {
       // tail term for odd n, normaliser 1/(n-3) (dense_tracking_impl.cpp:596), symmetric 2x2
       double c[3];
@@ -395,137 +211,85 @@ __global__ void k_pair_mid(PairState* states, const float* __restrict__ scale_ex
   // exclusive prefix of valid counts per tile (rank base for the log-likelihood tail drop)
   long long run = lane_base[lane];
   for (int t = t0; t < t1; ++t) {
-    tile_base[(size_t)pair * ntiles + t] = (int)run;
-    run += __float_as_int(e[(size_t)t * kScaleExportFloats]);
+    seg_base[t] = (int)run;
+    run += __float_as_int(__ldcg(e + (size_t)t * kCtaExportFloats));
   }
+  __syncwarp();
+}
+
+__global__ void k_pair_mid(PairState* states, const float* __restrict__ scale_export, int* __restrict__ tile_base,
+                           int ntiles, int* active, LevelLaunch lp, dvo_b200_iteration_stats* ilog, int max_log) {
+  const int pair = blockIdx.x;
+  PairState& st = states[pair];
+  if (!st.level_active) return;
+  __shared__ PairMidSmem sm;
+  pair_mid_warp(st, pair, scale_export + (size_t)pair * ntiles * kCtaExportFloats, tile_base + (size_t)pair * ntiles, ntiles,
+                active, lp, ilog, max_log, sm);
 }
 
 // ------------------------------------------------------------------------------------------------
-// stage B
+// stage B kernel: one warp per segment, CTA-level reduction of the 28 values in a fixed order
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kTileThreads)
+__global__ void __launch_bounds__(kSegmentsPerTile * 32)
 k_normal(const PairState* __restrict__ states, const PairLevel* __restrict__ pls, const float* __restrict__ records,
-         const float* __restrict__ scale_export, const int* __restrict__ tile_base, float* __restrict__ partial, int w,
-         int h, int n, int ntiles) {
+         const float* __restrict__ seg_export, const int* __restrict__ seg_base, float* __restrict__ partial,
+         LevelLaunch lp) {
   const int pair = blockIdx.y, tile = blockIdx.x;
   const PairState& st = states[pair];
   if (!st.level_active || !st.phase_ok) return;
   const PairLevel pl = pls[pair];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const float* rec = records + (size_t)pair * 7 * n;
-  const float P0 = st.precision[0], P1 = st.precision[1], P2 = st.precision[2], P3 = st.precision[3];
-  const long long n_keep = st.n_keep;
-  const int tbase = tile_base[(size_t)pair * ntiles + tile];
-  const int tcount = __float_as_int(scale_export[((size_t)pair * ntiles + tile) * kScaleExportFloats]);
-  const bool need_rank = (long long)tbase + tcount > n_keep;   // only the last tile(s) of the image
-
-  __shared__ int warp_cnt[kTileThreads / 32];
-  const int seg_base = tile * kTilePixels + warp * 128;
-  int warp_prefix = 0;
-  if (need_rank) {   // block-uniform
-    int c = 0;
-    for (int r = 0; r < 4; ++r) {
-      int idx = seg_base + r * 32 + lane;
-      float v = idx < n ? rec[idx] : __int_as_float(0x7fc00000);
-      c += __popc(__ballot_sync(kFull, v == v));
-    }
-    if (lane == 0) warp_cnt[warp] = c;
-    __syncthreads();
-    for (int k = 0; k < warp; ++k) warp_prefix += warp_cnt[k];
+  StageBConsts c;
+  load_stage_b_consts(st, c);
+  const int seg = tile * kSegmentsPerTile + warp;
+  StageBAcc acc;
+  stage_b_init(acc);
+  if (seg < lp.nseg) {
+    const int begin = seg * kSegmentPixels;
+    const int end = min(begin + kSegmentPixels, lp.n);
+    const RecordPlanes rec = record_planes(const_cast<float*>(records) + (size_t)pair * kRecordFloatsPerPixel * lp.n, lp.n);
+    const float* ce = seg_export + ((size_t)pair * lp.ntiles + tile) * kCtaExportFloats;
+    long long base = seg_base[(size_t)pair * lp.ntiles + tile];
+    for (int k = 0; k < warp; ++k) base += __float_as_int(ce[12 + k]);
+    const int cnt = __float_as_int(ce[12 + warp]);
+    const bool need_rank = base + cnt > st.n_keep;    // only the segments holding the tail of the point list
+    stage_b_segment(pl, c, lp.w, lp.wmagic, lp.n, begin, end, rec, base, st.n_keep, need_rank, acc);
   }
-
-  float acc[27];
+  float v[kNormalValues];
+  stage_b_values(acc, v);
+  __shared__ float red[kSegmentsPerTile][kNormalValues];
 #pragma unroll
-  for (int i = 0; i < 27; ++i) acc[i] = 0.f;
-  float prod = 1.0f;
-  float llsum = 0.f;
-  int seen = 0;
-#pragma unroll 1
-  for (int r = 0; r < 4; ++r) {
-    const int base = seg_base + r * 32;
-    if (base >= n) break;
-    const int idx = base + lane;
-    float ei = idx < n ? rec[idx] : __int_as_float(0x7fc00000);
-    bool valid = ei == ei;
-    bool keep = valid;
-    if (need_rank) {
-      unsigned m = __ballot_sync(kFull, valid);
-      long long rank = (long long)tbase + warp_prefix + seen + __popc(m & ((1u << lane) - 1u));
-      keep = valid && rank < n_keep;
-      seen += __popc(m);
-    }
-    if (!valid) continue;
-    float ez = rec[(size_t)n + idx], gx = rec[2 * (size_t)n + idx], gy = rec[3 * (size_t)n + idx];
-    float hx = rec[4 * (size_t)n + idx], hy = rec[5 * (size_t)n + idx], wgt = rec[6 * (size_t)n + idx];
-    // log-likelihood term (dense_tracking_impl.cpp:406-425): log(1 + 0.2 r^T P r)
-    float d = (ei * P0 + ez * P2) * ei + (ei * P1 + ez * P3) * ez;
-    if (keep) prod *= fmaf(0.2f, d, 1.0f);
-    // Jacobians at the untransformed reference point (dense_tracking.cpp:448-476, 338-339)
-    int y = idx / w, x = idx - y * w;
-    float z = __ldg(pl.r0 + idx).y;
-    float tx = __ldg(pl.rtmpl + x), ty = __ldg(pl.rtmpl + w + y);
-    float px = tx * z, py = ty * z;
-    float zi = 1.0f / z, zs = zi * zi;
-    float a2 = -px * zs, a3 = a2 * py, a4 = 1.0f - a2 * px, a5 = -py * zi;
-    float b2 = -py * zs, b3 = -1.0f + b2 * py, b4 = -a3, b5 = px * zi;
-    float J0[6] = {gx * zi, gy * zi, gx * a2 + gy * b2, gx * a3 + gy * b3, gx * a4 + gy * b4, gx * a5 + gy * b5};
-    float J1[6] = {hx * zi, hy * zi, hx * a2 + hy * b2 - 1.0f, hx * a3 + hy * b3 - py, hx * a4 + hy * b4 + px,
-                   hx * a5 + hy * b5};
-    // W = w * P_k ; A += J^T W J ; b -= J^T W r (least_squares.cpp:58-64)
-    float W00 = wgt * P0, W01 = wgt * P1, W10 = wgt * P2, W11 = wgt * P3;
-    float ua[6], ub[6];
+  for (int i = 0; i < kNormalValues; ++i) {
 #pragma unroll
-    for (int c = 0; c < 6; ++c) { ua[c] = J0[c] * W00 + J1[c] * W10; ub[c] = J0[c] * W01 + J1[c] * W11; }
-    int k = 0;
-#pragma unroll
-    for (int i = 0; i < 6; ++i) {
-#pragma unroll
-      for (int j = i; j < 6; ++j) { acc[k] += ua[i] * J0[j] + ub[i] * J1[j]; ++k; }
-    }
-#pragma unroll
-    for (int i = 0; i < 6; ++i) acc[21 + i] -= ua[i] * ei + ub[i] * ez;
-  }
-  llsum = logf(prod);
-  // block reduction: warp shuffles then shared memory, fixed order
-  __shared__ float red[kTileThreads / 32][kNormalPartialFloats];
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) llsum += __shfl_xor_sync(kFull, llsum, off);
-#pragma unroll
-  for (int i = 0; i < 27; ++i) {
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) acc[i] += __shfl_xor_sync(kFull, acc[i], off);
+    for (int off = 16; off > 0; off >>= 1) v[i] += __shfl_xor_sync(kFull, v[i], off);
   }
   if (lane == 0) {
-    red[warp][0] = llsum;
 #pragma unroll
-    for (int i = 0; i < 27; ++i) red[warp][1 + i] = acc[i];
+    for (int i = 0; i < kNormalValues; ++i) red[warp][i] = v[i];
   }
   __syncthreads();
-  if (threadIdx.x < kNormalPartialFloats) {
+  if (threadIdx.x < kNormalValues) {
     float s = 0.f;
-    for (int k = 0; k < kTileThreads / 32; ++k) s += red[k][threadIdx.x];
-    partial[((size_t)pair * ntiles + tile) * kNormalPartialFloats + threadIdx.x] = s;
+    for (int k = 0; k < kSegmentsPerTile; ++k) s += red[k][threadIdx.x];
+    partial[((size_t)pair * lp.ntiles + tile) * kNormalValues + threadIdx.x] = s;
   }
 }
 
 // one warp per pair: reduce tile partials, log-likelihood, accept test, solve, termination
 // (dense_tracking.cpp:297-363)
-__global__ void k_pair_end(PairState* states, const PairLevel* pls, const float* __restrict__ partial, int ntiles,
-                           int* active, LevelLaunch lp, dvo_b200_iteration_stats* ilog, int max_log) {
-  const int pair = blockIdx.x, lane = threadIdx.x;
-  PairState& st = states[pair];
-  if (!st.level_active || !st.phase_ok) return;
+__device__ __noinline__ void pair_end_warp(PairState& st, const PairLevel& pl, int pair, const float* partial, int ntiles, int* active,
+                              const LevelLaunch& lp, dvo_b200_iteration_stats* ilog, int max_log) {
+  const int lane = threadIdx.x & 31;
   double v = 0.0;
-  if (lane < kNormalPartialFloats) {
-    const float* p = partial + (size_t)pair * ntiles * kNormalPartialFloats + lane;
-    for (int t = 0; t < ntiles; ++t) v += (double)p[(size_t)t * kNormalPartialFloats];
+  if (lane < kNormalValues) {
+    const float* p = partial + lane;
+    for (int t = 0; t < ntiles; ++t) v += (double)__ldcg(p + (size_t)t * kNormalValues);
   }
-  double vals[kNormalPartialFloats];
+  double vals[kNormalValues];
 #pragma unroll
-  for (int i = 0; i < kNormalPartialFloats; ++i) vals[i] = __shfl_sync(kFull, v, i);
+  for (int i = 0; i < kNormalValues; ++i) vals[i] = __shfl_sync(kFull, v, i);
   if (lane != 0) return;
 
-  const PairLevel& pl = pls[pair];
   LevelSummary& ls = st.levels[lp.level_index];
   // computeCompleteDataLogLikelihood: 0.5 n log det P - 3.5 sum log(1 + 0.2 d), returned as float
   float det = __fsub_rn(__fmul_rn(st.precision[0], st.precision[3]), __fmul_rn(st.precision[1], st.precision[2]));
@@ -533,10 +297,12 @@ __global__ void k_pair_end(PairState* states, const PairLevel* pls, const float*
   float ll = (float)(0.5 * (double)st.n * (double)logdet - 0.5 * (5.0 + 2.0) * vals[0]);
   st.ll = ll;
   st.nll_cur = -(double)ll;
-  double li[6];
-  se3_log(st.initial, li);
+  double li[6] = {0, 0, 0, 0, 0, 0};
   double sq = 0;
-  for (int i = 0; i < 6; ++i) sq += li[i] * li[i];
+  if (lp.mu != 0.0) {                              // mu == 0: prior term and the mu*log(initial) shift vanish
+    se3_log(st.initial, li);
+    for (int i = 0; i < 6; ++i) sq += li[i] * li[i];
+  }
   st.prior_cur = lp.mu * sq;                       // dense_tracking.cpp:302
   st.last_error = st.error;                        // dense_tracking.cpp:306-307
   st.error = -(double)ll;
@@ -579,9 +345,205 @@ __global__ void k_pair_end(PairState* states, const PairLevel* pls, const float*
                 st.termination == DVO_B200_TERM_TOO_FEW_CONSTRAINTS) ? 2 : 1;
     ls.has_inc = ls.num_iterations >= need;
     st.level_active = 0;
-    atomicSub(active, 1);
+    if (active) atomicSub(active, 1);
   } else {
     prepare_iteration(st, pl);
+  }
+}
+
+__global__ void k_pair_end(PairState* states, const PairLevel* pls, const float* __restrict__ partial, int ntiles,
+                           int* active, LevelLaunch lp, dvo_b200_iteration_stats* ilog, int max_log) {
+  const int pair = blockIdx.x;
+  PairState& st = states[pair];
+  if (!st.level_active || !st.phase_ok) return;
+  pair_end_warp(st, pls[pair], pair, partial + (size_t)pair * ntiles * kNormalValues, ntiles, active, lp, ilog, max_log);
+}
+
+// ------------------------------------------------------------------------------------------------
+// One persistent cooperative kernel per pyramid level.
+//
+// The grid is num_sms x C CTAs (C = resident CTAs per SM).  CTAs are grouped into squads of g CTAs
+// (g chosen per level so that a warp walks >= ~8 rounds of 32 pixels); a squad owns ONE frame pair at
+// a time and runs all its Gauss-Newton iterations on this level inside the kernel:
+//   stage A over the squad's warp segments -> squad barrier, the last CTA to arrive computes P_k
+//   (pair_mid_warp) -> stage B -> squad barrier, the last CTA reduces the partials, tests the
+//   log-likelihood, solves the 6x6 system and updates the pose (pair_end_warp) -> next iteration,
+// then takes the next pair from a global queue.  The residual records of the pair in flight live in a
+// per-squad scratch buffer that is rewritten every iteration and therefore stays in L2; the squads of
+// different resident-CTA slots share each SM, so one squad's barrier wait is hidden by the others.
+// ------------------------------------------------------------------------------------------------
+#ifndef DVO_PERSISTENT_CTAS_PER_SM
+#define DVO_PERSISTENT_CTAS_PER_SM 5   // resident 128-thread CTAs per SM the register budget is tuned for
+#endif
+
+struct SquadState {
+  int pair;
+  unsigned arrive;
+  unsigned phase;
+  int pad_[29];   // one 128-byte line per squad
+};
+
+struct PersistentArgs {
+  PairState* states;
+  const PairLevel* pls;
+  float* records;
+  float* seg_export;
+  int* seg_base;
+  float* partial;
+  SquadState* squads;
+  int* next_pair;
+  int* error_flag;
+  dvo_b200_iteration_stats* ilog;
+  int max_log;
+  int npairs, g, squads_per_slot, num_sms, rpw, nseg;
+  LevelLaunch lp;
+};
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// returns true in every thread of the CTA that arrived last at barrier episode `episode`
+__device__ __forceinline__ bool squad_arrive(SquadState* sq, unsigned episode, int g, int* s_flag) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    unsigned old = atomicAdd(&sq->arrive, 1u);
+    int last = old == (episode + 1u) * (unsigned)g - 1u;
+    if (last) __threadfence();
+    s_flag[0] = last;
+  }
+  __syncthreads();
+  return s_flag[0] != 0;
+}
+__device__ __forceinline__ void squad_release(SquadState* sq, unsigned episode) {
+  __threadfence();
+  atomicExch(&sq->phase, episode + 1u);
+}
+__device__ __forceinline__ void squad_wait(SquadState* sq, unsigned episode, int* error_flag) {
+  if (threadIdx.x == 0) {
+    unsigned spins = 0;
+    while (ld_acquire_u32(&sq->phase) < episode + 1u) {
+      __nanosleep(200);
+      if (((++spins) & 4095u) == 0u) {
+        if (*reinterpret_cast<volatile int*>(error_flag)) break;
+        if (spins > (1u << 25)) { atomicExch(error_flag, 1); break; }   // ~ seconds: never hang the GPU
+      }
+    }
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kSegmentsPerTile * 32, DVO_PERSISTENT_CTAS_PER_SM)
+k_level_persistent(PersistentArgs a) {
+  const int slot = blockIdx.x / a.num_sms, smi = blockIdx.x % a.num_sms;
+  const int sq_in_slot = smi / a.g;
+  if (sq_in_slot >= a.squads_per_slot) return;   // leftover CTAs of this slot
+  const int squad = slot * a.squads_per_slot + sq_in_slot;
+  const int rank = smi - sq_in_slot * a.g;
+  SquadState* sq = a.squads + squad;
+  const LevelLaunch& lp = a.lp;
+  float* rec_base = a.records + (size_t)squad * kRecordFloatsPerPixel * lp.n;
+  float* exports = a.seg_export + (size_t)squad * a.g * kCtaExportFloats;
+  int* segbase = a.seg_base + (size_t)squad * a.g;
+  float* partial = a.partial + (size_t)squad * a.g * kNormalValues;
+  const RecordPlanes rec = record_planes(rec_base, lp.n);
+
+  __shared__ PairMidSmem sm_mid;
+  __shared__ float red[kSegmentsPerTile][kNormalValues];
+  __shared__ float sm_exp[kSegmentsPerTile][kSegExportFloats];
+  __shared__ int s_flag[2];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wk = rank * kSegmentsPerTile + warp;           // this warp's segment index inside the squad
+  const int R = (lp.n + 31) >> 5;
+  const int r0 = min(wk * a.rpw, R), r1 = min(r0 + a.rpw, R);
+  const int begin = r0 * 32, end = min(r1 * 32, lp.n);
+  unsigned episode = 0;
+
+  for (;;) {
+    // ---- take the next pair from the queue (the last CTA to arrive does it for the squad) ----
+    if (squad_arrive(sq, episode, a.g, s_flag)) {
+      if (threadIdx.x == 0) {
+        int p = atomicAdd(a.next_pair, 1);
+        sq->pair = p < a.npairs ? p : -1;
+        squad_release(sq, episode);
+      }
+    } else {
+      squad_wait(sq, episode, a.error_flag);
+    }
+    __syncthreads();
+    ++episode;
+    const int pair = __ldcg(&sq->pair);
+    if (pair < 0 || *reinterpret_cast<volatile int*>(a.error_flag)) break;
+    PairState& st = a.states[pair];
+    const PairLevel pl = a.pls[pair];
+
+    for (;;) {
+      // ---- stage A ----
+      {
+        StageConsts c;
+        load_stage_consts(st, pl, lp.w, lp.h, c);
+        stage_a_segment(pl, c, lp.w, lp.wmagic, lp.n, begin, end, rec, sm_exp[warp]);
+        __syncthreads();
+        if (threadIdx.x == 0) cta_export_segments(sm_exp, exports + (size_t)rank * kCtaExportFloats);
+      }
+      if (squad_arrive(sq, episode, a.g, s_flag)) {
+        if (warp == 0) {
+          pair_mid_warp(st, pair, exports, segbase, a.g, nullptr, lp, a.ilog, a.max_log, sm_mid);
+          if (lane == 0) squad_release(sq, episode);
+        }
+      } else {
+        squad_wait(sq, episode, a.error_flag);
+      }
+      __syncthreads();
+      ++episode;
+      if (!__ldcg(&st.level_active) || *reinterpret_cast<volatile int*>(a.error_flag)) break;   // too few constraints
+
+      // ---- stage B ----
+      {
+        StageBConsts cb;
+        load_stage_b_consts(st, cb);
+        StageBAcc acc;
+        stage_b_init(acc);
+        const long long n_keep = __ldcg(&st.n_keep);
+        long long base = __ldcg(&segbase[rank]);
+        for (int k = 0; k < warp; ++k) base += __float_as_int(sm_exp[k][0]);
+        const int cnt = __float_as_int(sm_exp[warp][0]);
+        stage_b_segment(pl, cb, lp.w, lp.wmagic, lp.n, begin, end, rec, base, n_keep, base + cnt > n_keep, acc);
+        float v[kNormalValues];
+        stage_b_values(acc, v);
+#pragma unroll
+        for (int i = 0; i < kNormalValues; ++i) {
+#pragma unroll
+          for (int off = 16; off > 0; off >>= 1) v[i] += __shfl_xor_sync(kFull, v[i], off);
+        }
+        if (lane == 0) {
+#pragma unroll
+          for (int i = 0; i < kNormalValues; ++i) red[warp][i] = v[i];
+        }
+        __syncthreads();
+        if (threadIdx.x < kNormalValues) {
+          float s = 0.f;
+          for (int k = 0; k < kSegmentsPerTile; ++k) s += red[k][threadIdx.x];
+          partial[(size_t)rank * kNormalValues + threadIdx.x] = s;
+        }
+      }
+      if (squad_arrive(sq, episode, a.g, s_flag)) {
+        if (warp == 0) {
+          pair_end_warp(st, pl, pair, partial, a.g, nullptr, lp, a.ilog, a.max_log);
+          __syncwarp();
+          if (lane == 0) squad_release(sq, episode);
+        }
+      } else {
+        squad_wait(sq, episode, a.error_flag);
+      }
+      __syncthreads();
+      ++episode;
+      if (!__ldcg(&st.level_active) || *reinterpret_cast<volatile int*>(a.error_flag)) break;
+    }
   }
 }
 
@@ -646,6 +608,7 @@ __global__ void k_set_state(PairState* states, const PairLevel* pls, const doubl
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
+inline int level_flag_slot(int li) { return li < 8 ? li : 7; }
 template <typename T>
 int grow(dvo_b200_ctx* ctx, T*& ptr, size_t& cap, size_t need) {
   if (need <= cap) return 0;
@@ -655,9 +618,12 @@ int grow(dvo_b200_ctx* ctx, T*& ptr, size_t& cap, size_t need) {
   return 0;
 }
 
-int ensure_workspace(dvo_b200_ctx* ctx, int npairs, int n0, int max_log_per_pair) {
+struct ScratchNeed {
+  size_t record_floats = 0, export_floats = 0, segbase_ints = 0, partial_floats = 0, squads = 0;
+};
+
+int ensure_workspace(dvo_b200_ctx* ctx, int npairs, const ScratchNeed& need, int max_log_per_pair) {
   Workspace& ws = ctx->ws;
-  int ntiles0 = (n0 + kTilePixels - 1) / kTilePixels;
   if ((size_t)npairs > ws.cap_pairs) {
     if (ws.d_pair_level) { cudaStreamSynchronize(ctx->stream); cudaFree(ws.d_pair_level); cudaFree(ws.d_state); }
     ws.d_pair_level = nullptr; ws.d_state = nullptr; ws.cap_pairs = 0;
@@ -666,25 +632,47 @@ int ensure_workspace(dvo_b200_ctx* ctx, int npairs, int n0, int max_log_per_pair
     ws.cap_pairs = npairs;
   }
   int rc;
-  if ((rc = grow(ctx, ws.d_records, ws.cap_records, (size_t)npairs * 7 * n0))) return rc;
-  size_t tiles = (size_t)npairs * ntiles0;
-  if (tiles > ws.cap_tiles) {
-    if (ws.d_scale_export) { cudaStreamSynchronize(ctx->stream); cudaFree(ws.d_scale_export); cudaFree(ws.d_tile_base); cudaFree(ws.d_normal_partial); }
-    ws.d_scale_export = nullptr; ws.d_tile_base = nullptr; ws.d_normal_partial = nullptr; ws.cap_tiles = 0;
-    DVO_CUDA(ctx, cudaMalloc((void**)&ws.d_scale_export, tiles * kScaleExportFloats * sizeof(float)));
-    DVO_CUDA(ctx, cudaMalloc((void**)&ws.d_tile_base, tiles * sizeof(int)));
-    DVO_CUDA(ctx, cudaMalloc((void**)&ws.d_normal_partial, tiles * kNormalPartialFloats * sizeof(float)));
-    ws.cap_tiles = tiles;
-  }
+  if ((rc = grow(ctx, ws.d_records, ws.cap_records, need.record_floats))) return rc;
+  if ((rc = grow(ctx, ws.d_scale_export, ws.cap_export, need.export_floats))) return rc;
+  if ((rc = grow(ctx, ws.d_tile_base, ws.cap_segbase, need.segbase_ints))) return rc;
+  if ((rc = grow(ctx, ws.d_normal_partial, ws.cap_partial, need.partial_floats))) return rc;
+  if ((rc = grow(ctx, ws.d_squads, ws.cap_squads, need.squads * sizeof(SquadState)))) return rc;
   if (!ws.d_active) {
-    DVO_CUDA(ctx, cudaMalloc((void**)&ws.d_active, sizeof(int) * 4));
-    DVO_CUDA(ctx, cudaMallocHost((void**)&ws.h_active, sizeof(int) * 4));
+    DVO_CUDA(ctx, cudaMalloc((void**)&ws.d_active, sizeof(int) * 8));
+    DVO_CUDA(ctx, cudaMallocHost((void**)&ws.h_active, sizeof(int) * 8));
   }
   if (max_log_per_pair > 0) {
-    size_t need = (size_t)npairs * max_log_per_pair;
-    if ((rc = grow(ctx, ws.d_iter_log, ws.cap_iter_log, need))) return rc;
+    size_t n = (size_t)npairs * max_log_per_pair;
+    if ((rc = grow(ctx, ws.d_iter_log, ws.cap_iter_log, n))) return rc;
   }
   return 0;
+}
+
+// How one pyramid level is spread over the persistent grid.
+struct LevelPlan {
+  int g;                // CTAs per squad
+  int squads_per_slot;  // num_sms / g
+  int nsquads;          // ctas_per_sm * squads_per_slot
+  int rpw;              // rounds of 32 pixels per warp
+  int nseg;             // warp segments per pair = g * kSegmentsPerTile
+};
+
+LevelPlan plan_level(int n, int num_sms, int ctas_per_sm) {
+  LevelPlan p;
+  const int R = (n + 31) / 32;
+  const int warps = kSegmentsPerTile;
+  // Squad size: enough CTAs that a warp walks about `target` rounds of 32 pixels per stage.  Small squads keep
+  // many pairs in flight and amortise the two barriers and the serial P_k / solve sections of an iteration.
+  static const int target = [] { const char* e = getenv("DVO_B200_RPW"); int v = e ? atoi(e) : 0; return v > 0 ? v : 64; }();
+  int g_raw = std::max(1, std::min(num_sms, (R + warps * target - 1) / (warps * target)));
+  int k = std::max(1, num_sms / g_raw);   // squads per resident-CTA slot
+  int g = num_sms / k;
+  p.g = g;
+  p.squads_per_slot = k;
+  p.nsquads = ctas_per_sm * p.squads_per_slot;
+  p.rpw = (R + g * warps - 1) / (g * warps);
+  p.nseg = g * warps;
+  return p;
 }
 
 int check_batch(dvo_b200_ctx* ctx, const dvo_b200_config* cfg, int n, dvo_b200_pyramid* const* refs,
@@ -744,7 +732,27 @@ int tracker_match_batch(dvo_b200_ctx* ctx, const dvo_b200_config* cfg, int n, dv
   Workspace& ws = ctx->ws;
   const int last = cfg->last_level, first = cfg->first_level;
   const int max_log = iter_stats ? max_iter_stats : 0;
-  rc = ensure_workspace(ctx, n, refs[0]->L[last].n, max_log);
+  // persistent grid geometry
+  if (ctx->num_sms == 0) {
+    cudaDeviceProp prop;
+    DVO_CUDA(ctx, cudaGetDeviceProperties(&prop, ctx->device));
+    ctx->num_sms = prop.multiProcessorCount;
+    int per_sm = 0;
+    DVO_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_level_persistent, kSegmentsPerTile * 32, 0));
+    if (per_sm < 1) return set_error(ctx, DVO_B200_ERR_CUDA, "persistent kernel does not fit on an SM");
+    ctx->ctas_per_sm = per_sm;
+  }
+  ScratchNeed need;
+  for (int level = first; level >= last; --level) {
+    const int nl = refs[0]->L[level].n;
+    LevelPlan pl = plan_level(nl, ctx->num_sms, ctx->ctas_per_sm);
+    need.record_floats = std::max(need.record_floats, (size_t)pl.nsquads * kRecordFloatsPerPixel * nl);
+    need.export_floats = std::max(need.export_floats, (size_t)pl.nsquads * pl.g * kCtaExportFloats);
+    need.segbase_ints = std::max(need.segbase_ints, (size_t)pl.nsquads * pl.g);
+    need.partial_floats = std::max(need.partial_floats, (size_t)pl.nsquads * pl.g * kNormalValues);
+    need.squads = std::max(need.squads, (size_t)pl.nsquads + 1);
+  }
+  rc = ensure_workspace(ctx, n, need, max_log);
   if (rc) return rc;
 
   // selection masks for non-default thresholds (PointSelection caches per pyramid, point_selection.cpp:100-113)
@@ -762,48 +770,41 @@ int tracker_match_batch(dvo_b200_ctx* ctx, const dvo_b200_config* cfg, int n, dv
     ctx->h2d_bytes += bytes;
   }
 
+  for (int i = 0; i < 8; ++i) ws.h_active[i] = 0;
   for (int level = first, li = 0; level >= last; --level, ++li) {
     const LevelInfo& L = refs[0]->L[level];
     LevelLaunch lp;
-    lp.w = L.w; lp.h = L.h; lp.n = L.n; lp.ntiles = (L.n + kTilePixels - 1) / kTilePixels;
+    lp.w = L.w; lp.h = L.h; lp.n = L.n; lp.nseg = (L.n + kSegmentPixels - 1) / kSegmentPixels; lp.ntiles = (lp.nseg + kSegmentsPerTile - 1) / kSegmentsPerTile;
+    lp.wmagic = (unsigned)((1ull << 32) / (unsigned)L.w) + 1u;
     lp.level_index = li; lp.level_id = level; lp.max_iterations = cfg->max_iterations_per_level;
     lp.first_level = li == 0; lp.use_initial_estimate = cfg->use_initial_estimate;
     lp.precision = cfg->precision; lp.mu = cfg->mu;
     if ((rc = upload_pair_levels(ctx, n, refs, curs, level))) return rc;
-    ws.h_active[0] = n;
-    DVO_CUDA(ctx, cudaMemcpyAsync(ws.d_active, ws.h_active, sizeof(int), cudaMemcpyHostToDevice, st));
+    const LevelPlan plan = plan_level(L.n, ctx->num_sms, ctx->ctas_per_sm);
+    // squad states, queue head and error flag (last SquadState slot) start at zero
+    DVO_CUDA(ctx, cudaMemsetAsync(ws.d_squads, 0, sizeof(SquadState) * (plan.nsquads + 1), st));
     {
       ProfScope prof(ctx, 2);
       k_level_begin<<<(n + 63) / 64, 64, 0, st>>>(ws.d_state, ws.d_pair_level, d_Tinit, n, lp);
       ctx->launches++;
     }
-    dim3 grid(lp.ntiles, n);
-    for (int it = 0; it < lp.max_iterations || it == 0; ++it) {
-      {
-        ProfScope prof(ctx, 0);
-        k_residual<<<grid, kTileThreads, 0, st>>>(ws.d_state, ws.d_pair_level, ws.d_records, ws.d_scale_export, lp.w, lp.h,
-                                                  lp.n, lp.ntiles);
-      }
-      {
-        ProfScope prof(ctx, 2);
-        k_pair_mid<<<n, 32, 0, st>>>(ws.d_state, ws.d_scale_export, ws.d_tile_base, lp.ntiles, ws.d_active, lp,
-                                     ws.d_iter_log, max_log);
-      }
-      {
-        ProfScope prof(ctx, 1);
-        k_normal<<<grid, kTileThreads, 0, st>>>(ws.d_state, ws.d_pair_level, ws.d_records, ws.d_scale_export, ws.d_tile_base,
-                                                ws.d_normal_partial, lp.w, lp.h, lp.n, lp.ntiles);
-      }
-      {
-        ProfScope prof(ctx, 2);
-        k_pair_end<<<n, 32, 0, st>>>(ws.d_state, ws.d_pair_level, ws.d_normal_partial, lp.ntiles, ws.d_active, lp,
-                                     ws.d_iter_log, max_log);
-      }
-      ctx->launches += 4;
-      DVO_CUDA(ctx, cudaMemcpyAsync(ws.h_active, ws.d_active, sizeof(int), cudaMemcpyDeviceToHost, st));
-      DVO_CUDA(ctx, cudaStreamSynchronize(st));
-      if (ws.h_active[0] <= 0) break;
+    PersistentArgs pa;
+    pa.states = ws.d_state; pa.pls = ws.d_pair_level; pa.records = ws.d_records; pa.seg_export = ws.d_scale_export;
+    pa.seg_base = ws.d_tile_base; pa.partial = ws.d_normal_partial;
+    pa.squads = reinterpret_cast<SquadState*>(ws.d_squads);
+    int* tail = reinterpret_cast<int*>(pa.squads + plan.nsquads);
+    pa.next_pair = tail; pa.error_flag = tail + 1;
+    pa.ilog = ws.d_iter_log; pa.max_log = max_log;
+    pa.npairs = n; pa.g = plan.g; pa.squads_per_slot = plan.squads_per_slot; pa.num_sms = ctx->num_sms; pa.rpw = plan.rpw;
+    pa.nseg = plan.nseg; pa.lp = lp;
+    {
+      ProfScope prof(ctx, 0);
+      void* args[] = {&pa};
+      DVO_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)k_level_persistent, dim3(ctx->num_sms * ctx->ctas_per_sm),
+                                                dim3(kSegmentsPerTile * 32), args, 0, st));
+      ctx->launches++;
     }
+    DVO_CUDA(ctx, cudaMemcpyAsync(&ws.h_active[level_flag_slot(li)], tail + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
   }
   // results
   dvo_b200_result* d_res = (dvo_b200_result*)d_results_user;
@@ -835,6 +836,8 @@ int tracker_match_batch(dvo_b200_ctx* ctx, const dvo_b200_config* cfg, int n, dv
     DVO_CUDA(ctx, cudaStreamSynchronize(st));
     std::memcpy(h_results, ctx->h_results, bytes);
     ctx->d2h_bytes += bytes;
+    for (int li = 0; li <= first - last && li < 8; ++li)
+      if (ws.h_active[li] != 0) return set_error(ctx, DVO_B200_ERR_CUDA, "persistent level kernel: squad barrier timed out");
   }
   return 0;
 }
@@ -852,10 +855,20 @@ int tracker_linearize(dvo_b200_ctx* ctx, const dvo_b200_config* cfg, dvo_b200_py
   cudaStream_t st = ctx->stream;
   Workspace& ws = ctx->ws;
   const LevelInfo& L = ref->L[level];
-  if ((rc = ensure_workspace(ctx, 1, L.n, 0))) return rc;
+  {
+    const size_t nseg = (L.n + kSegmentPixels - 1) / kSegmentPixels;
+    ScratchNeed need;
+    need.record_floats = (size_t)kRecordFloatsPerPixel * L.n;
+    need.export_floats = nseg * kCtaExportFloats;
+    need.segbase_ints = nseg;
+    need.partial_floats = nseg * kNormalValues;
+    need.squads = 2;
+    if ((rc = ensure_workspace(ctx, 1, need, 0))) return rc;
+  }
   if ((rc = pyramid_reselect(ctx, ref, cfg->intensity_derivative_threshold, cfg->depth_derivative_threshold))) return rc;
   LevelLaunch lp;
-  lp.w = L.w; lp.h = L.h; lp.n = L.n; lp.ntiles = (L.n + kTilePixels - 1) / kTilePixels;
+  lp.w = L.w; lp.h = L.h; lp.n = L.n; lp.nseg = (L.n + kSegmentPixels - 1) / kSegmentPixels; lp.ntiles = (lp.nseg + kSegmentsPerTile - 1) / kSegmentsPerTile;
+    lp.wmagic = (unsigned)((1ull << 32) / (unsigned)L.w) + 1u;
   lp.level_index = 0; lp.level_id = level; lp.max_iterations = 1 << 30; lp.first_level = 1;
   lp.use_initial_estimate = 0; lp.precision = 0.0; lp.mu = 0.0;
   if ((rc = upload_pair_levels(ctx, 1, refs, curs, level))) return rc;
@@ -871,12 +884,12 @@ int tracker_linearize(dvo_b200_ctx* ctx, const dvo_b200_config* cfg, dvo_b200_py
   k_set_state<<<1, 1, 0, st>>>(ws.d_state, ws.d_pair_level, (const double*)ctx->d_stage,
                                (const float*)((char*)ctx->d_stage + 128), use_weights, lp);
   dim3 grid(lp.ntiles, 1);
-  k_residual<<<grid, kTileThreads, 0, st>>>(ws.d_state, ws.d_pair_level, ws.d_records, ws.d_scale_export, lp.w, lp.h, lp.n, lp.ntiles);
+  k_residual<<<grid, kSegmentsPerTile * 32, 0, st>>>(ws.d_state, ws.d_pair_level, ws.d_records, ws.d_scale_export, lp);
   k_pair_mid<<<1, 32, 0, st>>>(ws.d_state, ws.d_scale_export, ws.d_tile_base, lp.ntiles, ws.d_active, lp, nullptr, 0);
   ctx->launches += 3;
   if (!planes7) {
-    k_normal<<<grid, kTileThreads, 0, st>>>(ws.d_state, ws.d_pair_level, ws.d_records, ws.d_scale_export, ws.d_tile_base,
-                                            ws.d_normal_partial, lp.w, lp.h, lp.n, lp.ntiles);
+    k_normal<<<grid, kSegmentsPerTile * 32, 0, st>>>(ws.d_state, ws.d_pair_level, ws.d_records, ws.d_scale_export, ws.d_tile_base,
+                                                     ws.d_normal_partial, lp);
     k_pair_end<<<1, 32, 0, st>>>(ws.d_state, ws.d_pair_level, ws.d_normal_partial, lp.ntiles, ws.d_active, lp, nullptr, 0);
     ctx->launches += 2;
   }
@@ -899,9 +912,13 @@ int tracker_linearize(dvo_b200_ctx* ctx, const dvo_b200_config* cfg, dvo_b200_py
     DVO_CUDA(ctx, cudaMemcpy(p0.data(), ref->planes + L.plane_off, sizeof(float) * 2 * N, cudaMemcpyDeviceToHost));
     ctx->d2h_bytes += sizeof(float) * 9 * N;
     const float nanv = std::numeric_limits<float>::quiet_NaN();
+    // scratch layout: float2 planes E = (e.i, e.z), G = (e.idx, e.idy), H = (e.zdx, e.zdy), then W
     for (size_t i = 0; i < N; ++i) {
-      bool valid = rec[i] == rec[i];
-      for (int k = 0; k < 6; ++k) planes7[k * N + i] = valid ? rec[k * N + i] : nanv;
+      bool valid = rec[2 * i] == rec[2 * i];
+      for (int pl = 0; pl < 3; ++pl) {
+        planes7[(2 * pl) * N + i] = valid ? rec[pl * 2 * N + 2 * i] : nanv;
+        planes7[(2 * pl + 1) * N + i] = valid ? rec[pl * 2 * N + 2 * i + 1] : nanv;
+      }
       planes7[6 * N + i] = valid ? p0[2 * i + 1] : nanv;
     }
   }
