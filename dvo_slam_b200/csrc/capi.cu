@@ -2,6 +2,7 @@
 #include "common.cuh"
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 
@@ -87,6 +88,10 @@ int dvo_b200_create(int device, void* stream, dvo_b200_ctx** out) {
   else {
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); delete ctx; return DVO_B200_ERR_CUDA; }
     ctx->own_stream = true;
+  }
+  if (getenv("DVO_B200_TIMING")) {
+    cudaMalloc((void**)&ctx->d_dbg, sizeof(unsigned long long) * 64);
+    cudaMemset(ctx->d_dbg, 0, sizeof(unsigned long long) * 64);
   }
   *out = ctx;
   return 0;
@@ -294,6 +299,19 @@ int dvo_b200_profile_read(dvo_b200_ctx* ctx, double ms_out[8], int64_t launches_
   if (!ctx) return DVO_B200_ERR_INVALID_ARGUMENT;
   cudaSetDevice(ctx->device);
   drain_profile(ctx);
+  if (ctx->d_dbg) {   // developer timing dump (DVO_B200_TIMING=1)
+    unsigned long long h[64];
+    cudaStreamSynchronize(ctx->stream);
+    cudaMemcpy(h, ctx->d_dbg, sizeof(h), cudaMemcpyDeviceToHost);
+    static const char* names[8] = {"stageA", "stageB", "waitA", "waitB", "mid", "end", "queue", "total"};
+    for (int l = 0; l < 8; ++l) {
+      if (!h[8 * l + 7]) continue;
+      fprintf(stderr, "[dvo_b200 timing] level-slot %d:", l);
+      for (int i = 0; i < 8; ++i) fprintf(stderr, " %s=%.1f%%", names[i], 100.0 * (double)h[8 * l + i] / (double)h[8 * l + 7]);
+      fprintf(stderr, " (cta-ms total %.1f)\n", (double)h[8 * l + 7] * 1e-6);
+    }
+    if (reset) cudaMemset(ctx->d_dbg, 0, sizeof(h));
+  }
   for (int i = 0; i < 8; ++i) {
     if (ms_out) ms_out[i] = ctx->prof_ms[i];
     if (launches_out) launches_out[i] = ctx->prof_launches[i];

@@ -133,6 +133,7 @@ struct Workspace {              // per-ctx scratch for a lock-step batch
 struct dvo_b200_ctx {
   int device = 0;
   int num_sms = 0, ctas_per_sm = 0;   // persistent-kernel grid geometry (queried once)
+  unsigned long long* d_dbg = nullptr;   // DVO_B200_TIMING=1: per-level phase timers of the persistent kernel (64 slots)
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   std::string last_error;

@@ -75,8 +75,8 @@ struct RefPixel {
 __device__ __forceinline__ RefPixel load_ref_pixel(const PairLevel& pl, int idx, int w, unsigned wmagic, int n) {
   RefPixel r;
   const int i = min(idx, n - 1);                   // lanes past the end of the image read a valid address
-  r.a = ldg_f2(pl.r0 + i);
-  r.g = ldg_f2(pl.r1 + i);
+  { const float2 v = __ldcs(pl.r0 + i); r.a = pk(v.x, v.y); }   // reference planes are streamed once per iteration
+  { const float2 v = __ldcs(pl.r1 + i); r.g = pk(v.x, v.y); }
   const int y = (int)__umulhi((unsigned)i, wmagic);   // i / w (exact for i*w < 2^32)
   const int x = i - y * w;
   r.tx = __ldg(pl.rtmpl + x);
@@ -84,49 +84,72 @@ __device__ __forceinline__ RefPixel load_ref_pixel(const PairLevel& pl, int idx,
   return r;
 }
 
-// The residual record of one reference pixel (computeResidualsSse, dense_tracking_impl.cpp:133-393):
-//   point (x,y,z) = (tx*z, ty*z, z); (X,Y,Z') = fma chains over the rows of K*T; (u,v) = (X,Y)*rcp_rn(Z')
-//   bounds 0<=u<=w-2, 0<=v<=h-2; truncation; bilinear blend of the six channels (three float2 planes)
-//   residual weights of dense_tracking.cpp:215-220; occlusion test of line 275.
-// Branch-free: every lane issues its twelve tap loads at once (a rejected point reads tap 0), the
-// verdict is returned.  E = (e.i, e.z), G = (e.idx, e.idy), H = (e.zdx, e.zdy).
-__device__ __forceinline__ bool pixel_record(const RefPixel& r, bool selected, int w, const PairLevel& pl, const StageConsts& c,
-                                             f2& E, f2& G, f2& H) {
+// The residual record of one reference pixel (computeResidualsSse, dense_tracking_impl.cpp:133-393) is
+// computed in three steps so that the twelve bilinear taps of round r+1 are in flight while round r
+// is blended:
+//   project_pixel : point (x,y,z) = (tx*z, ty*z, z); (X,Y,Z') = fma chains over the rows of K*T;
+//                   (u,v) = (X,Y)*rcp_rn(Z'); bounds 0<=u<=w-2, 0<=v<=h-2; truncation -> tap index, weights
+//   load_taps     : the four neighbours in the three float2 planes of the current image
+//   finish_pixel  : bilinear blend, residual weights of dense_tracking.cpp:215-220, NaN test (line 261),
+//                   occlusion test (line 275).  E = (e.i, e.z), G = (e.idx, e.idy), H = (e.zdx, e.zdy).
+// Branch-free: a rejected point reads tap 0 and is flagged invalid.
+struct PixelProjection {
+  f2 f, gq;        // (fu, fv), (gu, gv)
+  f2 g;            // (Ix_r, Iy_r)
+  float Zt, z, Ir;
+  int b;           // index of the upper-left tap
+  bool inb;
+};
+struct PixelTaps {
+  f2 p00, p10, p01, p11, q00, q10, q01, q11, s00, s10, s01, s11;
+};
+
+__device__ __forceinline__ PixelProjection project_pixel(const RefPixel& r, bool selected, int w, const StageConsts& c) {
+  PixelProjection p;
   const float z = hi(r.a);
   const f2 pxy = mul2(pk(r.tx, r.ty), bc(z));
   const float px = lo(pxy), py = hi(pxy);
   const f2 XY = fma2(c.k0, bc(px), fma2(c.k1, bc(py), fma2(c.k2, bc(z), c.k3)));
-  const float Zt = __fmaf_rn(c.k8, px, __fmaf_rn(c.k9, py, __fmaf_rn(c.k10, z, c.k11)));
-  f2 uv = mul2(XY, bc(rcp_rn(Zt)));
+  p.Zt = __fmaf_rn(c.k8, px, __fmaf_rn(c.k9, py, __fmaf_rn(c.k10, z, c.k11)));
+  f2 uv = mul2(XY, bc(rcp_rn(p.Zt)));
   const float u = lo(uv), v = hi(uv);
-  const bool inb = selected && u >= 0.f && u <= c.ubx && v >= 0.f && v <= c.uby;   // NaN compares false
-  uv = inb ? uv : 0ull;
+  p.inb = selected && u >= 0.f && u <= c.ubx && v >= 0.f && v <= c.uby;   // NaN compares false
+  uv = p.inb ? uv : 0ull;
   // truncation without conversions: for 0 <= t < 2^23, RZ(t + 2^23) carries floor(t) in its mantissa
   const f2 t = add2_rz(uv, bc(8388608.0f));
-  const f2 f = sub2(uv, sub2(t, bc(8388608.0f)));   // (fu, fv)
-  const f2 gq = sub2(bc(1.0f), f);                   // (gu, gv)
+  p.f = sub2(uv, sub2(t, bc(8388608.0f)));
+  p.gq = sub2(bc(1.0f), p.f);
   const int u0 = __float_as_int(lo(t)) - 0x4b000000, v0 = __float_as_int(hi(t)) - 0x4b000000;
-  const float fu = lo(f), fv = hi(f), gu = lo(gq), gv = hi(gq);
-  const int b = v0 * w + u0;
-  const f2 p00 = ldg_f2(pl.c0 + b), p10 = ldg_f2(pl.c0 + b + 1), p01 = ldg_f2(pl.c0 + b + w), p11 = ldg_f2(pl.c0 + b + w + 1);
-  const f2 q00 = ldg_f2(pl.c1 + b), q10 = ldg_f2(pl.c1 + b + 1), q01 = ldg_f2(pl.c1 + b + w), q11 = ldg_f2(pl.c1 + b + w + 1);
-  const f2 s00 = ldg_f2(pl.c2 + b), s10 = ldg_f2(pl.c2 + b + 1), s01 = ldg_f2(pl.c2 + b + w), s11 = ldg_f2(pl.c2 + b + w + 1);
+  p.b = v0 * w + u0;
+  p.g = r.g; p.z = z; p.Ir = lo(r.a);
+  return p;
+}
+
+__device__ __forceinline__ PixelTaps load_taps(const PairLevel& pl, int b, int w) {
+  PixelTaps t;
+  t.p00 = ldg_f2(pl.c0 + b); t.p10 = ldg_f2(pl.c0 + b + 1); t.p01 = ldg_f2(pl.c0 + b + w); t.p11 = ldg_f2(pl.c0 + b + w + 1);
+  t.q00 = ldg_f2(pl.c1 + b); t.q10 = ldg_f2(pl.c1 + b + 1); t.q01 = ldg_f2(pl.c1 + b + w); t.q11 = ldg_f2(pl.c1 + b + w + 1);
+  t.s00 = ldg_f2(pl.c2 + b); t.s10 = ldg_f2(pl.c2 + b + 1); t.s01 = ldg_f2(pl.c2 + b + w); t.s11 = ldg_f2(pl.c2 + b + w + 1);
+  return t;
+}
+
+__device__ __forceinline__ bool finish_pixel(const PixelProjection& p, const PixelTaps& t, const StageConsts& c, f2& E, f2& G, f2& H) {
+  const float fu = lo(p.f), fv = hi(p.f), gu = lo(p.gq), gv = hi(p.gq);
 #define DVO_BLEND2(c00, c10, c01, c11) \
   fma2(bc(fv), fma2(bc(fu), c11, mul2(bc(gu), c01)), mul2(bc(gv), fma2(bc(fu), c10, mul2(bc(gu), c00))))
-  const f2 IZ = DVO_BLEND2(p00, p10, p01, p11);
-  const f2 Gc = DVO_BLEND2(q00, q10, q01, q11);
-  const f2 Hc = DVO_BLEND2(s00, s10, s01, s11);
+  const f2 IZ = DVO_BLEND2(t.p00, t.p10, t.p01, t.p11);
+  const f2 Gc = DVO_BLEND2(t.q00, t.q10, t.q01, t.q11);
+  const f2 Hc = DVO_BLEND2(t.s00, t.s10, t.s01, t.s11);
 #undef DVO_BLEND2
   const float Zc = hi(IZ);
-  const float ez = __fsub_rn(Zc, Zt);
-  const float s = __fsub_rn(z, 0.4f);
+  const float ez = __fsub_rn(Zc, p.Zt);
+  const float s = __fsub_rn(p.z, 0.4f);
   const float sig = __fmaf_rn(__fmul_rn(0.0019f, s), s, 0.0012f);    // depthStdDevZ (lines 122-128)
-  const float ei = __fmaf_rn(c.c_i, lo(IZ), __fmul_rn(-c.c_i, lo(r.a)));
+  const float ei = __fmaf_rn(c.c_i, lo(IZ), __fmul_rn(-c.c_i, p.Ir));
   E = pk(ei, ez);
-  G = fma2(c.cg, Gc, mul2(c.cg, r.g));
+  G = fma2(c.cg, Gc, mul2(c.cg, p.g));
   H = mul2(c.fxy, Hc);
-  // masked depth NaN = any NaN lane of the reference's 8-vector (line 261); occlusion test (line 275)
-  return inb && Zc == Zc && ez > __fmul_rn(-20.0f, sig);
+  return p.inb && Zc == Zc && ez > __fmul_rn(-20.0f, sig);
 }
 
 // ---- pairwise scale sum ---------------------------------------------------------------------------
@@ -214,122 +237,142 @@ __device__ __forceinline__ float student_weight(const StageConsts& c, float ei, 
 __device__ __forceinline__ void store_record(const RecordPlanes& rec, int idx, int n, bool valid, f2 E, f2 G, f2 H, float wgt) {
   if (idx < n) {
     if (valid) {
-      rec.E[idx] = make_float2(lo(E), hi(E));
-      rec.G[idx] = make_float2(lo(G), hi(G));
-      rec.H[idx] = make_float2(lo(H), hi(H));
-      rec.W[idx] = wgt;
+      __stcs(rec.E + idx, make_float2(lo(E), hi(E)));    // st.global.cs: streamed, evict-first in L2
+      __stcs(rec.G + idx, make_float2(lo(G), hi(G)));
+      __stcs(rec.H + idx, make_float2(lo(H), hi(H)));
+      __stcs(rec.W + idx, wgt);
     } else {
       const float nanf_ = __int_as_float(0x7fc00000);
-      rec.E[idx] = make_float2(nanf_, nanf_);
+      __stcs(rec.E + idx, make_float2(nanf_, nanf_));
     }
   }
 }
 
+// Running state of the pairwise scale sum of one warp segment (see the comment above SegT).
+struct ScaleState {
+  float sall0, sall1, sall2, salt0, salt1, salt2;
+  float pw, po0, po1, po2;   // pending leader: the last valid point seen, waiting for the next valid weight
+  float wfirst;
+  int psign, cnt;
+  bool pend;
+};
+
+__device__ __forceinline__ void scale_state_init(ScaleState& s) {
+  s.sall0 = s.sall1 = s.sall2 = s.salt0 = s.salt1 = s.salt2 = 0.f;
+  s.pw = s.po0 = s.po1 = s.po2 = 0.f; s.wfirst = 0.f; s.psign = 0; s.cnt = 0; s.pend = false;
+}
+
+// Adds the 64 points {pixel base+lane: (v0, w0, ei0, ez0)} then {pixel base+32+lane: (v1, ...)} to the state.
+__device__ __forceinline__ void scale_round64(ScaleState& st, int lane, bool v0, float w0, float ei0, float ez0,
+                                              bool v1, float w1, float ei1, float ez1) {
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const unsigned m0 = __ballot_sync(kFullMask, v0), m1 = __ballot_sync(kFullMask, v1);
+  if ((m0 | m1) == 0u) return;
+  const float w1_first = __shfl_sync(kFullMask, w1, m1 ? __ffs(m1) - 1 : 0);        // first valid weight of the upper half
+  const float w_first = m0 ? __shfl_sync(kFullMask, w0, __ffs(m0) - 1) : w1_first;   // first valid weight of the round
+  if (st.cnt == 0) st.wfirst = w_first;
+  {   // the pending leader of an earlier round pairs with the first valid point of this round
+    const float s = st.pend ? st.pw + w_first : 0.f;
+    const float sa = __int_as_float(__float_as_int(s) ^ st.psign);
+    st.sall0 = fmaf(s, st.po0, st.sall0); st.sall1 = fmaf(s, st.po1, st.sall1); st.sall2 = fmaf(s, st.po2, st.sall2);
+    st.salt0 = fmaf(sa, st.po0, st.salt0); st.salt1 = fmaf(sa, st.po1, st.salt1); st.salt2 = fmaf(sa, st.po2, st.salt2);
+  }
+  const unsigned above0 = (m0 >> lane) >> 1, above1 = (m1 >> lane) >> 1;
+  float wn0 = __shfl_sync(kFullMask, w0, above0 ? lane + __ffs(above0) : lane);
+  const float wn1 = __shfl_sync(kFullMask, w1, above1 ? lane + __ffs(above1) : lane);
+  wn0 = above0 ? wn0 : w1_first;
+  const bool next0 = above0 != 0u || m1 != 0u, next1 = above1 != 0u;
+  const int c0n = __popc(m0);
+  const int sg0 = ((st.cnt + __popc(m0 & lt_mask)) & 1) << 31;          // sign bit set for odd rank
+  const int sg1 = ((st.cnt + c0n + __popc(m1 & lt_mask)) & 1) << 31;
+  // rejected points carry garbage (possibly NaN) residuals: zero them so that 0 * outer stays 0
+  const float xi0 = v0 ? ei0 : 0.f, xz0 = v0 ? ez0 : 0.f, xi1 = v1 ? ei1 : 0.f, xz1 = v1 ? ez1 : 0.f;
+  const float a0 = xi0 * xi0, a1 = xi0 * xz0, a2 = xz0 * xz0;
+  const float b0 = xi1 * xi1, b1 = xi1 * xz1, b2 = xz1 * xz1;
+  {
+    const float s = (v0 && next0) ? w0 + wn0 : 0.f;
+    const float sa = __int_as_float(__float_as_int(s) ^ sg0);
+    st.sall0 = fmaf(s, a0, st.sall0); st.sall1 = fmaf(s, a1, st.sall1); st.sall2 = fmaf(s, a2, st.sall2);
+    st.salt0 = fmaf(sa, a0, st.salt0); st.salt1 = fmaf(sa, a1, st.salt1); st.salt2 = fmaf(sa, a2, st.salt2);
+  }
+  {
+    const float s = (v1 && next1) ? w1 + wn1 : 0.f;
+    const float sa = __int_as_float(__float_as_int(s) ^ sg1);
+    st.sall0 = fmaf(s, b0, st.sall0); st.sall1 = fmaf(s, b1, st.sall1); st.sall2 = fmaf(s, b2, st.sall2);
+    st.salt0 = fmaf(sa, b0, st.salt0); st.salt1 = fmaf(sa, b1, st.salt1); st.salt2 = fmaf(sa, b2, st.salt2);
+  }
+  // new pending leader: the last valid point of the round
+  const bool np1 = v1 && !next1, np0 = v0 && !next0;
+  st.pend = np0 || np1;
+  st.pw = np1 ? w1 : (np0 ? w0 : st.pw);
+  st.po0 = np1 ? b0 : (np0 ? a0 : st.po0); st.po1 = np1 ? b1 : (np0 ? a1 : st.po1); st.po2 = np1 ? b2 : (np0 ? a2 : st.po2);
+  st.psign = np1 ? sg1 : (np0 ? sg0 : st.psign);
+  st.cnt += c0n + __popc(m1);
+}
+
+// warp-reduce the sums and write the segment summary (kSegExportFloats floats)
+__device__ __forceinline__ void scale_state_export(ScaleState& st, int lane, float* seg_out) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    st.sall0 += __shfl_xor_sync(kFullMask, st.sall0, off); st.sall1 += __shfl_xor_sync(kFullMask, st.sall1, off);
+    st.sall2 += __shfl_xor_sync(kFullMask, st.sall2, off); st.salt0 += __shfl_xor_sync(kFullMask, st.salt0, off);
+    st.salt1 += __shfl_xor_sync(kFullMask, st.salt1, off); st.salt2 += __shfl_xor_sync(kFullMask, st.salt2, off);
+  }
+  // leaders at even local rank belong to hypothesis 0, odd to hypothesis 1: S0 = (all + alt)/2, S1 = (all - alt)/2
+  if (lane == 0) {
+    seg_out[0] = __int_as_float(st.cnt);
+    seg_out[1] = 0.5f * (st.sall0 + st.salt0); seg_out[2] = 0.5f * (st.sall1 + st.salt1); seg_out[3] = 0.5f * (st.sall2 + st.salt2);
+    seg_out[4] = 0.5f * (st.sall0 - st.salt0); seg_out[5] = 0.5f * (st.sall1 - st.salt1); seg_out[6] = 0.5f * (st.sall2 - st.salt2);
+    seg_out[7] = st.wfirst;
+    if (st.cnt == 0) { seg_out[8] = 0.f; seg_out[9] = 0.f; seg_out[10] = 0.f; seg_out[11] = 0.f; }
+  }
+  if (st.pend) {   // exactly one lane when cnt > 0: the last valid point of the segment
+    seg_out[8] = st.pw; seg_out[9] = st.po0; seg_out[10] = st.po1; seg_out[11] = st.po2;
+  }
+}
+
 // Stage A over the pixels [begin, end) of one pair (begin a multiple of 32): writes the residual
-// records and the segment summary (kSegExportFloats floats at `seg_out`).  The warp walks 64 pixels
-// per round, two per lane (base + lane and base + 32 + lane), with the reference-side loads of the
-// next round issued before the current round's taps are consumed.
+// records and the segment summary (kSegExportFloats floats at `seg_out`).  The warp walks 32 pixels per
+// round as a two-deep software pipeline: while round r is blended, the twelve taps of round r+1 and the
+// reference-side loads of round r+2 are in flight.  The pairwise scale sum runs once per two rounds.
 __device__ __forceinline__ void stage_a_segment(const PairLevel& pl, const StageConsts& c, int w, unsigned wmagic, int n,
                                                 int begin, int end, const RecordPlanes& rec, float* seg_out) {
   const int lane = threadIdx.x & 31;
-  const unsigned lt_mask = (1u << lane) - 1u;
-  float sall0 = 0.f, sall1 = 0.f, sall2 = 0.f, salt0 = 0.f, salt1 = 0.f, salt2 = 0.f;
-  // the last valid lane seen so far keeps its own point as "pending leader" until the next valid weight is known
-  bool pend = false;
-  float pw = 0.f, po0 = 0.f, po1 = 0.f, po2 = 0.f;
-  int psign = 0;
-  int cnt = 0;
-  float wfirst = 0.f;
+  ScaleState ss;
+  scale_state_init(ss);
   if (begin < end) {
-    RefPixel r0 = load_ref_pixel(pl, begin + lane, w, wmagic, n);
-    RefPixel r1 = load_ref_pixel(pl, begin + 32 + lane, w, wmagic, n);
-    unsigned sel0 = __ldg(pl.rmask + (begin >> 5));
-    unsigned sel1 = begin + 32 < end ? __ldg(pl.rmask + (begin >> 5) + 1) : 0u;
+    // prologue: project round 0 and issue its taps, load the reference data of round 1
+    RefPixel ref = load_ref_pixel(pl, begin + lane, w, wmagic, n);
+    unsigned sel = __ldg(pl.rmask + (begin >> 5));
+    PixelProjection proj = project_pixel(ref, ((sel >> lane) & 1u) && (begin + lane) != c.drop_idx, w, c);
+    PixelTaps taps = load_taps(pl, proj.b, w);
+    ref = load_ref_pixel(pl, begin + 32 + lane, w, wmagic, n);
+    sel = begin + 32 < end ? __ldg(pl.rmask + (begin >> 5) + 1) : 0u;
+    bool sv = false; float sw = 0.f, sei = 0.f, sez = 0.f;   // stashed even round
+    bool odd = false;
 #pragma unroll 1
-    for (int base = begin; base < end; base += 64) {
-      const int i0 = base + lane, i1 = base + 32 + lane;
-      const RefPixel c0 = r0, c1 = r1;
-      const bool s0 = ((sel0 >> lane) & 1u) && i0 != c.drop_idx;
-      const bool s1 = ((sel1 >> lane) & 1u) && i1 != c.drop_idx;
-      const int nb = base + 64;
-      if (nb < end) {   // warp-uniform: prefetch the next round's reference data
-        r0 = load_ref_pixel(pl, nb + lane, w, wmagic, n);
-        r1 = load_ref_pixel(pl, nb + 32 + lane, w, wmagic, n);
-        sel0 = __ldg(pl.rmask + (nb >> 5));
-        sel1 = nb + 32 < end ? __ldg(pl.rmask + (nb >> 5) + 1) : 0u;
+    for (int base = begin; base < end; base += 32) {
+      const PixelProjection pcur = proj;
+      const PixelTaps tcur = taps;
+      const int nb = base + 32;
+      if (nb < end) {   // warp-uniform
+        proj = project_pixel(ref, ((sel >> lane) & 1u) && (nb + lane) != c.drop_idx, w, c);
+        taps = load_taps(pl, proj.b, w);
+        ref = load_ref_pixel(pl, nb + 32 + lane, w, wmagic, n);
+        sel = nb + 32 < end ? __ldg(pl.rmask + (nb >> 5) + 1) : 0u;
       }
-      f2 E0, G0, H0, E1, G1, H1;
-      const bool v0 = pixel_record(c0, s0, w, pl, c, E0, G0, H0);
-      const bool v1 = pixel_record(c1, s1, w, pl, c, E1, G1, H1);
-      const float ei0 = lo(E0), ez0 = hi(E0), ei1 = lo(E1), ez1 = hi(E1);
-      const float w0 = student_weight(c, ei0, ez0), w1 = student_weight(c, ei1, ez1);
-      store_record(rec, i0, end, v0, E0, G0, H0, w0);   // end <= n: never touch another warp's pixels
-      store_record(rec, i1, end, v1, E1, G1, H1, w1);
-
-      // ---- pairwise scale sums over the 64 points of this round (bit i of m0 = pixel base+i, of m1 = base+32+i) ----
-      const unsigned m0 = __ballot_sync(kFullMask, v0), m1 = __ballot_sync(kFullMask, v1);
-      if (m0 | m1) {
-        const float w1_first = __shfl_sync(kFullMask, w1, m1 ? __ffs(m1) - 1 : 0);        // first valid weight of the upper half
-        const float w_first = m0 ? __shfl_sync(kFullMask, w0, __ffs(m0) - 1) : w1_first;   // first valid weight of the round
-        if (cnt == 0) wfirst = w_first;
-        // the pending leader of an earlier round pairs with the first valid point of this round
-        {
-          const float s = pend ? pw + w_first : 0.f;
-          const float sa = __int_as_float(__float_as_int(s) ^ psign);
-          sall0 = fmaf(s, po0, sall0); sall1 = fmaf(s, po1, sall1); sall2 = fmaf(s, po2, sall2);
-          salt0 = fmaf(sa, po0, salt0); salt1 = fmaf(sa, po1, salt1); salt2 = fmaf(sa, po2, salt2);
-        }
-        const unsigned above0 = (m0 >> lane) >> 1, above1 = (m1 >> lane) >> 1;
-        float wn0 = __shfl_sync(kFullMask, w0, above0 ? lane + __ffs(above0) : lane);
-        const float wn1 = __shfl_sync(kFullMask, w1, above1 ? lane + __ffs(above1) : lane);
-        wn0 = above0 ? wn0 : w1_first;
-        const bool next0 = above0 != 0u || m1 != 0u, next1 = above1 != 0u;
-        const int c0n = __popc(m0);
-        const int sg0 = ((cnt + __popc(m0 & lt_mask)) & 1) << 31;          // sign bit set for odd rank
-        const int sg1 = ((cnt + c0n + __popc(m1 & lt_mask)) & 1) << 31;
-        // rejected points carry garbage (possibly NaN) residuals: zero them so that 0 * outer stays 0
-        const float xi0 = v0 ? ei0 : 0.f, xz0 = v0 ? ez0 : 0.f, xi1 = v1 ? ei1 : 0.f, xz1 = v1 ? ez1 : 0.f;
-        const float a0 = xi0 * xi0, a1 = xi0 * xz0, a2 = xz0 * xz0;
-        const float b0 = xi1 * xi1, b1 = xi1 * xz1, b2 = xz1 * xz1;
-        {
-          const float s = (v0 && next0) ? w0 + wn0 : 0.f;
-          const float sa = __int_as_float(__float_as_int(s) ^ sg0);
-          sall0 = fmaf(s, a0, sall0); sall1 = fmaf(s, a1, sall1); sall2 = fmaf(s, a2, sall2);
-          salt0 = fmaf(sa, a0, salt0); salt1 = fmaf(sa, a1, salt1); salt2 = fmaf(sa, a2, salt2);
-        }
-        {
-          const float s = (v1 && next1) ? w1 + wn1 : 0.f;
-          const float sa = __int_as_float(__float_as_int(s) ^ sg1);
-          sall0 = fmaf(s, b0, sall0); sall1 = fmaf(s, b1, sall1); sall2 = fmaf(s, b2, sall2);
-          salt0 = fmaf(sa, b0, salt0); salt1 = fmaf(sa, b1, salt1); salt2 = fmaf(sa, b2, salt2);
-        }
-        // new pending leader: the last valid point of the round
-        const bool np1 = v1 && !next1, np0 = v0 && !next0;
-        pend = np0 || np1;
-        pw = np1 ? w1 : (np0 ? w0 : pw);
-        po0 = np1 ? b0 : (np0 ? a0 : po0); po1 = np1 ? b1 : (np0 ? a1 : po1); po2 = np1 ? b2 : (np0 ? a2 : po2);
-        psign = np1 ? sg1 : (np0 ? sg0 : psign);
-        cnt += c0n + __popc(m1);
-      }
+      f2 E, G, H;
+      const bool v = finish_pixel(pcur, tcur, c, E, G, H);
+      const float ei = lo(E), ez = hi(E);
+      const float wgt = student_weight(c, ei, ez);
+      store_record(rec, base + lane, end, v, E, G, H, wgt);   // end <= n: never touch another warp's pixels
+      if (!odd) { sv = v; sw = wgt; sei = ei; sez = ez; }
+      else scale_round64(ss, lane, sv, sw, sei, sez, v, wgt, ei, ez);
+      odd = !odd;
     }
+    if (odd) scale_round64(ss, lane, sv, sw, sei, sez, false, 0.f, 0.f, 0.f);
   }
-  // leaders at even local rank belong to hypothesis 0, odd to hypothesis 1: S0 = (all + alt)/2, S1 = (all - alt)/2
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) {
-    sall0 += __shfl_xor_sync(kFullMask, sall0, off); sall1 += __shfl_xor_sync(kFullMask, sall1, off);
-    sall2 += __shfl_xor_sync(kFullMask, sall2, off); salt0 += __shfl_xor_sync(kFullMask, salt0, off);
-    salt1 += __shfl_xor_sync(kFullMask, salt1, off); salt2 += __shfl_xor_sync(kFullMask, salt2, off);
-  }
-  if (lane == 0) {
-    seg_out[0] = __int_as_float(cnt);
-    seg_out[1] = 0.5f * (sall0 + salt0); seg_out[2] = 0.5f * (sall1 + salt1); seg_out[3] = 0.5f * (sall2 + salt2);
-    seg_out[4] = 0.5f * (sall0 - salt0); seg_out[5] = 0.5f * (sall1 - salt1); seg_out[6] = 0.5f * (sall2 - salt2);
-    seg_out[7] = wfirst;
-    if (cnt == 0) { seg_out[8] = 0.f; seg_out[9] = 0.f; seg_out[10] = 0.f; seg_out[11] = 0.f; }
-  }
-  if (pend) {   // exactly one lane when cnt > 0: the last valid point of the segment
-    seg_out[8] = pw; seg_out[9] = po0; seg_out[10] = po1; seg_out[11] = po2;
-  }
+  scale_state_export(ss, lane, seg_out);
 }
 
 // ---- stage B -----------------------------------------------------------------------------------------
@@ -380,17 +423,44 @@ __device__ __forceinline__ void stage_b_rank1(StageBAcc& acc, const f2 V[3], flo
 // so each point contributes two rank-1 updates.  J rows at the untransformed reference point
 // (dense_tracking.cpp:448-476): J0 = gx a + gy b, J1 = hx a + hy b - c with
 //   a = [1/z, 0, -x/z^2, a2 y, 1 - a2 x, -y/z], b = [0, 1/z, -y/z^2, b2 y - 1, -a3, x/z], c = [0, 0, 1, y, -x, 0].
+struct StageBInput {   // everything stage B reads for one pixel; loaded two rounds ahead of its use
+  float2 e, g, h;
+  float w, z, tx, ty;
+};
+
+__device__ __forceinline__ StageBInput load_stage_b_input(const PairLevel& pl, const RecordPlanes& rec, int idx, int w,
+                                                          unsigned wmagic, int limit) {
+  StageBInput in;
+  const int i = min(idx, limit - 1);
+  in.e = __ldcs(rec.E + i);      // ld.global.cs: read once, do not keep in L2
+  in.g = __ldcs(rec.G + i);
+  in.h = __ldcs(rec.H + i);
+  in.w = __ldcs(rec.W + i);
+  in.z = __ldcs(pl.r0 + i).y;
+  const int y = (int)__umulhi((unsigned)i, wmagic);
+  const int x = i - y * w;
+  in.tx = __ldg(pl.rtmpl + x);
+  in.ty = __ldg(pl.rtmpl + w + y);
+  if (idx >= limit) in.e.x = __int_as_float(0x7fc00000);
+  return in;
+}
+
 __device__ __forceinline__ void stage_b_segment(const PairLevel& pl, const StageBConsts& c, int w, unsigned wmagic, int n,
                                                 int begin, int end, const RecordPlanes& rec, long long rank_base,
                                                 long long n_keep, bool need_rank, StageBAcc& acc) {
   const int lane = threadIdx.x & 31;
   const unsigned lt_mask = (1u << lane) - 1u;
   int seen = 0;
-#pragma unroll 2
+  if (begin >= end) return;
+  // software pipeline: the loads of rounds r+1 and r+2 are in flight while round r is consumed
+  StageBInput in0 = load_stage_b_input(pl, rec, begin + lane, w, wmagic, end);
+  StageBInput in1 = load_stage_b_input(pl, rec, begin + 32 + lane, w, wmagic, end);
+#pragma unroll 1
   for (int base = begin; base < end; base += 32) {
-    const int idx = base + lane;
-    float2 e = idx < n ? rec.E[idx] : make_float2(__int_as_float(0x7fc00000), 0.f);
-    const bool valid = e.x == e.x;
+    const StageBInput in = in0;
+    in0 = in1;
+    in1 = load_stage_b_input(pl, rec, base + 64 + lane, w, wmagic, end);
+    const bool valid = in.e.x == in.e.x;
     bool keep = valid;
     if (need_rank) {   // warp-uniform: only the segments that contain the tail of the point list
       const unsigned m = __ballot_sync(kFullMask, valid);
@@ -398,26 +468,22 @@ __device__ __forceinline__ void stage_b_segment(const PairLevel& pl, const Stage
       seen += __popc(m);
     }
     if (!valid) continue;
-    const float2 g2 = rec.G[idx], h2 = rec.H[idx];
-    const float wgt = rec.W[idx];
-    const float ei = e.x, ez = e.y;
+    const float ei = in.e.x, ez = in.e.y;
     // log-likelihood term: log(1 + 0.2 r^T P r), accumulated as a product
     const float d = (ei * c.P00 + ez * c.P10) * ei + (ei * c.P01 + ez * c.P11) * ez;
     if (keep) {
       acc.prod *= fmaf(0.2f, d, 1.0f);
       if (acc.prod > 1e18f) { acc.llsum += __logf(acc.prod); acc.prod = 1.0f; }   // keep the product in range
     }
-    const int y = (int)__umulhi((unsigned)idx, wmagic);
-    const int x = idx - y * w;
-    const float z = __ldg(pl.r0 + idx).y;
-    const float px = __ldg(pl.rtmpl + x) * z, py = __ldg(pl.rtmpl + w + y) * z;
+    const float z = in.z;
+    const float px = in.tx * z, py = in.ty * z;
     const float zi = rcp_fast(z), zs = zi * zi;
     const float a2 = -px * zs, b2 = -py * zs;
     const float a3 = a2 * py;
     const f2 A23 = pk(a2, a3), B23 = pk(b2, fmaf(b2, py, -1.0f));
     const f2 A45 = pk(fmaf(-a2, px, 1.0f), -py * zi), B45 = pk(-a3, px * zi);
     const f2 NC23 = pk(-1.0f, -py), NC45 = pk(px, 0.0f);     // -c[2..3], -c[4..5]
-    const f2 G = pk(g2.x, g2.y), H = pk(h2.x, h2.y);
+    const f2 G = pk(in.g.x, in.g.y), H = pk(in.h.x, in.h.y);
     const f2 Gp = fma2(bc(c.l), H, G);                        // (gx + l hx, gy + l hy)
     const float gx = lo(Gp), gy = hi(Gp);
     f2 V0[3], V1[3];
@@ -425,11 +491,11 @@ __device__ __forceinline__ void stage_b_segment(const PairLevel& pl, const Stage
     V0[1] = fma2(bc(gx), A23, fma2(bc(gy), B23, mul2(bc(c.l), NC23)));
     V0[2] = fma2(bc(gx), A45, fma2(bc(gy), B45, mul2(bc(c.l), NC45)));
     V1[0] = mul2(H, bc(zi));
-    V1[1] = fma2(bc(h2.x), A23, fma2(bc(h2.y), B23, NC23));
-    V1[2] = fma2(bc(h2.x), A45, fma2(bc(h2.y), B45, NC45));
+    V1[1] = fma2(bc(in.h.x), A23, fma2(bc(in.h.y), B23, NC23));
+    V1[2] = fma2(bc(in.h.x), A45, fma2(bc(in.h.y), B45, NC45));
     // b -= J^T W r
-    stage_b_rank1(acc, V0, wgt * c.wd0, -fmaf(c.l, ez, ei));
-    stage_b_rank1(acc, V1, wgt * c.wd1, -ez);
+    stage_b_rank1(acc, V0, in.w * c.wd0, -fmaf(c.l, ez, ei));
+    stage_b_rank1(acc, V1, in.w * c.wd1, -ez);
   }
 }
 

@@ -395,9 +395,16 @@ struct PersistentArgs {
   int* error_flag;
   dvo_b200_iteration_stats* ilog;
   int max_log;
+  unsigned long long* dbg;   // optional: ns spent per CTA in {stage A, stage B, wait A, wait B, mid, end, queue, total}
   int npairs, g, squads_per_slot, num_sms, rpw, nseg;
   LevelLaunch lp;
 };
+
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
 
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
   unsigned v;
@@ -462,8 +469,14 @@ k_level_persistent(PersistentArgs a) {
   const int r0 = min(wk * a.rpw, R), r1 = min(r0 + a.rpw, R);
   const int begin = r0 * 32, end = min(r1 * 32, lp.n);
   unsigned episode = 0;
+  unsigned long long t_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t0 = 0, t1 = 0;
+  const bool timing = a.dbg != nullptr && threadIdx.x == 0;
+  const unsigned long long t_start = timing ? global_ns() : 0;
+#define DVO_TICK() do { if (timing) t0 = global_ns(); } while (0)
+#define DVO_TOCK(slot) do { if (timing) { t1 = global_ns(); t_acc[slot] += t1 - t0; t0 = t1; } } while (0)
 
   for (;;) {
+    DVO_TICK();
     // ---- take the next pair from the queue (the last CTA to arrive does it for the squad) ----
     if (squad_arrive(sq, episode, a.g, s_flag)) {
       if (threadIdx.x == 0) {
@@ -476,6 +489,7 @@ k_level_persistent(PersistentArgs a) {
     }
     __syncthreads();
     ++episode;
+    DVO_TOCK(6);
     const int pair = __ldcg(&sq->pair);
     if (pair < 0 || *reinterpret_cast<volatile int*>(a.error_flag)) break;
     PairState& st = a.states[pair];
@@ -490,13 +504,18 @@ k_level_persistent(PersistentArgs a) {
         __syncthreads();
         if (threadIdx.x == 0) cta_export_segments(sm_exp, exports + (size_t)rank * kCtaExportFloats);
       }
+      DVO_TOCK(0);
       if (squad_arrive(sq, episode, a.g, s_flag)) {
+        DVO_TOCK(2);
         if (warp == 0) {
           pair_mid_warp(st, pair, exports, segbase, a.g, nullptr, lp, a.ilog, a.max_log, sm_mid);
           if (lane == 0) squad_release(sq, episode);
         }
+        __syncthreads();
+        DVO_TOCK(4);
       } else {
         squad_wait(sq, episode, a.error_flag);
+        DVO_TOCK(2);
       }
       __syncthreads();
       ++episode;
@@ -531,20 +550,31 @@ k_level_persistent(PersistentArgs a) {
           partial[(size_t)rank * kNormalValues + threadIdx.x] = s;
         }
       }
+      DVO_TOCK(1);
       if (squad_arrive(sq, episode, a.g, s_flag)) {
+        DVO_TOCK(3);
         if (warp == 0) {
           pair_end_warp(st, pl, pair, partial, a.g, nullptr, lp, a.ilog, a.max_log);
           __syncwarp();
           if (lane == 0) squad_release(sq, episode);
         }
+        __syncthreads();
+        DVO_TOCK(5);
       } else {
         squad_wait(sq, episode, a.error_flag);
+        DVO_TOCK(3);
       }
       __syncthreads();
       ++episode;
       if (!__ldcg(&st.level_active) || *reinterpret_cast<volatile int*>(a.error_flag)) break;
     }
   }
+  if (timing) {
+    t_acc[7] = global_ns() - t_start;
+    for (int i = 0; i < 8; ++i) atomicAdd(a.dbg + i, t_acc[i]);
+  }
+#undef DVO_TICK
+#undef DVO_TOCK
 }
 
 // Result assembly (dense_tracking.cpp:368-373)
@@ -795,6 +825,7 @@ int tracker_match_batch(dvo_b200_ctx* ctx, const dvo_b200_config* cfg, int n, dv
     int* tail = reinterpret_cast<int*>(pa.squads + plan.nsquads);
     pa.next_pair = tail; pa.error_flag = tail + 1;
     pa.ilog = ws.d_iter_log; pa.max_log = max_log;
+    pa.dbg = ctx->d_dbg ? ctx->d_dbg + 8 * li : nullptr;
     pa.npairs = n; pa.g = plan.g; pa.squads_per_slot = plan.squads_per_slot; pa.num_sms = ctx->num_sms; pa.rpw = plan.rpw;
     pa.nseg = plan.nseg; pa.lp = lp;
     {

@@ -1,0 +1,63 @@
+// selftest.cpp -- exercises the adapter exactly the way dvo_benchmark / LocalTracker use dvo_core:
+// RgbdCameraPyramid::create -> two DenseTracker::match calls on a shared current image
+// (benchmark_slam.cpp:392,483-488; local_tracker.cpp:172-184).  Reads a raw float32 pair written by
+// tests/test_host_adapter.py, prints the resulting pose as JSON.  Exit 3 = no CUDA device.
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <iostream>
+#include <vector>
+
+#include "dvo/dense_tracking.h"
+
+static cv::Mat load_plane(std::ifstream& f, int w, int h) {
+  cv::Mat m(h, w, CV_32FC1);
+  f.read(reinterpret_cast<char*>(m.ptr<float>()), sizeof(float) * size_t(w) * h);
+  return m;
+}
+
+int main(int argc, char** argv) {
+  if (argc < 8) { std::fprintf(stderr, "usage: selftest pair.bin w h fx fy ox oy [first last]\n"); return 2; }
+  const int w = std::atoi(argv[2]), h = std::atoi(argv[3]);
+  dvo::core::IntrinsicMatrix K = dvo::core::IntrinsicMatrix::create(float(std::atof(argv[4])), float(std::atof(argv[5])), float(std::atof(argv[6])), float(std::atof(argv[7])));
+  std::ifstream f(argv[1], std::ios::binary);
+  if (!f) { std::fprintf(stderr, "cannot open %s\n", argv[1]); return 2; }
+  cv::Mat Ir = load_plane(f, w, h), Zr = load_plane(f, w, h), Ic = load_plane(f, w, h), Zc = load_plane(f, w, h);
+
+  dvo::core::RgbdCameraPyramid camera(w, h, K);
+  dvo::core::RgbdImagePyramidPtr reference = camera.create(Ir, Zr), current = camera.create(Ic, Zc);
+
+  dvo::DenseTracker::Config cfg = dvo::DenseTracker::getDefaultConfig();
+  cfg.FirstLevel = argc > 8 ? std::atoi(argv[8]) : 3;
+  cfg.LastLevel = argc > 9 ? std::atoi(argv[9]) : 1;
+  cfg.MaxIterationsPerLevel = 50;
+  cfg.Precision = 1e-4;
+  dvo::DenseTracker tracker(cfg);
+  tracker.collectIterationStatistics(true);
+  dvo::DenseTracker::Result result;
+  try {
+    tracker.match(*reference, *current, result);
+  } catch (const std::exception& e) {
+    std::fprintf(stderr, "%s\n", e.what());
+    return 3;
+  }
+  std::printf("{\"T\": [");
+  for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) std::printf("%s%.17g", (i + j) ? ", " : "", result.Transformation.matrix()(i, j));
+  std::printf("], \"ll\": %.17g, \"nan\": %d, \"levels\": [", result.LogLikelihood, int(result.isNaN()));
+  for (size_t l = 0; l < result.Statistics.Levels.size(); ++l) {
+    const dvo::DenseTracker::LevelStats& s = result.Statistics.Levels[l];
+    std::printf("%s{\"id\": %zu, \"tc\": %d, \"valid\": %zu, \"its\": %zu, \"n_last\": %zu}", l ? ", " : "", s.Id, int(s.TerminationCriterion),
+                s.ValidPixels, s.Iterations.size(), s.Iterations.empty() ? size_t(0) : s.Iterations.back().ValidConstraints);
+  }
+  // a second tracker on the same current image (LocalTracker runs two), and the error image (N4)
+  dvo::DenseTracker second(tracker);
+  dvo::core::AffineTransformd guess;
+  second.match(*reference, *current, guess);
+  cv::Mat err = tracker.computeIntensityErrorImage(*reference, *current, result.Transformation.inverse(), size_t(cfg.LastLevel));
+  double esum = 0;
+  for (size_t i = 0; i < err.total(); ++i) esum += err.ptr<float>()[i];
+  std::printf("], \"second_t\": [%.17g, %.17g, %.17g], \"err_sum\": %.9g, \"level1_w\": %d}\n", guess.matrix()(0, 3), guess.matrix()(1, 3), guess.matrix()(2, 3),
+              esum, reference->level(1).intensity.cols);
+  std::cerr << result.Statistics;
+  return 0;
+}
