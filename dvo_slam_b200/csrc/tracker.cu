@@ -373,7 +373,7 @@ __global__ void k_pair_end(PairState* states, const PairLevel* pls, const float*
 // different resident-CTA slots share each SM, so one squad's barrier wait is hidden by the others.
 // ------------------------------------------------------------------------------------------------
 #ifndef DVO_PERSISTENT_CTAS_PER_SM
-#define DVO_PERSISTENT_CTAS_PER_SM 5   // resident 128-thread CTAs per SM the register budget is tuned for
+#define DVO_PERSISTENT_CTAS_PER_SM 4   // resident 128-thread CTAs per SM the register budget is tuned for (128 regs/thread)
 #endif
 
 struct SquadState {
@@ -693,7 +693,7 @@ LevelPlan plan_level(int n, int num_sms, int ctas_per_sm) {
   const int warps = kSegmentsPerTile;
   // Squad size: enough CTAs that a warp walks about `target` rounds of 32 pixels per stage.  Small squads keep
   // many pairs in flight and amortise the two barriers and the serial P_k / solve sections of an iteration.
-  static const int target = [] { const char* e = getenv("DVO_B200_RPW"); int v = e ? atoi(e) : 0; return v > 0 ? v : 64; }();
+  static const int target = [] { const char* e = getenv("DVO_B200_RPW"); int v = e ? atoi(e) : 0; return v > 0 ? v : 128; }();
   int g_raw = std::max(1, std::min(num_sms, (R + warps * target - 1) / (warps * target)));
   int k = std::max(1, num_sms / g_raw);   // squads per resident-CTA slot
   int g = num_sms / k;

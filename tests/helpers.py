@@ -6,11 +6,13 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 GOLDEN_SEEDS = (11, 12, 13)
 GOLDEN_LEVELS = 3
 
-# Stated SE(3) tolerance of the path (DESIGN.md "Parity"): the reference's own numerical noise
-# (_mm_rcp_ps, round-toward-zero, fp32 serial sums) moves the converged pose by up to ~6e-4 m /
-# 1.2e-4 rad between otherwise equivalent implementations (FAITHFUL <-> MIRROR/EXACT oracle spread).
-POSE_TOL_T = 1e-3   # metres
-POSE_TOL_R = 1e-3   # radians (SURVEY.md 8c proposal; measured spread is ~1e-4)
+# Stated SE(3) tolerance of the path (DESIGN.md "Parity").  Measured with scripts/oracle_spread.py over 96
+# seeded 640x480 pairs: the reference's own numerical noise (_mm_rcp_ps, round-toward-zero, fp32 serial
+# sums; FAITHFUL vs MIRROR oracle) moves the converged pose by median 1.3e-4 m / 3.0e-5 rad,
+# p90 6.2e-4 m / 7.6e-5 rad, max 1.06e-3 m / 3.4e-4 rad -- the same order as the method's accuracy on
+# this data (FAITHFUL vs ground truth: median 9.7e-4 m, max 2.3e-3 m).  Tolerance = ~2x the max spread.
+POSE_TOL_T = 2e-3   # metres
+POSE_TOL_R = 1e-3   # radians
 
 
 def load_golden(seed):

@@ -5,7 +5,8 @@ inputs.  Tolerances (see DESIGN.md "Parity"):
     kernels' operation order): residual records BIT-EXACT, valid-constraint counts exact,
     precision / log-likelihood / A / b to 2e-6 relative (summation order only);
   * whole alignments against the oracle's FAITHFUL mode (the reference's SSE numerics): pose within
-    POSE_TOL_T = 1e-3 m / POSE_TOL_R = 1e-3 rad at 640x480, identical selected-pixel counts.
+    POSE_TOL_T = 2e-3 m / POSE_TOL_R = 1e-3 rad at 640x480 (helpers.py: ~2x the measured FAITHFUL<->MIRROR
+    spread), identical selected-pixel counts.
 """
 import numpy as np
 import pytest
@@ -250,17 +251,20 @@ def test_statistical_agreement_on_a_batch(engine, oracle):
     Ic, Zc = np.stack([p["I_cur"].numpy() for p in pairs]), np.stack([p["Z_cur"].numpy() for p in pairs])
     res = engine.match_batch(engine.pyramid_batch(Ir, Zr, K, 5), engine.pyramid_batch(Ic, Zc, K, 5), cfg)
     same = 0
+    dts = []
     for i in range(n):
         oref, ocur = oracle.Pyramid(Ir[i], Zr[i], K, 5), oracle.Pyramid(Ic[i], Zc[i], K, 5)
         fa = oracle.match(oref, ocur, ocfg, oracle.mode("faithful"))
         mi = oracle.match(oref, ocur, ocfg, oracle.mode("mirror"))
         dt, dr = pose_delta(fa["T"], res[i].transformation)
         assert dt < POSE_TOL_T and dr < POSE_TOL_R, (i, dt, dr)
+        dts.append(dt)
         if [l["num_iterations"] for l in res[i].levels] == [l["num_iterations"] for l in mi["levels"]]:
             same += 1
             dt, dr = pose_delta(mi["T"], res[i].transformation)
             assert dt < 5e-5 and dr < 5e-5
     assert same >= int(0.5 * n), same
+    assert np.median(dts) < 5e-4, np.median(dts)      # typical agreement is far inside the tolerance
 
 
 def test_full_size_properties_without_oracle(engine):
