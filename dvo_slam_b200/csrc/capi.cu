@@ -160,13 +160,13 @@ int dvo_b200_pyramid_create(dvo_b200_ctx* ctx, const float* intensity, const flo
   return dvo_b200_pyramid_create_batch(ctx, 1, intensity, depth, width, height, fx, fy, ox, oy, levels, out);
 }
 
-int dvo_b200_pyramid_create_raw(dvo_b200_ctx* ctx, const uint8_t* grey, const uint16_t* raw_depth, float depth_scale,
-                                int32_t width, int32_t height, float fx, float fy, float ox, float oy, int32_t levels,
-                                dvo_b200_pyramid** out) {
-  if (!ctx || !grey || !raw_depth || !out || width <= 0 || height <= 0)
+int dvo_b200_pyramid_create_raw_batch(dvo_b200_ctx* ctx, int32_t n, const uint8_t* grey, const uint16_t* raw_depth,
+                                      float depth_scale, int32_t width, int32_t height, float fx, float fy, float ox,
+                                      float oy, int32_t levels, dvo_b200_pyramid** out) {
+  if (!ctx || !grey || !raw_depth || !out || n <= 0 || width <= 0 || height <= 0)
     return set_error(ctx, DVO_B200_ERR_INVALID_ARGUMENT, "pyramid_create_raw: null/invalid argument");
   cudaSetDevice(ctx->device);
-  size_t npx = (size_t)width * height;
+  size_t npx = (size_t)width * height * n;
   size_t fbytes = npx * sizeof(float);
   size_t raw_off = 2 * fbytes;
   int rc = ensure_stage(ctx, raw_off + npx * 3 + 64, 0);
@@ -180,7 +180,13 @@ int dvo_b200_pyramid_create_raw(dvo_b200_ctx* ctx, const uint8_t* grey, const ui
   ctx->h2d_bytes += npx * 3;
   k_convert_raw<<<(unsigned)((npx + 255) / 256), 256, 0, ctx->stream>>>(dG, dR, depth_scale, dI, dZ, (int)npx);
   ctx->launches++;
-  return pyramid_build_batch(ctx, 1, dI, dZ, width, height, fx, fy, ox, oy, levels, 0.f, 0.f, out);
+  return pyramid_build_batch(ctx, n, dI, dZ, width, height, fx, fy, ox, oy, levels, 0.f, 0.f, out);
+}
+
+int dvo_b200_pyramid_create_raw(dvo_b200_ctx* ctx, const uint8_t* grey, const uint16_t* raw_depth, float depth_scale,
+                                int32_t width, int32_t height, float fx, float fy, float ox, float oy, int32_t levels,
+                                dvo_b200_pyramid** out) {
+  return dvo_b200_pyramid_create_raw_batch(ctx, 1, grey, raw_depth, depth_scale, width, height, fx, fy, ox, oy, levels, out);
 }
 
 int dvo_b200_pyramid_retain(dvo_b200_pyramid* p) {

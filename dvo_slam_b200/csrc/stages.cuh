@@ -250,7 +250,9 @@ __device__ __forceinline__ void store_record(const RecordPlanes& rec, int idx, i
 
 // Running state of the pairwise scale sum of one warp segment (see the comment above SegT).
 struct ScaleState {
-  float sall0, sall1, sall2, salt0, salt1, salt2;
+  // fp64 accumulators: the covariance is inverted and feeds accept/reject decisions, so the sums are kept
+  // independent of how the pixels are partitioned over warps (to ~1e-12) at the cost of 12 DADD per 64 pixels
+  double sall0, sall1, sall2, salt0, salt1, salt2;
   float pw, po0, po1, po2;   // pending leader: the last valid point seen, waiting for the next valid weight
   float wfirst;
   int psign, cnt;
@@ -258,7 +260,7 @@ struct ScaleState {
 };
 
 __device__ __forceinline__ void scale_state_init(ScaleState& s) {
-  s.sall0 = s.sall1 = s.sall2 = s.salt0 = s.salt1 = s.salt2 = 0.f;
+  s.sall0 = s.sall1 = s.sall2 = s.salt0 = s.salt1 = s.salt2 = 0.0;
   s.pw = s.po0 = s.po1 = s.po2 = 0.f; s.wfirst = 0.f; s.psign = 0; s.cnt = 0; s.pend = false;
 }
 
@@ -274,8 +276,8 @@ __device__ __forceinline__ void scale_round64(ScaleState& st, int lane, bool v0,
   {   // the pending leader of an earlier round pairs with the first valid point of this round
     const float s = st.pend ? st.pw + w_first : 0.f;
     const float sa = __int_as_float(__float_as_int(s) ^ st.psign);
-    st.sall0 = fmaf(s, st.po0, st.sall0); st.sall1 = fmaf(s, st.po1, st.sall1); st.sall2 = fmaf(s, st.po2, st.sall2);
-    st.salt0 = fmaf(sa, st.po0, st.salt0); st.salt1 = fmaf(sa, st.po1, st.salt1); st.salt2 = fmaf(sa, st.po2, st.salt2);
+    st.sall0 += (double)(s * st.po0); st.sall1 += (double)(s * st.po1); st.sall2 += (double)(s * st.po2);
+    st.salt0 += (double)(sa * st.po0); st.salt1 += (double)(sa * st.po1); st.salt2 += (double)(sa * st.po2);
   }
   const unsigned above0 = (m0 >> lane) >> 1, above1 = (m1 >> lane) >> 1;
   float wn0 = __shfl_sync(kFullMask, w0, above0 ? lane + __ffs(above0) : lane);
@@ -292,14 +294,14 @@ __device__ __forceinline__ void scale_round64(ScaleState& st, int lane, bool v0,
   {
     const float s = (v0 && next0) ? w0 + wn0 : 0.f;
     const float sa = __int_as_float(__float_as_int(s) ^ sg0);
-    st.sall0 = fmaf(s, a0, st.sall0); st.sall1 = fmaf(s, a1, st.sall1); st.sall2 = fmaf(s, a2, st.sall2);
-    st.salt0 = fmaf(sa, a0, st.salt0); st.salt1 = fmaf(sa, a1, st.salt1); st.salt2 = fmaf(sa, a2, st.salt2);
+    st.sall0 += (double)(s * a0); st.sall1 += (double)(s * a1); st.sall2 += (double)(s * a2);
+    st.salt0 += (double)(sa * a0); st.salt1 += (double)(sa * a1); st.salt2 += (double)(sa * a2);
   }
   {
     const float s = (v1 && next1) ? w1 + wn1 : 0.f;
     const float sa = __int_as_float(__float_as_int(s) ^ sg1);
-    st.sall0 = fmaf(s, b0, st.sall0); st.sall1 = fmaf(s, b1, st.sall1); st.sall2 = fmaf(s, b2, st.sall2);
-    st.salt0 = fmaf(sa, b0, st.salt0); st.salt1 = fmaf(sa, b1, st.salt1); st.salt2 = fmaf(sa, b2, st.salt2);
+    st.sall0 += (double)(s * b0); st.sall1 += (double)(s * b1); st.sall2 += (double)(s * b2);
+    st.salt0 += (double)(sa * b0); st.salt1 += (double)(sa * b1); st.salt2 += (double)(sa * b2);
   }
   // new pending leader: the last valid point of the round
   const bool np1 = v1 && !next1, np0 = v0 && !next0;
@@ -321,8 +323,8 @@ __device__ __forceinline__ void scale_state_export(ScaleState& st, int lane, flo
   // leaders at even local rank belong to hypothesis 0, odd to hypothesis 1: S0 = (all + alt)/2, S1 = (all - alt)/2
   if (lane == 0) {
     seg_out[0] = __int_as_float(st.cnt);
-    seg_out[1] = 0.5f * (st.sall0 + st.salt0); seg_out[2] = 0.5f * (st.sall1 + st.salt1); seg_out[3] = 0.5f * (st.sall2 + st.salt2);
-    seg_out[4] = 0.5f * (st.sall0 - st.salt0); seg_out[5] = 0.5f * (st.sall1 - st.salt1); seg_out[6] = 0.5f * (st.sall2 - st.salt2);
+    seg_out[1] = (float)(0.5 * (st.sall0 + st.salt0)); seg_out[2] = (float)(0.5 * (st.sall1 + st.salt1)); seg_out[3] = (float)(0.5 * (st.sall2 + st.salt2));
+    seg_out[4] = (float)(0.5 * (st.sall0 - st.salt0)); seg_out[5] = (float)(0.5 * (st.sall1 - st.salt1)); seg_out[6] = (float)(0.5 * (st.sall2 - st.salt2));
     seg_out[7] = st.wfirst;
     if (st.cnt == 0) { seg_out[8] = 0.f; seg_out[9] = 0.f; seg_out[10] = 0.f; seg_out[11] = 0.f; }
   }

@@ -687,7 +687,7 @@ struct LevelPlan {
   int nseg;             // warp segments per pair = g * kSegmentsPerTile
 };
 
-LevelPlan plan_level(int n, int num_sms, int ctas_per_sm) {
+LevelPlan plan_level(int n, int num_sms, int ctas_per_sm, int npairs) {
   LevelPlan p;
   const int R = (n + 31) / 32;
   const int warps = kSegmentsPerTile;
@@ -696,6 +696,7 @@ LevelPlan plan_level(int n, int num_sms, int ctas_per_sm) {
   static const int target = [] { const char* e = getenv("DVO_B200_RPW"); int v = e ? atoi(e) : 0; return v > 0 ? v : 128; }();
   int g_raw = std::max(1, std::min(num_sms, (R + warps * target - 1) / (warps * target)));
   int k = std::max(1, num_sms / g_raw);   // squads per resident-CTA slot
+  k = std::min(k, std::max(1, (npairs + ctas_per_sm - 1) / ctas_per_sm));   // few pairs: fewer, larger squads (latency)
   int g = num_sms / k;
   p.g = g;
   p.squads_per_slot = k;
@@ -775,7 +776,7 @@ int tracker_match_batch(dvo_b200_ctx* ctx, const dvo_b200_config* cfg, int n, dv
   ScratchNeed need;
   for (int level = first; level >= last; --level) {
     const int nl = refs[0]->L[level].n;
-    LevelPlan pl = plan_level(nl, ctx->num_sms, ctx->ctas_per_sm);
+    LevelPlan pl = plan_level(nl, ctx->num_sms, ctx->ctas_per_sm, n);
     need.record_floats = std::max(need.record_floats, (size_t)pl.nsquads * kRecordFloatsPerPixel * nl);
     need.export_floats = std::max(need.export_floats, (size_t)pl.nsquads * pl.g * kCtaExportFloats);
     need.segbase_ints = std::max(need.segbase_ints, (size_t)pl.nsquads * pl.g);
@@ -810,7 +811,7 @@ int tracker_match_batch(dvo_b200_ctx* ctx, const dvo_b200_config* cfg, int n, dv
     lp.first_level = li == 0; lp.use_initial_estimate = cfg->use_initial_estimate;
     lp.precision = cfg->precision; lp.mu = cfg->mu;
     if ((rc = upload_pair_levels(ctx, n, refs, curs, level))) return rc;
-    const LevelPlan plan = plan_level(L.n, ctx->num_sms, ctx->ctas_per_sm);
+    const LevelPlan plan = plan_level(L.n, ctx->num_sms, ctx->ctas_per_sm, n);
     // squad states, queue head and error flag (last SquadState slot) start at zero
     DVO_CUDA(ctx, cudaMemsetAsync(ws.d_squads, 0, sizeof(SquadState) * (plan.nsquads + 1), st));
     {

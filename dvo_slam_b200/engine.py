@@ -22,6 +22,7 @@ ABI_SYMBOLS = [
     "dvo_b200_abi_version", "dvo_b200_create", "dvo_b200_destroy", "dvo_b200_stream", "dvo_b200_synchronize",
     "dvo_b200_last_error", "dvo_b200_config_default", "dvo_b200_kernel_launches", "dvo_b200_h2d_bytes",
     "dvo_b200_d2h_bytes", "dvo_b200_pyramid_create", "dvo_b200_pyramid_create_batch", "dvo_b200_pyramid_create_raw",
+    "dvo_b200_pyramid_create_raw_batch",
     "dvo_b200_pyramid_retain", "dvo_b200_pyramid_release", "dvo_b200_pyramid_num_levels", "dvo_b200_pyramid_level_info",
     "dvo_b200_pyramid_download", "dvo_b200_pyramid_select", "dvo_b200_match", "dvo_b200_match_batch",
     "dvo_b200_match_batch_device", "dvo_b200_residual_image", "dvo_b200_linearize", "dvo_b200_profile_enable",
@@ -115,6 +116,7 @@ def load_library():
     L.dvo_b200_pyramid_create.argtypes = [vp, vp, vp, i32, i32, C.c_float, C.c_float, C.c_float, C.c_float, i32, C.POINTER(vp)]
     L.dvo_b200_pyramid_create_batch.argtypes = [vp, i32, vp, vp, i32, i32, C.c_float, C.c_float, C.c_float, C.c_float, i32, C.POINTER(vp)]
     L.dvo_b200_pyramid_create_raw.argtypes = [vp, vp, vp, C.c_float, i32, i32, C.c_float, C.c_float, C.c_float, C.c_float, i32, C.POINTER(vp)]
+    L.dvo_b200_pyramid_create_raw_batch.argtypes = [vp, i32, vp, vp, C.c_float, i32, i32, C.c_float, C.c_float, C.c_float, C.c_float, i32, C.POINTER(vp)]
     L.dvo_b200_pyramid_retain.argtypes = [vp]
     L.dvo_b200_pyramid_release.argtypes = [vp]
     L.dvo_b200_pyramid_num_levels.argtypes = [vp]
@@ -247,6 +249,14 @@ class Engine:
         self._check(self.lib.dvo_b200_pyramid_create_batch(self.ctx, n, pI, pZ, w, h, fx, fy, ox, oy, levels, out))
         if host_ptrs is None:
             self.synchronize()
+        return [Pyramid(self, out[i]) for i in range(n)]
+
+    def pyramid_raw_batch(self, host_ptrs, depth_scale, intrinsics, levels: int) -> list[Pyramid]:
+        """host_ptrs = (ptr_grey_u8, ptr_depth_u16, n, h, w): n consecutive raw images in (pinned) host memory."""
+        pG, pD, n, h, w = host_ptrs
+        fx, fy, ox, oy = intrinsics
+        out = (C.c_void_p * n)()
+        self._check(self.lib.dvo_b200_pyramid_create_raw_batch(self.ctx, n, pG, pD, depth_scale, w, h, fx, fy, ox, oy, levels, out))
         return [Pyramid(self, out[i]) for i in range(n)]
 
     def pyramid_raw(self, grey_u8, depth_u16, depth_scale, intrinsics, levels: int) -> Pyramid:

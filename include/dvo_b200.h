@@ -129,6 +129,10 @@ int dvo_b200_pyramid_create_batch(dvo_b200_ctx* ctx, int32_t n, const float* int
 int dvo_b200_pyramid_create_raw(dvo_b200_ctx* ctx, const uint8_t* grey, const uint16_t* raw_depth, float depth_scale,
                                 int32_t width, int32_t height, float fx, float fy, float ox, float oy,
                                 int32_t levels, dvo_b200_pyramid** out);
+/* n images with identical geometry; grey / raw_depth point to n consecutive images. */
+int dvo_b200_pyramid_create_raw_batch(dvo_b200_ctx* ctx, int32_t n, const uint8_t* grey, const uint16_t* raw_depth,
+                                      float depth_scale, int32_t width, int32_t height, float fx, float fy, float ox,
+                                      float oy, int32_t levels, dvo_b200_pyramid** out /* n handles */);
 int dvo_b200_pyramid_retain(dvo_b200_pyramid* p);   /* boost::shared_ptr semantics of RgbdImagePyramidPtr */
 int dvo_b200_pyramid_release(dvo_b200_pyramid* p);
 int dvo_b200_pyramid_num_levels(const dvo_b200_pyramid* p);

@@ -755,9 +755,10 @@ int orc_match(orc_pyramid* ref, orc_pyramid* cur, const orc_config* cfg, const d
   bool accept = true;
 
   float precision[4] = {0, 0, 0, 0};
-  std::vector<RefPoint> pts;
-  std::vector<ErrPoint> err;
-  std::vector<float> weights;
+  // per-thread scratch (the reference keeps points_error / residuals / weights as DenseTracker members, dense_tracking.cpp:160-165)
+  static thread_local std::vector<RefPoint> pts;
+  static thread_local std::vector<ErrPoint> err;
+  static thread_local std::vector<float> weights;
 
   // per-level record of the last two iterations' information/LL for the final pick (lines 368-373)
   std::vector<orc_iteration_stats> level_iters;
