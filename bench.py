@@ -336,7 +336,7 @@ def run_ours(args, rank, local_rank, world):
     try:
         with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
             tj = json.load(f)
-        traffic, traffic_note = tj["dram_bytes"], tj["note"]
+        traffic, traffic_note = tj["dram_bytes_per_step"] / tj["launches_per_step"], tj["note"]
     except Exception:
         pass
 
@@ -411,6 +411,8 @@ def run_ours(args, rank, local_rank, world):
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
                              "traffic": traffic, "traffic_note": traffic_note, "kernel": "k_level_persistent (one launch per pyramid level: warp+residual+weight+scale, LL+J^T W J, on-device solve)",
                              "algorithmic_bytes_per_step": algo_bytes, "kernel_ms_per_step": stage_ms,
+                             "algorithmic_bytes_per_launch": algo_bytes / stage_launches if stage_launches else None,
+                             "kernel_ms_per_launch": stage_ms / stage_launches if stage_launches else None,
                              "launches_per_step": stage_launches,
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                              "kernel_share_of_step": stage_ms / ms_per_step if ms_per_step else None,
