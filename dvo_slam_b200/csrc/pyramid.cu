@@ -14,79 +14,105 @@ namespace {
 
 __device__ __forceinline__ bool is_nan(float v) { return v != v; }
 
-// level-0 intensity into P0.x (Z slot filled later by the finish pass)
-__global__ void k_pyr_intensity0(const float* __restrict__ I0, float2* __restrict__ planes, size_t planes_per_image,
-                                 size_t plane_off, int n) {
-  int img = blockIdx.y;
-  int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= n) return;
-  float2* P0 = planes + img * planes_per_image + plane_off;
-  P0[idx] = make_float2(I0[(size_t)img * n + idx], 0.f);
-}
-
-// level l intensity = ((a+b)+c)+d)/4 of the 2x2 block of level l-1 (rgbd_image.cpp:38-55)
-__global__ void k_pyr_intensity_down(float2* __restrict__ planes, size_t planes_per_image, size_t src_off, int sw,
-                                     size_t dst_off, int dw, int dh) {
+// level l intensity = ((a+b)+c)+d)/4 of the 2x2 block of level l-1 (rgbd_image.cpp:38-55), into P0.x (the Z slot is
+// filled by the finish pass).  kFromInput: level 1 reads the input image, which is level 0's intensity.
+template <bool kFromInput>
+__global__ void k_pyr_intensity_down(const float* __restrict__ I0, size_t in_stride, float2* __restrict__ planes,
+                                     size_t planes_per_image, size_t src_off, int sw, size_t dst_off, int dw, int dh) {
   int img = blockIdx.y;
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= dw * dh) return;
   int y = idx / dw, x = idx - y * dw;
-  const float2* S = planes + img * planes_per_image + src_off;
   float2* D = planes + img * planes_per_image + dst_off;
-  const float2* r0 = S + (size_t)(2 * y) * sw + 2 * x;
-  const float2* r1 = r0 + sw;
-  float s = __fadd_rn(r0[0].x, r0[1].x);
-  s = __fadd_rn(s, r1[0].x);
-  s = __fadd_rn(s, r1[1].x);
+  float a, b, c, d;
+  if (kFromInput) {
+    const float2* r0 = reinterpret_cast<const float2*>(I0 + (size_t)img * in_stride + (size_t)(2 * y) * sw + 2 * x);
+    const float2 u = __ldg(r0), v = __ldg(r0 + sw / 2);    // sw is even: rows stay 8-byte aligned
+    a = u.x; b = u.y; c = v.x; d = v.y;
+  } else {
+    const float2* S = planes + img * planes_per_image + src_off;
+    const float2* r0 = S + (size_t)(2 * y) * sw + 2 * x;
+    const float2* r1 = r0 + sw;
+    a = r0[0].x; b = r0[1].x; c = r1[0].x; d = r1[1].x;
+  }
+  float s = __fadd_rn(a, b);
+  s = __fadd_rn(s, c);
+  s = __fadd_rn(s, d);
   D[idx] = make_float2(s * 0.25f, 0.f);
 }
 
 // gradients (clamped central differences), masked depth, default selection mask for one level.
 // Depth of level l is the pure subsample chain of level 0 (rgbd_image.cpp:127-139): Z_l(y,x) = Z_0(y<<l, x<<l).
-__global__ void k_pyr_finish(const float* __restrict__ Z0, int w0, int n0, float2* __restrict__ planes,
-                             size_t planes_per_image, size_t plane_off, int w, int h, int level,
-                             uint32_t* __restrict__ masks, size_t mask_words_per_image, size_t mask_off,
-                             int* __restrict__ sel_info, int sel_info_per_image, float ti, float td) {
-  int img = blockIdx.y;
-  int n = w * h;
-  int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  bool in = idx < n;
+// Level 0 reads its intensity straight from the input image I0 (no intermediate copy); the other levels read the
+// intensity that k_pyr_intensity_down left in P0.x.  The selection count / last selected index are derived from
+// the masks afterwards (k_sel_info): no atomics here.
+template <bool kLevel0>
+__global__ void __launch_bounds__(256)
+k_pyr_finish(const float* __restrict__ I0, const float* __restrict__ Z0, int w0, int n0, float2* __restrict__ planes,
+             size_t planes_per_image, size_t plane_off, int w, int h, int level,
+             uint32_t* __restrict__ masks, size_t mask_words_per_image, size_t mask_off, float ti, float td) {
+  const int img = blockIdx.y;
+  const int n = w * h;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool in = idx < n;
   bool sel = false;
   if (in) {
-    int y = idx / w, x = idx - y * w;
+    const int y = idx / w, x = idx - y * w;
     float2* P0 = planes + img * planes_per_image + plane_off;
     float2* P1 = P0 + n;
     float2* P2 = P1 + n;
     const float* Z = Z0 + (size_t)img * n0;
-    int xp = max(x - 1, 0), xn = min(x + 1, w - 1), yp = max(y - 1, 0), yn = min(y + 1, h - 1);
-    float I = P0[idx].x;
-    float ix = (P0[y * w + xn].x - P0[y * w + xp].x) * 0.5f;
-    float iy = (P0[yn * w + x].x - P0[yp * w + x].x) * 0.5f;
-    float z = Z[(size_t)(y << level) * w0 + (x << level)];
-    float zx = (Z[(size_t)(y << level) * w0 + (xn << level)] - Z[(size_t)(y << level) * w0 + (xp << level)]) * 0.5f;
-    float zy = (Z[(size_t)(yn << level) * w0 + (x << level)] - Z[(size_t)(yp << level) * w0 + (x << level)]) * 0.5f;
-    bool bad = is_nan(I) || is_nan(ix) || is_nan(iy) || is_nan(z) || is_nan(zx) || is_nan(zy);
-    float zm = bad ? __int_as_float(0x7fc00000) : z;
+    const int xp = max(x - 1, 0), xn = min(x + 1, w - 1), yp = max(y - 1, 0), yn = min(y + 1, h - 1);
+    float I, ixp, ixn, iyp, iyn;
+    if (kLevel0) {
+      const float* Ii = I0 + (size_t)img * n0;
+      I = __ldg(Ii + idx); ixp = __ldg(Ii + y * w + xp); ixn = __ldg(Ii + y * w + xn);
+      iyp = __ldg(Ii + yp * w + x); iyn = __ldg(Ii + yn * w + x);
+    } else {
+      I = P0[idx].x; ixp = P0[y * w + xp].x; ixn = P0[y * w + xn].x; iyp = P0[yp * w + x].x; iyn = P0[yn * w + x].x;
+    }
+    const float ix = (ixn - ixp) * 0.5f;
+    const float iy = (iyn - iyp) * 0.5f;
+    const size_t zr = (size_t)(y << level) * w0;
+    const float z = __ldg(Z + zr + (x << level));
+    const float zx = (__ldg(Z + zr + (xn << level)) - __ldg(Z + zr + (xp << level))) * 0.5f;
+    const float zy = (__ldg(Z + (size_t)(yn << level) * w0 + (x << level)) - __ldg(Z + (size_t)(yp << level) * w0 + (x << level))) * 0.5f;
+    const bool bad = is_nan(I) || is_nan(ix) || is_nan(iy) || is_nan(z) || is_nan(zx) || is_nan(zy);
+    const float zm = bad ? __int_as_float(0x7fc00000) : z;
     P0[idx] = make_float2(I, zm);
     P1[idx] = make_float2(ix, iy);
     P2[idx] = make_float2(zx, zy);
     // ValidPointAndGradientThresholdPredicate::isPointOk (point_selection.h:63-66)
     sel = !bad && (fabsf(ix) > ti || fabsf(iy) > ti || fabsf(zx) > td || fabsf(zy) > td);
   }
-  unsigned m = __ballot_sync(0xffffffffu, sel);
-  if ((threadIdx.x & 31) == 0 && idx < ((n + 31) / 32) * 32) {
-    masks[img * mask_words_per_image + mask_off + (idx >> 5)] = m;
-    if (m) {
-      int* info = sel_info + img * sel_info_per_image + 2 * level;
-      atomicAdd(&info[0], __popc(m));
-      atomicMax(&info[1], idx + 31 - __clz(m));
-    }
+  const unsigned m = __ballot_sync(0xffffffffu, sel);
+  if ((threadIdx.x & 31) == 0 && idx < ((n + 31) / 32) * 32) masks[img * mask_words_per_image + mask_off + (idx >> 5)] = m;
+}
+
+// {S, last selected linear index} of one (image, level) from its selection mask: one warp each
+__global__ void k_sel_info(const uint32_t* __restrict__ masks, size_t mask_words_per_image, size_t mask_off, int words,
+                           int* __restrict__ sel_info, int sel_info_per_image, int level) {
+  const int img = blockIdx.x, lane = threadIdx.x;
+  const uint32_t* m = masks + img * mask_words_per_image + mask_off;
+  int cnt = 0, last = -1;
+  for (int i = lane; i < words; i += 32) {
+    const uint32_t v = m[i];
+    cnt += __popc(v);
+    if (v) last = i * 32 + 31 - __clz(v);     // i increases: the lane's last non-empty word wins
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
+    last = max(last, __shfl_xor_sync(0xffffffffu, last, off));
+  }
+  if (lane == 0) {
+    sel_info[img * sel_info_per_image + 2 * level] = cnt;
+    sel_info[img * sel_info_per_image + 2 * level + 1] = last;
   }
 }
 
 // recompute only the selection mask of one level for non-default thresholds
-__global__ void k_reselect(const float2* __restrict__ P0, int n, uint32_t* __restrict__ mask, int* __restrict__ info,
-                           float ti, float td) {
+__global__ void k_reselect(const float2* __restrict__ P0, int n, uint32_t* __restrict__ mask, float ti, float td) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   bool sel = false;
   if (idx < n) {
@@ -94,28 +120,17 @@ __global__ void k_reselect(const float2* __restrict__ P0, int n, uint32_t* __res
     sel = !is_nan(a.y) && (fabsf(b.x) > ti || fabsf(b.y) > ti || fabsf(c.x) > td || fabsf(c.y) > td);
   }
   unsigned m = __ballot_sync(0xffffffffu, sel);
-  if ((threadIdx.x & 31) == 0 && idx < ((n + 31) / 32) * 32) {
-    mask[idx >> 5] = m;
-    if (m) {
-      atomicAdd(&info[0], __popc(m));
-      atomicMax(&info[1], idx + 31 - __clz(m));
-    }
-  }
+  if ((threadIdx.x & 31) == 0 && idx < ((n + 31) / 32) * 32) mask[idx >> 5] = m;
 }
 
 // point-cloud template tx[x] = (x - ox)/fx, ty[y] = (y - oy)/fy (IEEE division, rgbd_image.cpp:197-198)
-// and sel_info initialisation {S = 0, last = -1}
 __global__ void k_template(float* __restrict__ tmpl, size_t tmpl_per_image, size_t off, int w, int h, float fx,
-                           float fy, float ox, float oy, int* __restrict__ sel_info, int sel_info_per_image, int level) {
+                           float fy, float ox, float oy) {
   int img = blockIdx.y;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   float* t = tmpl + img * tmpl_per_image + off;
   if (i < w) t[i] = __fdiv_rn((float)i - ox, fx);
   else if (i < w + h) t[i] = __fdiv_rn((float)(i - w) - oy, fy);
-  if (i == 0) {
-    sel_info[img * sel_info_per_image + 2 * level] = 0;
-    sel_info[img * sel_info_per_image + 2 * level + 1] = -1;
-  }
 }
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -137,6 +152,7 @@ int ensure_stage(dvo_b200_ctx* ctx, size_t dev_bytes, size_t host_bytes) {
 }
 
 static Slab* acquire_slab(dvo_b200_ctx* ctx, size_t bytes) {
+  std::lock_guard<std::mutex> lock(ctx->mu);   // pyramids may be released by another host thread (see pyramid_free)
   auto it = ctx->free_slabs.find(bytes);
   if (it != ctx->free_slabs.end()) {
     Slab* s = it->second;
@@ -161,7 +177,14 @@ void pyramid_free(dvo_b200_pyramid* p) {
   dvo_b200_ctx* ctx = p->ctx;
   Slab* s = p->slab;
   delete p;
-  if (s && --s->refs == 0) {
+  if (!s) return;
+  if (!ctx) {
+    if (--s->refs == 0) { cudaFree(s->base); if (s->ready) cudaEventDestroy(s->ready); delete s; }
+    return;
+  }
+  // a consumer thread that matched against pyramids built by this ctx releases them from its own thread
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  if (--s->refs == 0) {
     if (ctx) ctx->free_slabs.insert({s->bytes, s});
     else { cudaFree(s->base); if (s->ready) cudaEventDestroy(s->ready); delete s; }
   }
@@ -206,23 +229,26 @@ int pyramid_build_batch(dvo_b200_ctx* ctx, int n, const float* d_I, const float*
 
   cudaStream_t st = ctx->stream;
   {
-    ProfScope prof(ctx, 3, 3 * levels);
+    ProfScope prof(ctx, 3, 4 * levels - 1);
     const int T = 256;
     for (int l = 0; l < levels; ++l) {
       const LevelInfo& q = L[l];
       dim3 gt((q.w + q.h + T - 1) / T, n);
-      k_template<<<gt, T, 0, st>>>(tmpl, tmpl_floats, q.tmpl_off, q.w, q.h, q.fx, q.fy, q.ox, q.oy, sel, sel_ints, l);
+      k_template<<<gt, T, 0, st>>>(tmpl, tmpl_floats, q.tmpl_off, q.w, q.h, q.fx, q.fy, q.ox, q.oy);
+      ctx->launches += 1;
+      if (l == 0) continue;   // level 0 takes its intensity from the input image
       dim3 g((q.n + T - 1) / T, n);
-      if (l == 0) k_pyr_intensity0<<<g, T, 0, st>>>(d_I, planes, plane_f2, q.plane_off, q.n);
-      else k_pyr_intensity_down<<<g, T, 0, st>>>(planes, plane_f2, L[l - 1].plane_off, L[l - 1].w, q.plane_off, q.w, q.h);
-      ctx->launches += 2;
+      if (l == 1) k_pyr_intensity_down<true><<<g, T, 0, st>>>(d_I, (size_t)w * h, planes, plane_f2, 0, L[0].w, q.plane_off, q.w, q.h);
+      else k_pyr_intensity_down<false><<<g, T, 0, st>>>(nullptr, 0, planes, plane_f2, L[l - 1].plane_off, L[l - 1].w, q.plane_off, q.w, q.h);
+      ctx->launches += 1;
     }
     for (int l = 0; l < levels; ++l) {
       const LevelInfo& q = L[l];
       dim3 g((q.words * 32 + T - 1) / T, n);
-      k_pyr_finish<<<g, T, 0, st>>>(d_Z, w, w * h, planes, plane_f2, q.plane_off, q.w, q.h, l, masks, mask_words, q.mask_off,
-                                    sel, sel_ints, ti, td);
-      ctx->launches += 1;
+      if (l == 0) k_pyr_finish<true><<<g, T, 0, st>>>(d_I, d_Z, w, w * h, planes, plane_f2, q.plane_off, q.w, q.h, l, masks, mask_words, q.mask_off, ti, td);
+      else k_pyr_finish<false><<<g, T, 0, st>>>(d_I, d_Z, w, w * h, planes, plane_f2, q.plane_off, q.w, q.h, l, masks, mask_words, q.mask_off, ti, td);
+      k_sel_info<<<n, 32, 0, st>>>(masks, mask_words, q.mask_off, q.words, sel, sel_ints, l);
+      ctx->launches += 2;
     }
   }
   DVO_CUDA(ctx, cudaGetLastError());
@@ -247,24 +273,15 @@ int pyramid_build_batch(dvo_b200_ctx* ctx, int n, const float* d_I, const float*
 int pyramid_reselect(dvo_b200_ctx* ctx, dvo_b200_pyramid* p, float ti, float td) {
   if (p->sel_ti == ti && p->sel_td == td) return 0;
   cudaStream_t st = ctx->stream;
-  std::vector<int> init(2 * kMaxLevels);
-  for (int l = 0; l < kMaxLevels; ++l) { init[2 * l] = 0; init[2 * l + 1] = -1; }
-  // small synchronous-ish upload through the pinned stage
-  int rc = ensure_stage(ctx, 0, 4096);
-  if (rc) return rc;
-  DVO_CUDA(ctx, cudaStreamSynchronize(st));
-  std::memcpy(ctx->h_stage, init.data(), init.size() * sizeof(int));
-  DVO_CUDA(ctx, cudaMemcpyAsync(p->sel_info, ctx->h_stage, init.size() * sizeof(int), cudaMemcpyHostToDevice, st));
   ProfScope prof(ctx, 4, p->levels);
   for (int l = 0; l < p->levels; ++l) {
     const LevelInfo& q = p->L[l];
     const int T = 256;
-    k_reselect<<<(q.words * 32 + T - 1) / T, T, 0, st>>>(p->planes + q.plane_off, q.n, p->sel_mask + q.mask_off,
-                                                         p->sel_info + 2 * l, ti, td);
-    ctx->launches += 1;
+    k_reselect<<<(q.words * 32 + T - 1) / T, T, 0, st>>>(p->planes + q.plane_off, q.n, p->sel_mask + q.mask_off, ti, td);
+    k_sel_info<<<1, 32, 0, st>>>(p->sel_mask, 0, q.mask_off, q.words, p->sel_info, 0, l);
+    ctx->launches += 2;
   }
   DVO_CUDA(ctx, cudaGetLastError());
-  DVO_CUDA(ctx, cudaStreamSynchronize(st));  // h_stage reuse safety
   p->sel_ti = ti; p->sel_td = td;
   return 0;
 }

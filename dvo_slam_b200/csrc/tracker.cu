@@ -74,12 +74,16 @@ __device__ void log_iteration(dvo_b200_iteration_stats* ilog, int max_log, int p
   for (int i = 0; i < 36; ++i) e.information[i] = with_increment ? st.A_done[i] : nan;
 }
 
-__global__ void k_level_begin(PairState* states, const PairLevel* pls, const double* T_init, int npairs,
+// pls_src: this level's pair descriptors, either in device memory already (pls_src == pls) or in pinned host
+// memory that the kernel reads over PCIe (the tracker path: keeps the per-level upload off the H2D copy engine,
+// where it would queue behind a bulk image upload of another context).  T_init likewise.
+__global__ void k_level_begin(PairState* states, const PairLevel* pls_src, PairLevel* pls, const double* T_init, int npairs,
                               LevelLaunch lp) {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= npairs) return;
   PairState& st = states[p];
-  const PairLevel& pl = pls[p];
+  const PairLevel pl = pls_src[p];
+  if (pls_src != pls) pls[p] = pl;
   if (lp.first_level) {
     // dense_tracking.cpp:137-150: first increment is the given guess
     st.inc = (lp.use_initial_estimate && T_init) ? se3_from_matrix(T_init + (size_t)p * 16) : se3_identity();
@@ -691,12 +695,27 @@ LevelPlan plan_level(int n, int num_sms, int ctas_per_sm, int npairs) {
   LevelPlan p;
   const int R = (n + 31) / 32;
   const int warps = kSegmentsPerTile;
-  // Squad size: enough CTAs that a warp walks about `target` rounds of 32 pixels per stage.  Small squads keep
-  // many pairs in flight and amortise the two barriers and the serial P_k / solve sections of an iteration.
+  // Squad size.  Small squads keep many pairs in flight and amortise the two barriers and the serial P_k / solve
+  // sections of an iteration over long warp segments (`target` rounds of 32 pixels per warp and stage); but the
+  // batch is processed in waves of nsquads pairs, and a last wave that is mostly empty wastes more than that.
+  // Pairs are handed out from a queue, so a level takes about (pairs per squad + tail) x time per pair, where the
+  // tail (pairs that need two or three times the mean number of iterations) is worth a bit more than one pair
+  // and the time per pair goes with (rounds per warp + per-iteration overhead in round units).  Pick the number
+  // of squads per resident-CTA slot that minimises that among the sizes near the target.
   static const int target = [] { const char* e = getenv("DVO_B200_RPW"); int v = e ? atoi(e) : 0; return v > 0 ? v : 128; }();
-  int g_raw = std::max(1, std::min(num_sms, (R + warps * target - 1) / (warps * target)));
-  int k = std::max(1, num_sms / g_raw);   // squads per resident-CTA slot
-  k = std::min(k, std::max(1, (npairs + ctas_per_sm - 1) / ctas_per_sm));   // few pairs: fewer, larger squads (latency)
+  const int overhead = 16;
+  const int k_max = std::max(1, (npairs + ctas_per_sm - 1) / ctas_per_sm);   // few pairs: fewer, larger squads (latency)
+  int best_k = 1;
+  double best_cost = -1.0;
+  for (int k = 1; k <= std::min(num_sms, k_max); ++k) {
+    const int g = num_sms / k;
+    const int rpw = (R + g * warps - 1) / (g * warps);
+    if (rpw > target + target / 2 && k > 1) break;    // rpw grows with k
+    const double per_squad = (double)npairs / ((double)ctas_per_sm * k);
+    const double cost = (std::max(per_squad, 1.0) + 1.2) * (rpw + overhead);
+    if (best_cost < 0 || cost < best_cost - 1e-9) { best_cost = cost; best_k = k; }
+  }
+  const int k = best_k;
   int g = num_sms / k;
   p.g = g;
   p.squads_per_slot = k;
@@ -726,12 +745,7 @@ int check_batch(dvo_b200_ctx* ctx, const dvo_b200_config* cfg, int n, dvo_b200_p
   return 0;
 }
 
-int upload_pair_levels(dvo_b200_ctx* ctx, int n, dvo_b200_pyramid* const* refs, dvo_b200_pyramid* const* curs, int level) {
-  size_t bytes = sizeof(PairLevel) * n;
-  int rc = ensure_stage(ctx, 0, bytes);
-  if (rc) return rc;
-  DVO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // previous use of the pinned stage has drained
-  PairLevel* h = (PairLevel*)ctx->h_stage;
+void fill_pair_levels(PairLevel* h, int n, dvo_b200_pyramid* const* refs, dvo_b200_pyramid* const* curs, int level) {
   for (int i = 0; i < n; ++i) {
     const dvo_b200_pyramid* r = refs[i];
     const dvo_b200_pyramid* c = curs[i];
@@ -747,7 +761,15 @@ int upload_pair_levels(dvo_b200_ctx* ctx, int n, dvo_b200_pyramid* const* refs, 
     // PointSelection::getMaximumNumberOfPoints (point_selection.cpp:68-71)
     q.max_valid_pixels = (long long)(size_t)((double)r->L[0].n * pow(0.25, (double)level));
   }
-  DVO_CUDA(ctx, cudaMemcpyAsync(ctx->ws.d_pair_level, h, bytes, cudaMemcpyHostToDevice, ctx->stream));
+}
+
+int upload_pair_levels(dvo_b200_ctx* ctx, int n, dvo_b200_pyramid* const* refs, dvo_b200_pyramid* const* curs, int level) {
+  size_t bytes = sizeof(PairLevel) * n;
+  int rc = ensure_stage(ctx, 0, bytes);
+  if (rc) return rc;
+  DVO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // previous use of the pinned stage has drained
+  fill_pair_levels((PairLevel*)ctx->h_stage, n, refs, curs, level);
+  DVO_CUDA(ctx, cudaMemcpyAsync(ctx->ws.d_pair_level, ctx->h_stage, bytes, cudaMemcpyHostToDevice, ctx->stream));
   ctx->h2d_bytes += bytes;
   return 0;
 }
@@ -790,16 +812,23 @@ int tracker_match_batch(dvo_b200_ctx* ctx, const dvo_b200_config* cfg, int n, dv
   for (int i = 0; i < n; ++i)
     if ((rc = pyramid_reselect(ctx, refs[i], cfg->intensity_derivative_threshold, cfg->depth_derivative_threshold))) return rc;
 
-  // T_init upload
+  // Pair descriptors of every level and the initial estimates go into the pinned stage once; k_level_begin
+  // reads them from there (host-mapped, unified addressing), so the level loop below never touches the H2D copy
+  // engine or the host between launches.
+  const int nlev = first - last + 1;
+  const size_t desc_bytes = sizeof(PairLevel) * (size_t)n * nlev;
+  const bool have_init = cfg->use_initial_estimate && T_init;
+  const size_t init_bytes = have_init ? sizeof(double) * 16 * (size_t)n : 0;
+  if ((rc = ensure_stage(ctx, 0, desc_bytes + init_bytes))) return rc;
+  DVO_CUDA(ctx, cudaStreamSynchronize(st));   // previous use of the pinned stage has drained
+  PairLevel* h_desc = (PairLevel*)ctx->h_stage;
+  for (int level = first, li = 0; level >= last; --level, ++li) fill_pair_levels(h_desc + (size_t)li * n, n, refs, curs, level);
   double* d_Tinit = nullptr;
-  if (cfg->use_initial_estimate && T_init) {
-    size_t bytes = sizeof(double) * 16 * n;
-    if ((rc = ensure_stage(ctx, bytes + 256, 0))) return rc;
-    d_Tinit = (double*)ctx->d_stage;
-    DVO_CUDA(ctx, cudaMemcpyAsync(d_Tinit, T_init, bytes, cudaMemcpyHostToDevice, st));
-    DVO_CUDA(ctx, cudaStreamSynchronize(st));
-    ctx->h2d_bytes += bytes;
+  if (have_init) {
+    d_Tinit = (double*)((char*)ctx->h_stage + desc_bytes);
+    std::memcpy(d_Tinit, T_init, init_bytes);
   }
+  ctx->h2d_bytes += desc_bytes + init_bytes;
 
   for (int i = 0; i < 8; ++i) ws.h_active[i] = 0;
   for (int level = first, li = 0; level >= last; --level, ++li) {
@@ -810,13 +839,12 @@ int tracker_match_batch(dvo_b200_ctx* ctx, const dvo_b200_config* cfg, int n, dv
     lp.level_index = li; lp.level_id = level; lp.max_iterations = cfg->max_iterations_per_level;
     lp.first_level = li == 0; lp.use_initial_estimate = cfg->use_initial_estimate;
     lp.precision = cfg->precision; lp.mu = cfg->mu;
-    if ((rc = upload_pair_levels(ctx, n, refs, curs, level))) return rc;
     const LevelPlan plan = plan_level(L.n, ctx->num_sms, ctx->ctas_per_sm, n);
     // squad states, queue head and error flag (last SquadState slot) start at zero
     DVO_CUDA(ctx, cudaMemsetAsync(ws.d_squads, 0, sizeof(SquadState) * (plan.nsquads + 1), st));
     {
       ProfScope prof(ctx, 2);
-      k_level_begin<<<(n + 63) / 64, 64, 0, st>>>(ws.d_state, ws.d_pair_level, d_Tinit, n, lp);
+      k_level_begin<<<(n + 63) / 64, 64, 0, st>>>(ws.d_state, h_desc + (size_t)li * n, ws.d_pair_level, d_Tinit, n, lp);
       ctx->launches++;
     }
     PersistentArgs pa;
