@@ -279,68 +279,126 @@ k_normal(const PairState* __restrict__ states, const PairLevel* __restrict__ pls
   }
 }
 
-// one warp per pair: reduce tile partials, log-likelihood, accept test, solve, termination
-// (dense_tracking.cpp:297-363)
-__device__ __noinline__ void pair_end_warp(PairState& st, const PairLevel& pl, int pair, const float* partial, int ntiles, int* active,
-                              const LevelLaunch& lp, dvo_b200_iteration_stats* ilog, int max_log) {
-  const int lane = threadIdx.x & 31;
-  double v = 0.0;
-  if (lane < kNormalValues) {
-    const float* p = partial + lane;
-    for (int t = 0; t < ntiles; ++t) v += (double)__ldcg(p + (size_t)t * kNormalValues);
+// End of an iteration (dense_tracking.cpp:297-363): reduce the CTA partials, log-likelihood, accept test, solve,
+// pose update, termination.  Every thread of the CTA calls; thread 0 does the scalar part in two steps:
+//   critical : everything the other CTAs of the squad wait for -- the new K*T and iteration flag, or
+//              level_active = 0 -- followed by `release` (the squad barrier of the persistent kernel);
+//   deferred : Revertable bookkeeping, statistics, the iteration log.  It finishes before this CTA arrives at
+//              the squad's next barrier, so the next P_k / end step (run by whichever CTA arrives last) sees it.
+struct PairEndSmem {
+  double part[kSegmentsPerTile][32];
+};
+
+template <typename Release>
+__device__ __noinline__ void pair_end_cta(PairState& st, const PairLevel& pl, int pair, const float* partial, int ntiles,
+                                             int* active, const LevelLaunch& lp, dvo_b200_iteration_stats* ilog, int max_log,
+                                             PairEndSmem& sm, Release release) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  {   // fp64 sum of the partials: warp q takes tiles q, q+4, ... with independent loads in flight
+    double v = 0.0;
+    if (lane < kNormalValues) {
+      const float* p = partial + lane;
+      int t = warp;
+      for (; t + 3 * kSegmentsPerTile < ntiles; t += 4 * kSegmentsPerTile) {
+        const float a0 = __ldcg(p + (size_t)t * kNormalValues);
+        const float a1 = __ldcg(p + (size_t)(t + kSegmentsPerTile) * kNormalValues);
+        const float a2 = __ldcg(p + (size_t)(t + 2 * kSegmentsPerTile) * kNormalValues);
+        const float a3 = __ldcg(p + (size_t)(t + 3 * kSegmentsPerTile) * kNormalValues);
+        v += (double)a0; v += (double)a1; v += (double)a2; v += (double)a3;
+      }
+      for (; t < ntiles; t += kSegmentsPerTile) v += (double)__ldcg(p + (size_t)t * kNormalValues);
+    }
+    sm.part[warp][lane] = v;
   }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
   double vals[kNormalValues];
 #pragma unroll
-  for (int i = 0; i < kNormalValues; ++i) vals[i] = __shfl_sync(kFull, v, i);
-  if (lane != 0) return;
+  for (int i = 0; i < kNormalValues; ++i) {
+    double v = sm.part[0][i];
+#pragma unroll
+    for (int q = 1; q < kSegmentsPerTile; ++q) v += sm.part[q][i];
+    vals[i] = v;
+  }
 
-  LevelSummary& ls = st.levels[lp.level_index];
+  // ---- critical ----
+  const float P0 = st.precision[0], P1 = st.precision[1], P2 = st.precision[2], P3 = st.precision[3];
   // computeCompleteDataLogLikelihood: 0.5 n log det P - 3.5 sum log(1 + 0.2 d), returned as float
-  float det = __fsub_rn(__fmul_rn(st.precision[0], st.precision[3]), __fmul_rn(st.precision[1], st.precision[2]));
-  float logdet = (float)log((double)det);
-  float ll = (float)(0.5 * (double)st.n * (double)logdet - 0.5 * (5.0 + 2.0) * vals[0]);
-  st.ll = ll;
-  st.nll_cur = -(double)ll;
+  const float det = __fsub_rn(__fmul_rn(P0, P3), __fmul_rn(P1, P2));
+  const float logdet = (float)log((double)det);
+  const float ll = (float)(0.5 * (double)st.n * (double)logdet - 0.5 * (5.0 + 2.0) * vals[0]);
   double li[6] = {0, 0, 0, 0, 0, 0};
   double sq = 0;
   if (lp.mu != 0.0) {                              // mu == 0: prior term and the mu*log(initial) shift vanish
     se3_log(st.initial, li);
     for (int i = 0; i < 6; ++i) sq += li[i] * li[i];
   }
-  st.prior_cur = lp.mu * sq;                       // dense_tracking.cpp:302
-  st.last_error = st.error;                        // dense_tracking.cpp:306-307
-  st.error = -(double)ll;
-  bool accept = st.error < st.last_error;          // dense_tracking.cpp:312
-
-  // unpack A (upper triangle) and b
+  const double last_error = st.error;              // dense_tracking.cpp:306-307
+  const double error = -(double)ll;
+  const bool accept = error < last_error;          // dense_tracking.cpp:312
+  double A[36], bvec[6], x[6];
   {
     int k = 1;
     for (int i = 0; i < 6; ++i)
-      for (int j = i; j < 6; ++j) { st.A[i * 6 + j] = vals[k]; st.A[j * 6 + i] = vals[k]; ++k; }
-    for (int i = 0; i < 6; ++i) st.b[i] = vals[22 + i];
+      for (int j = i; j < 6; ++j) { A[i * 6 + j] = vals[k]; A[j * 6 + i] = vals[k]; ++k; }
+    for (int i = 0; i < 6; ++i) bvec[i] = vals[22 + i];
   }
-  bool level_done = false;
+  int iteration = st.iteration;
+  if (accept) {
+    double As[36], bs[6];
+    for (int i = 0; i < 36; ++i) As[i] = A[i];
+    for (int i = 0; i < 6; ++i) { As[i * 6 + i] += lp.mu; bs[i] = bvec[i] + lp.mu * li[i]; }   // lines 345-346
+    ldlt_solve6(As, bs, x);                                                                    // line 347
+    iteration += 1;                                                                            // line 353
+  } else {
+    for (int i = 0; i < 6; ++i) x[i] = st.x[i];
+  }
+  double m = 0; bool nanx = false;
+  for (int i = 0; i < 6; ++i) { m = fmax(m, fabs(x[i])); nanx |= x[i] != x[i]; }
+  const bool big = !nanx && m > lp.precision;
+  const bool exceeded = iteration >= lp.max_iterations;
+  const bool level_done = !(accept && big && !exceeded);                                       // line 357
+  SE3d inc, estimate_new;
+  if (!level_done) {
+    // dense_tracking.cpp:259-263 for the next iteration: estimate = exp(x) * estimate, then K * float(T)
+    inc = se3_exp(x);
+    estimate_new = se3_mul(inc, st.estimate);
+    double T[16];
+    se3_matrix(estimate_new, T);
+    for (int j = 0; j < 4; ++j) {   // reference operation order (dense_tracking_impl.cpp:142-152)
+      const float t0 = (float)T[j], t1 = (float)T[4 + j], t2 = (float)T[8 + j];
+      st.kt[j] = __fadd_rn(__fmul_rn(pl.cfx, t0), __fmul_rn(pl.cox, t2));
+      st.kt[4 + j] = __fadd_rn(__fmul_rn(pl.cfy, t1), __fmul_rn(pl.coy, t2));
+      st.kt[8 + j] = t2;
+    }
+    st.iteration = iteration;
+  } else {
+    st.level_active = 0;
+  }
+  release();
+
+  // ---- deferred ----
+  LevelSummary& ls = st.levels[lp.level_index];
+  st.ll = ll;
+  st.nll_cur = -(double)ll;
+  st.prior_cur = lp.mu * sq;                       // dense_tracking.cpp:302
+  st.last_error = last_error;
+  st.error = error;
+  for (int i = 0; i < 36; ++i) st.A[i] = A[i];
+  for (int i = 0; i < 6; ++i) st.b[i] = bvec[i];
   if (!accept) {
     st.initial = st.initial_old; st.estimate = st.estimate_old;   // dense_tracking.cpp:314-321
     st.termination = DVO_B200_TERM_LOG_LIKELIHOOD_DECREASED;
     log_iteration(ilog, max_log, pair, st, lp.level_id, false);
-    level_done = true;
   } else {
-    double A[36], b[6];
-    for (int i = 0; i < 36; ++i) A[i] = st.A[i];
-    for (int i = 0; i < 6; ++i) { A[i * 6 + i] += lp.mu; b[i] = st.b[i] + lp.mu * li[i]; }   // lines 345-346
-    ldlt_solve6(A, b, st.x);                                                                  // line 347
+    for (int i = 0; i < 6; ++i) st.x[i] = x[i];
     for (int i = 0; i < 36; ++i) st.A_done[i] = A[i];
+    for (int i = 0; i < 6; ++i) st.A_done[i * 6 + i] += lp.mu;
     st.nll_done = st.nll_cur; st.prior_done = st.prior_cur; st.have_done = 1;
     ls.last_inc_n = st.n; ls.last_inc_nll = st.nll_cur;
     log_iteration(ilog, max_log, pair, st, lp.level_id, true);
-    st.iteration += 1;                                                                        // line 353
+    st.iteration = iteration;
   }
-  double m = 0; bool nanx = false;
-  for (int i = 0; i < 6; ++i) { m = fmax(m, fabs(st.x[i])); nanx |= st.x[i] != st.x[i]; }
-  bool big = !nanx && m > lp.precision;
-  bool exceeded = st.iteration >= lp.max_iterations;
-  if (!(accept && big && !exceeded)) level_done = true;                                       // line 357
   if (level_done) {
     if (!nanx && m <= lp.precision) st.termination = DVO_B200_TERM_INCREMENT_TOO_SMALL;       // line 359
     if (exceeded) st.termination = DVO_B200_TERM_ITERATIONS_EXCEEDED;                         // line 362
@@ -348,19 +406,24 @@ __device__ __noinline__ void pair_end_warp(PairState& st, const PairLevel& pl, i
     int need = (st.termination == DVO_B200_TERM_LOG_LIKELIHOOD_DECREASED ||
                 st.termination == DVO_B200_TERM_TOO_FEW_CONSTRAINTS) ? 2 : 1;
     ls.has_inc = ls.num_iterations >= need;
-    st.level_active = 0;
     if (active) atomicSub(active, 1);
   } else {
-    prepare_iteration(st, pl);
+    st.inc = inc;
+    st.initial_old = st.initial;
+    st.initial = se3_mul(se3_inverse(inc), st.initial);
+    st.estimate_old = st.estimate;
+    st.estimate = estimate_new;
   }
 }
 
-__global__ void k_pair_end(PairState* states, const PairLevel* pls, const float* __restrict__ partial, int ntiles,
-                           int* active, LevelLaunch lp, dvo_b200_iteration_stats* ilog, int max_log) {
+__global__ void __launch_bounds__(kSegmentsPerTile * 32)
+k_pair_end(PairState* states, const PairLevel* pls, const float* __restrict__ partial, int ntiles,
+           int* active, LevelLaunch lp, dvo_b200_iteration_stats* ilog, int max_log) {
   const int pair = blockIdx.x;
   PairState& st = states[pair];
   if (!st.level_active || !st.phase_ok) return;
-  pair_end_warp(st, pls[pair], pair, partial + (size_t)pair * ntiles * kNormalValues, ntiles, active, lp, ilog, max_log);
+  __shared__ PairEndSmem sm;
+  pair_end_cta(st, pls[pair], pair, partial + (size_t)pair * ntiles * kNormalValues, ntiles, active, lp, ilog, max_log, sm, [] {});
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -371,7 +434,7 @@ __global__ void k_pair_end(PairState* states, const PairLevel* pls, const float*
 // a time and runs all its Gauss-Newton iterations on this level inside the kernel:
 //   stage A over the squad's warp segments -> squad barrier, the last CTA to arrive computes P_k
 //   (pair_mid_warp) -> stage B -> squad barrier, the last CTA reduces the partials, tests the
-//   log-likelihood, solves the 6x6 system and updates the pose (pair_end_warp) -> next iteration,
+//   log-likelihood, solves the 6x6 system and updates the pose (pair_end_cta) -> next iteration,
 // then takes the next pair from a global queue.  The residual records of the pair in flight live in a
 // per-squad scratch buffer that is rewritten every iteration and therefore stays in L2; the squads of
 // different resident-CTA slots share each SM, so one squad's barrier wait is hidden by the others.
@@ -463,6 +526,7 @@ k_level_persistent(PersistentArgs a) {
   const RecordPlanes rec = record_planes(rec_base, lp.n);
 
   __shared__ PairMidSmem sm_mid;
+  __shared__ PairEndSmem sm_end;
   __shared__ float red[kSegmentsPerTile][kNormalValues];
   __shared__ float sm_exp[kSegmentsPerTile][kSegExportFloats];
   __shared__ int s_flag[2];
@@ -557,11 +621,7 @@ k_level_persistent(PersistentArgs a) {
       DVO_TOCK(1);
       if (squad_arrive(sq, episode, a.g, s_flag)) {
         DVO_TOCK(3);
-        if (warp == 0) {
-          pair_end_warp(st, pl, pair, partial, a.g, nullptr, lp, a.ilog, a.max_log);
-          __syncwarp();
-          if (lane == 0) squad_release(sq, episode);
-        }
+        pair_end_cta(st, pl, pair, partial, a.g, nullptr, lp, a.ilog, a.max_log, sm_end, [&] { squad_release(sq, episode); });
         __syncthreads();
         DVO_TOCK(5);
       } else {
@@ -950,7 +1010,7 @@ int tracker_linearize(dvo_b200_ctx* ctx, const dvo_b200_config* cfg, dvo_b200_py
   if (!planes7) {
     k_normal<<<grid, kSegmentsPerTile * 32, 0, st>>>(ws.d_state, ws.d_pair_level, ws.d_records, ws.d_scale_export, ws.d_tile_base,
                                                      ws.d_normal_partial, lp);
-    k_pair_end<<<1, 32, 0, st>>>(ws.d_state, ws.d_pair_level, ws.d_normal_partial, lp.ntiles, ws.d_active, lp, nullptr, 0);
+    k_pair_end<<<1, kSegmentsPerTile * 32, 0, st>>>(ws.d_state, ws.d_pair_level, ws.d_normal_partial, lp.ntiles, ws.d_active, lp, nullptr, 0);
     ctx->launches += 2;
   }
   DVO_CUDA(ctx, cudaGetLastError());
