@@ -64,6 +64,19 @@ __global__ void k_convert_raw(const uint8_t* __restrict__ grey, const uint16_t* 
   Z[i] = r == 0 ? __int_as_float(0x7fc00000) : __fmul_rn((float)r, scale);
 }
 
+__global__ void k_convert_bgr(const uint8_t* __restrict__ bgr, const uint16_t* __restrict__ raw, float scale,
+                              float* __restrict__ I, float* __restrict__ Z, int n) {
+  // benchmark_slam.cpp:58-68: cv::cvtColor(rgb, grey, CV_BGR2GRAY) on CV_8UC3, then convertTo(CV_32F).
+  // OpenCV's 8-bit path is fixed point: (B*1868 + G*9617 + R*4899 + (1 << 13)) >> 14.
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint8_t* p = bgr + 3 * (size_t)i;
+  const int grey = (1868 * (int)p[0] + 9617 * (int)p[1] + 4899 * (int)p[2] + 8192) >> 14;
+  I[i] = (float)grey;
+  uint16_t r = raw[i];
+  Z[i] = r == 0 ? __int_as_float(0x7fc00000) : __fmul_rn((float)r, scale);
+}
+
 }  // namespace
 }  // namespace dvo_b200
 
@@ -84,6 +97,8 @@ int dvo_b200_create(int device, void* stream, dvo_b200_ctx** out) {
   if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return DVO_B200_ERR_CUDA; }
   dvo_b200_ctx* ctx = new dvo_b200_ctx;
   ctx->device = device;
+  ctx->pool = std::make_shared<SlabPool>();
+  ctx->pool->device = device;
   if (stream) { ctx->stream = (cudaStream_t)stream; ctx->own_stream = false; }
   else {
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); delete ctx; return DVO_B200_ERR_CUDA; }
@@ -107,7 +122,7 @@ int dvo_b200_destroy(dvo_b200_ctx* ctx) {
   cudaFree(ws.d_pair_level); cudaFree(ws.d_state); cudaFree(ws.d_records); cudaFree(ws.d_scale_export);
   cudaFree(ws.d_tile_base); cudaFree(ws.d_normal_partial); cudaFree(ws.d_active); cudaFree(ws.d_iter_log); cudaFree(ws.d_squads);
   if (ws.h_active) cudaFreeHost(ws.h_active);
-  for (auto& kv : ctx->free_slabs) { cudaFree(kv.second->base); if (kv.second->ready) cudaEventDestroy(kv.second->ready); delete kv.second; }
+  pool_close(ctx);
   cudaFree(ctx->d_stage);
   if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
   if (ctx->h_results) cudaFreeHost(ctx->h_results);
@@ -179,6 +194,29 @@ int dvo_b200_pyramid_create_raw_batch(dvo_b200_ctx* ctx, int32_t n, const uint8_
   DVO_CUDA(ctx, cudaMemcpyAsync(dG, grey, npx, cudaMemcpyHostToDevice, ctx->stream));
   ctx->h2d_bytes += npx * 3;
   k_convert_raw<<<(unsigned)((npx + 255) / 256), 256, 0, ctx->stream>>>(dG, dR, depth_scale, dI, dZ, (int)npx);
+  ctx->launches++;
+  return pyramid_build_batch(ctx, n, dI, dZ, width, height, fx, fy, ox, oy, levels, 0.f, 0.f, out);
+}
+
+int dvo_b200_pyramid_create_bgr_batch(dvo_b200_ctx* ctx, int32_t n, const uint8_t* bgr, const uint16_t* raw_depth,
+                                      float depth_scale, int32_t width, int32_t height, float fx, float fy, float ox,
+                                      float oy, int32_t levels, dvo_b200_pyramid** out) {
+  if (!ctx || !bgr || !raw_depth || !out || n <= 0 || width <= 0 || height <= 0)
+    return set_error(ctx, DVO_B200_ERR_INVALID_ARGUMENT, "pyramid_create_bgr: null/invalid argument");
+  cudaSetDevice(ctx->device);
+  size_t npx = (size_t)width * height * n;
+  size_t fbytes = npx * sizeof(float);
+  size_t raw_off = 2 * fbytes;
+  int rc = ensure_stage(ctx, raw_off + npx * 5 + 64, 0);
+  if (rc) return rc;
+  float* dI = (float*)ctx->d_stage;
+  float* dZ = dI + npx;
+  uint16_t* dR = (uint16_t*)((char*)ctx->d_stage + raw_off);
+  uint8_t* dC = (uint8_t*)((char*)ctx->d_stage + raw_off + npx * 2);
+  DVO_CUDA(ctx, cudaMemcpyAsync(dR, raw_depth, npx * 2, cudaMemcpyHostToDevice, ctx->stream));
+  DVO_CUDA(ctx, cudaMemcpyAsync(dC, bgr, npx * 3, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->h2d_bytes += npx * 5;
+  k_convert_bgr<<<(unsigned)((npx + 255) / 256), 256, 0, ctx->stream>>>(dC, dR, depth_scale, dI, dZ, (int)npx);
   ctx->launches++;
   return pyramid_build_batch(ctx, n, dI, dZ, width, height, fx, fy, ox, oy, levels, 0.f, 0.f, out);
 }

@@ -4,6 +4,7 @@
 #include <stdint.h>
 
 #include <map>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -37,11 +38,24 @@ struct LevelInfo {
   size_t tmpl_off;             // float offset of tx[w] then ty[h] inside tmpl
 };
 
+struct Slab;
+// Pool of released slabs of one context, keyed by size (release -> reuse instead of cudaFree).  Pyramids are
+// independent objects in the reference (boost::shared_ptr<RgbdImagePyramid>) and routinely outlive the tracker that
+// first used them, and they may be released from another host thread than the one that built them: the pool is
+// shared-owned by the context and by every slab, and guarded by its own mutex.
+struct SlabPool {
+  std::mutex mu;
+  std::multimap<size_t, Slab*> free;
+  bool closed = false;           // the context is gone: released slabs are freed instead of pooled
+  int device = 0;
+};
+
 struct Slab {                  // one cudaMalloc shared by a batch of pyramids
   void* base = nullptr;
   size_t bytes = 0;
   int refs = 0;
   cudaEvent_t ready = nullptr;   // recorded on the creating stream after the build kernels
+  std::shared_ptr<SlabPool> pool;
 };
 
 }  // namespace dvo_b200
@@ -140,8 +154,7 @@ struct dvo_b200_ctx {
   int64_t launches = 0, h2d_bytes = 0, d2h_bytes = 0;
   uint64_t next_pyramid_id = 1;
   dvo_b200::Workspace ws;
-  // pooled device slabs keyed by size (release -> reuse instead of cudaFree)
-  std::multimap<size_t, dvo_b200::Slab*> free_slabs;
+  std::shared_ptr<dvo_b200::SlabPool> pool;   // pooled device slabs (see SlabPool)
   // staging for uploads
   void* d_stage = nullptr; size_t d_stage_bytes = 0;
   void* h_stage = nullptr; size_t h_stage_bytes = 0;   // pinned bounce buffer for pageable sources
@@ -178,6 +191,7 @@ int pyramid_build_batch(dvo_b200_ctx* ctx, int n, const float* d_I, const float*
                         float ox, float oy, int levels, float ti, float td, dvo_b200_pyramid** out);
 int pyramid_reselect(dvo_b200_ctx* ctx, dvo_b200_pyramid* p, float ti, float td);
 void pyramid_free(dvo_b200_pyramid* p);
+void pool_close(dvo_b200_ctx* ctx);
 int ensure_stage(dvo_b200_ctx* ctx, size_t dev_bytes, size_t host_bytes);
 
 // tracker.cu

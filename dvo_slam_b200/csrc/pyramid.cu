@@ -151,43 +151,55 @@ int ensure_stage(dvo_b200_ctx* ctx, size_t dev_bytes, size_t host_bytes) {
   return 0;
 }
 
+static void destroy_slab(Slab* s) {
+  cudaFree(s->base);
+  if (s->ready) cudaEventDestroy(s->ready);
+  delete s;
+}
+
 static Slab* acquire_slab(dvo_b200_ctx* ctx, size_t bytes) {
-  std::lock_guard<std::mutex> lock(ctx->mu);   // pyramids may be released by another host thread (see pyramid_free)
-  auto it = ctx->free_slabs.find(bytes);
-  if (it != ctx->free_slabs.end()) {
+  SlabPool& pool = *ctx->pool;
+  std::lock_guard<std::mutex> lock(pool.mu);   // pyramids may be released by another host thread (see pyramid_free)
+  auto it = pool.free.find(bytes);
+  if (it != pool.free.end()) {
     Slab* s = it->second;
-    ctx->free_slabs.erase(it);
+    pool.free.erase(it);
     s->refs = 0;
     return s;
   }
   void* p = nullptr;
   if (cudaMalloc(&p, bytes) != cudaSuccess) {
     // drop the pool and retry once
-    for (auto& kv : ctx->free_slabs) { cudaFree(kv.second->base); if (kv.second->ready) cudaEventDestroy(kv.second->ready); delete kv.second; }
-    ctx->free_slabs.clear();
+    for (auto& kv : pool.free) destroy_slab(kv.second);
+    pool.free.clear();
     cudaGetLastError();
     if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
   }
   Slab* s = new Slab;
-  s->base = p; s->bytes = bytes; s->refs = 0;
+  s->base = p; s->bytes = bytes; s->refs = 0; s->pool = ctx->pool;
   return s;
 }
 
+// Called from any host thread, possibly after the owning context has been destroyed.
 void pyramid_free(dvo_b200_pyramid* p) {
-  dvo_b200_ctx* ctx = p->ctx;
   Slab* s = p->slab;
   delete p;
   if (!s) return;
-  if (!ctx) {
-    if (--s->refs == 0) { cudaFree(s->base); if (s->ready) cudaEventDestroy(s->ready); delete s; }
-    return;
-  }
-  // a consumer thread that matched against pyramids built by this ctx releases them from its own thread
-  std::lock_guard<std::mutex> lock(ctx->mu);
+  std::shared_ptr<SlabPool> pool = s->pool;    // keeps the pool alive while its mutex is held
+  std::lock_guard<std::mutex> lock(pool->mu);
   if (--s->refs == 0) {
-    if (ctx) ctx->free_slabs.insert({s->bytes, s});
-    else { cudaFree(s->base); if (s->ready) cudaEventDestroy(s->ready); delete s; }
+    if (pool->closed) { cudaSetDevice(pool->device); destroy_slab(s); }
+    else pool->free.insert({s->bytes, s});
   }
+}
+
+// The context goes away: free what is pooled, and have slabs still referenced by live pyramids freed on release.
+void pool_close(dvo_b200_ctx* ctx) {
+  if (!ctx->pool) return;
+  std::lock_guard<std::mutex> lock(ctx->pool->mu);
+  for (auto& kv : ctx->pool->free) destroy_slab(kv.second);
+  ctx->pool->free.clear();
+  ctx->pool->closed = true;
 }
 
 int pyramid_build_batch(dvo_b200_ctx* ctx, int n, const float* d_I, const float* d_Z, int w, int h, float fx, float fy,

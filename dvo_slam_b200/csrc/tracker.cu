@@ -795,7 +795,7 @@ int check_batch(dvo_b200_ctx* ctx, const dvo_b200_config* cfg, int n, dvo_b200_p
     if (!refs[i] || !curs[i]) return set_error(ctx, DVO_B200_ERR_INVALID_ARGUMENT, "match: null pyramid");
     // a pyramid built on another ctx's stream: order this stream after its build
     for (const dvo_b200_pyramid* p : {refs[i], curs[i]})
-      if (p->ctx != ctx && p->slab && p->slab->ready) cudaStreamWaitEvent(ctx->stream, p->slab->ready, 0);
+      if (p->slab && p->slab->pool != ctx->pool && p->slab->ready) cudaStreamWaitEvent(ctx->stream, p->slab->ready, 0);
     if (refs[i]->levels <= cfg->first_level || curs[i]->levels <= cfg->first_level)
       return set_error(ctx, DVO_B200_ERR_INVALID_ARGUMENT, "match: pyramid has fewer levels than FirstLevel+1");
     if (refs[i]->L[0].w != refs[0]->L[0].w || refs[i]->L[0].h != refs[0]->L[0].h ||

@@ -22,7 +22,7 @@ ABI_SYMBOLS = [
     "dvo_b200_abi_version", "dvo_b200_create", "dvo_b200_destroy", "dvo_b200_stream", "dvo_b200_synchronize",
     "dvo_b200_last_error", "dvo_b200_config_default", "dvo_b200_kernel_launches", "dvo_b200_h2d_bytes",
     "dvo_b200_d2h_bytes", "dvo_b200_pyramid_create", "dvo_b200_pyramid_create_batch", "dvo_b200_pyramid_create_raw",
-    "dvo_b200_pyramid_create_raw_batch",
+    "dvo_b200_pyramid_create_raw_batch", "dvo_b200_pyramid_create_bgr_batch",
     "dvo_b200_pyramid_retain", "dvo_b200_pyramid_release", "dvo_b200_pyramid_num_levels", "dvo_b200_pyramid_level_info",
     "dvo_b200_pyramid_download", "dvo_b200_pyramid_select", "dvo_b200_match", "dvo_b200_match_batch",
     "dvo_b200_match_batch_device", "dvo_b200_residual_image", "dvo_b200_linearize", "dvo_b200_profile_enable",
@@ -117,6 +117,7 @@ def load_library():
     L.dvo_b200_pyramid_create_batch.argtypes = [vp, i32, vp, vp, i32, i32, C.c_float, C.c_float, C.c_float, C.c_float, i32, C.POINTER(vp)]
     L.dvo_b200_pyramid_create_raw.argtypes = [vp, vp, vp, C.c_float, i32, i32, C.c_float, C.c_float, C.c_float, C.c_float, i32, C.POINTER(vp)]
     L.dvo_b200_pyramid_create_raw_batch.argtypes = [vp, i32, vp, vp, C.c_float, i32, i32, C.c_float, C.c_float, C.c_float, C.c_float, i32, C.POINTER(vp)]
+    L.dvo_b200_pyramid_create_bgr_batch.argtypes = [vp, i32, vp, vp, C.c_float, i32, i32, C.c_float, C.c_float, C.c_float, C.c_float, i32, C.POINTER(vp)]
     L.dvo_b200_pyramid_retain.argtypes = [vp]
     L.dvo_b200_pyramid_release.argtypes = [vp]
     L.dvo_b200_pyramid_num_levels.argtypes = [vp]
@@ -257,6 +258,15 @@ class Engine:
         fx, fy, ox, oy = intrinsics
         out = (C.c_void_p * n)()
         self._check(self.lib.dvo_b200_pyramid_create_raw_batch(self.ctx, n, pG, pD, depth_scale, w, h, fx, fy, ox, oy, levels, out))
+        return [Pyramid(self, out[i]) for i in range(n)]
+
+    def pyramid_bgr_batch(self, host_ptrs, depth_scale, intrinsics, levels: int) -> list[Pyramid]:
+        """host_ptrs = (ptr_bgr_u8x3, ptr_depth_u16, n, h, w): n consecutive interleaved-BGR images and raw depth images
+        in (pinned) host memory; grey conversion (OpenCV BGR2GRAY) and depth scaling run on the device."""
+        pC, pD, n, h, w = host_ptrs
+        fx, fy, ox, oy = intrinsics
+        out = (C.c_void_p * n)()
+        self._check(self.lib.dvo_b200_pyramid_create_bgr_batch(self.ctx, n, pC, pD, depth_scale, w, h, fx, fy, ox, oy, levels, out))
         return [Pyramid(self, out[i]) for i in range(n)]
 
     def pyramid_raw(self, grey_u8, depth_u16, depth_scale, intrinsics, levels: int) -> Pyramid:

@@ -3,12 +3,32 @@
 // (benchmark_slam.cpp:392,483-488; local_tracker.cpp:172-184).  Reads a raw float32 pair written by
 // tests/test_host_adapter.py, prints the resulting pose as JSON.  Exit 3 = no CUDA device.
 #include <cstdio>
+#include <cmath>
 #include <cstdlib>
 #include <fstream>
 #include <iostream>
 #include <vector>
 
 #include "dvo/dense_tracking.h"
+#include "dvo_slam/batched_alignment.h"
+#include "dvo_slam/tracking_result_evaluation.h"
+
+namespace {
+// the members of dvo_slam's Keyframe / ConstraintProposal that the validator's tracking loop touches
+struct Frame {
+  dvo::core::RgbdImagePyramidPtr pyramid;
+  dvo::core::RgbdImagePyramidPtr image() const { return pyramid; }
+};
+struct Proposal {
+  Frame *Reference, *Current;
+  dvo::core::AffineTransformd InitialTransformation;
+  dvo::DenseTracker::Result TrackingResult;
+};
+bool same_pose(const dvo::DenseTracker::Result& a, const dvo::DenseTracker::Result& b) {
+  for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) if (a.Transformation.matrix()(i, j) != b.Transformation.matrix()(i, j)) return false;
+  return a.LogLikelihood == b.LogLikelihood;
+}
+}  // namespace
 
 static cv::Mat load_plane(std::ifstream& f, int w, int h) {
   cv::Mat m(h, w, CV_32FC1);
@@ -56,8 +76,26 @@ int main(int argc, char** argv) {
   cv::Mat err = tracker.computeIntensityErrorImage(*reference, *current, result.Transformation.inverse(), size_t(cfg.LastLevel));
   double esum = 0;
   for (size_t i = 0; i < err.total(); ++i) esum += err.ptr<float>()[i];
-  std::printf("], \"second_t\": [%.17g, %.17g, %.17g], \"err_sum\": %.9g, \"level1_w\": %d}\n", guess.matrix()(0, 3), guess.matrix()(1, 3), guess.matrix()(2, 3),
-              esum, reference->level(1).intensity.cols);
+  // N1: the two fan-outs of dvo_slam as one batched call each; the answers must be those of the sequential calls
+  dvo::DenseTracker::Result r_keyframe, r_odometry;
+  dvo_slam::matchKeyframeAndOdometry(tracker, *reference, *reference, *current, r_keyframe, r_odometry);
+  Frame kf = {reference}, fr = {current};
+  Proposal p0 = {&kf, &fr, dvo::core::AffineTransformd(), dvo::DenseTracker::Result()}, p1 = p0, p2 = p0;
+  std::vector<Proposal*> proposals;
+  proposals.push_back(&p0); proposals.push_back(&p1); proposals.push_back(&p2);
+  dvo_slam::matchProposals(tracker, proposals);
+  const bool batch_equal = same_pose(r_keyframe, result) && same_pose(r_odometry, result);
+  const bool proposals_equal = same_pose(p0.TrackingResult, result) && same_pose(p1.TrackingResult, result) && same_pose(p2.TrackingResult, result);
+  // N4: keyframe-selection scores
+  dvo_slam::EntropyRatioTrackingResultEvaluation entropy(result);
+  dvo_slam::LogLikelihoodTrackingResultEvaluation loglik(result);
+  dvo_slam::NormalizedLogLikelihoodTrackingResultEvaluation nloglik(result);
+  entropy.add(r_keyframe);
+  std::printf("], \"second_t\": [%.17g, %.17g, %.17g], \"err_sum\": %.9g, \"level1_w\": %d, \"batch_equal\": %d, \"proposals_equal\": %d, "
+              "\"entropy_ratio_first\": %.17g, \"entropy_ratio_avg\": %.17g, \"ll_ratio\": %.17g, \"nll_ratio\": %.17g, \"logdet\": %.17g}\n",
+              guess.matrix()(0, 3), guess.matrix()(1, 3), guess.matrix()(2, 3), esum, reference->level(1).intensity.cols,
+              int(batch_equal), int(proposals_equal), entropy.ratioWithFirst(r_odometry), entropy.ratioWithAverage(r_odometry),
+              loglik.ratioWithFirst(result), nloglik.ratioWithAverage(result), std::log(result.Information.determinant()));
   std::cerr << result.Statistics;
   return 0;
 }

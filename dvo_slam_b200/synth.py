@@ -142,3 +142,30 @@ def make_pair(seed: int, cfg: SceneConfig | None = None, device="cpu"):
     I_cur, Z_cur = _render(cfg, T_true, tex, box, rng, device)
     return {"I_ref": I_ref, "Z_ref": Z_ref, "I_cur": I_cur, "Z_cur": Z_cur, "T_true": T_true, "xi": xi,
             "intrinsics": cfg.intrinsics, "width": cfg.width, "height": cfg.height}
+
+
+def make_sequence(seed: int, n_frames: int, cfg: SceneConfig | None = None, device="cpu"):
+    """A camera moving through one scene: returns (frames, poses) with frames[k] = (I, Z) float32 tensors and
+    poses[k] the float64 4x4 world-from-camera pose of frame k (frame 0 = identity).  Consecutive frames differ
+    by a twist drawn like make_pair's, so relative_k = poses[k-1]^-1 poses[k] is what DenseTracker::match returns
+    for (reference = frame k-1, current = frame k)."""
+    cfg = cfg or SceneConfig()
+    rng = np.random.default_rng(seed)
+    lam = np.exp(rng.uniform(math.log(0.04), math.log(0.60), cfg.n_sinusoids))
+    dirs = rng.standard_normal((cfg.n_sinusoids, 3))
+    dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
+    f64 = torch.float64
+    tex = (torch.tensor(dirs / lam[:, None], dtype=f64, device=device),
+           torch.tensor(rng.uniform(0, 2 * math.pi, cfg.n_sinusoids), dtype=f64, device=device),
+           torch.tensor(lam / lam.sum() * 2.2, dtype=f64, device=device))
+    box = (1.2 + rng.uniform(-0.1, 0.1), rng.uniform(-0.2, 0.2), rng.uniform(-0.15, 0.15), 0.28, 0.22)
+    T_cam = np.eye(4)            # p_cam = T_cam p_world
+    frames, poses = [], []
+    for k in range(n_frames):
+        if k > 0:
+            xi = np.concatenate([rng.uniform(-cfg.max_translation, cfg.max_translation, 3),
+                                 rng.uniform(-cfg.max_rotation, cfg.max_rotation, 3)])
+            T_cam = se3_exp(xi) @ T_cam
+        frames.append(_render(cfg, T_cam, tex, box, rng, device))
+        poses.append(np.linalg.inv(T_cam))
+    return frames, poses

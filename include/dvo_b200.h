@@ -133,6 +133,12 @@ int dvo_b200_pyramid_create_raw(dvo_b200_ctx* ctx, const uint8_t* grey, const ui
 int dvo_b200_pyramid_create_raw_batch(dvo_b200_ctx* ctx, int32_t n, const uint8_t* grey, const uint16_t* raw_depth,
                                       float depth_scale, int32_t width, int32_t height, float fx, float fy, float ox,
                                       float oy, int32_t levels, dvo_b200_pyramid** out /* n handles */);
+/* 8-bit BGR (interleaved, the order cv::imread(file, 1) returns) + 16-bit raw depth in: cv::cvtColor(rgb, grey,
+ * CV_BGR2GRAY) + convertTo(CV_32F) of the loader (benchmark_slam.cpp:50-68) and convertRawDepthImageSse run on the
+ * device.  Grey = (1868 B + 9617 G + 4899 R + 8192) >> 14, OpenCV's 8-bit fixed-point BGR2GRAY. */
+int dvo_b200_pyramid_create_bgr_batch(dvo_b200_ctx* ctx, int32_t n, const uint8_t* bgr, const uint16_t* raw_depth,
+                                      float depth_scale, int32_t width, int32_t height, float fx, float fy, float ox,
+                                      float oy, int32_t levels, dvo_b200_pyramid** out /* n handles */);
 int dvo_b200_pyramid_retain(dvo_b200_pyramid* p);   /* boost::shared_ptr semantics of RgbdImagePyramidPtr */
 int dvo_b200_pyramid_release(dvo_b200_pyramid* p);
 int dvo_b200_pyramid_num_levels(const dvo_b200_pyramid* p);

@@ -80,6 +80,24 @@ struct MatrixRC {
   void setConstant(double c) { for (double& x : v) x = c; }
   void setIdentity() { setZero(); for (int i = 0; i < (R < C ? R : C); ++i) v[i * C + i] = 1; }
   double sum() const { double s = 0; for (double x : v) s += x; return s; }
+  double determinant() const {   // partial-pivot LU (square matrices only)
+    static_assert(R == C, "determinant of a square matrix");
+    double a[R * C];
+    for (int i = 0; i < R * C; ++i) a[i] = v[i];
+    double det = 1.0;
+    for (int k = 0; k < R; ++k) {
+      int piv = k;
+      for (int i = k + 1; i < R; ++i) if (std::fabs(a[i * C + k]) > std::fabs(a[piv * C + k])) piv = i;
+      if (a[piv * C + k] == 0.0) return 0.0;
+      if (piv != k) { for (int j = 0; j < C; ++j) { double t = a[k * C + j]; a[k * C + j] = a[piv * C + j]; a[piv * C + j] = t; } det = -det; }
+      det *= a[k * C + k];
+      for (int i = k + 1; i < R; ++i) {
+        const double f = a[i * C + k] / a[k * C + k];
+        for (int j = k; j < C; ++j) a[i * C + j] -= f * a[k * C + j];
+      }
+    }
+    return det;
+  }
   double* data() { return v; }
   const double* data() const { return v; }
 };

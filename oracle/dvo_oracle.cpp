@@ -883,4 +883,11 @@ void orc_convert_raw_depth(const uint16_t* in, float* out, int64_t count, float 
   for (int64_t i = 0; i < count; ++i) out[i] = in[i] == 0 ? kNaNf : float(in[i]) * scale;
 }
 
+void orc_bgr_to_grey(const uint8_t* bgr, float* out, int64_t count) {
+  for (int64_t i = 0; i < count; ++i) {
+    const int b = bgr[3 * i], g = bgr[3 * i + 1], r = bgr[3 * i + 2];
+    out[i] = float((b * 1868 + g * 9617 + r * 4899 + (1 << 13)) >> 14);
+  }
+}
+
 }  // extern "C"

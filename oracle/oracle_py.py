@@ -91,6 +91,7 @@ def lib():
         L.orc_se3_log.argtypes = [dp, dp]
         L.orc_ldlt_solve6.argtypes = [dp, dp, dp]
         L.orc_convert_raw_depth.argtypes = [C.POINTER(C.c_uint16), fp, C.c_int64, C.c_float]
+        L.orc_bgr_to_grey.argtypes = [C.POINTER(C.c_uint8), fp, C.c_int64]
         _lib = L
     return _lib
 
@@ -222,6 +223,15 @@ def ldlt_solve6(A, b):
     x = np.zeros(6)
     lib().orc_ldlt_solve6(_dptr(A), _dptr(b), _dptr(x))
     return x
+
+
+def bgr_to_grey(bgr_u8):
+    """(h, w, 3) uint8 BGR -> (h, w) float32 grey, as cv::cvtColor(CV_BGR2GRAY) + convertTo(CV_32F)."""
+    bgr = np.ascontiguousarray(bgr_u8, dtype=np.uint8)
+    assert bgr.shape[-1] == 3
+    out = np.empty(bgr.shape[:-1], dtype=np.float32)
+    lib().orc_bgr_to_grey(bgr.ctypes.data_as(C.POINTER(C.c_uint8)), _fptr(out), out.size)
+    return out
 
 
 def convert_raw_depth(raw_u16, scale):

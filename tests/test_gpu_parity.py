@@ -77,6 +77,26 @@ def test_raw_input_conversion(engine, oracle):
         assert nan_equal(a.download(lvl), b.download(lvl))
 
 
+def test_bgr_input_conversion(engine, oracle):
+    """BGR8 + raw depth entry point (loader of benchmark_slam.cpp:50-77 on the device): the pyramid equals, bit for bit,
+    the one built from the oracle's grey conversion and depth scaling."""
+    rng = np.random.default_rng(11)
+    h, w, n = 96, 128, 3
+    bgr = rng.integers(0, 256, size=(n, h, w, 3), dtype=np.uint8)
+    raw = rng.integers(0, 20000, size=(n, h, w), dtype=np.uint16)
+    raw[rng.random((n, h, w)) < 0.05] = 0
+    K = (130.0, 129.0, 63.5, 47.5)
+    pyr = engine.pyramid_bgr_batch((bgr.ctypes.data, raw.ctypes.data, n, h, w), 1.0 / 5000.0, K, 3)
+    engine.synchronize()
+    for i in range(n):
+        grey = oracle.bgr_to_grey(bgr[i])
+        depth = oracle.convert_raw_depth(raw[i], 1.0 / 5000.0)
+        ref = engine.pyramid(grey, depth, K, 3)
+        for level in range(3):
+            assert nan_equal(pyr[i].download(level), ref.download(level))
+            assert pyr[i].select(level, 0.0, 0.0)[0] == ref.select(level, 0.0, 0.0)[0]
+
+
 @pytest.mark.parametrize("seed", GOLDEN_SEEDS)
 def test_residual_records_bit_exact_and_linearisation(engine, oracle, seed):
     g = load_golden(seed)
@@ -206,6 +226,26 @@ def test_initial_estimate_mu_and_default_levels(engine, oracle, full_pairs):
     if [l["num_iterations"] for l in r.levels] == [l["num_iterations"] for l in mi["levels"]]:
         assert np.allclose([it["prior"] for it in r.iterations], [it["prior"] for it in mi["iterations"]], rtol=1e-3, atol=1e-9)
         assert np.allclose(r.information, mi["information"], rtol=0, atol=1e-2 * np.abs(mi["information"]).max())   # one boundary pixel flipping shifts the pair parity of the scale sum
+
+
+def test_config5_1280x960_six_levels_with_damping(engine, oracle):
+    """BASELINE.json configs[4]: 1280x960 (2 x fr1), 6-level pyramid (FirstLevel 5 .. LastLevel 0), Student-t weights and
+    mu = 0.05 damping: pose within the stated tolerance of FAITHFUL, control flow as MIRROR."""
+    from dvo_slam_b200 import synth
+    scfg = synth.SceneConfig().scaled(2)
+    pair = synth.make_pair(41, scfg)
+    K = pair["intrinsics"]
+    a = {k: pair[k].numpy() for k in ("I_ref", "Z_ref", "I_cur", "Z_cur")}
+    cfg, ocfg = _cfgs(oracle, 5, 0, mu=0.05)
+    r = engine.match(engine.pyramid(a["I_ref"], a["Z_ref"], K, 6), engine.pyramid(a["I_cur"], a["Z_cur"], K, 6), cfg)
+    oref, ocur = oracle.Pyramid(a["I_ref"], a["Z_ref"], K, 6), oracle.Pyramid(a["I_cur"], a["Z_cur"], K, 6)
+    fa = oracle.match(oref, ocur, ocfg, oracle.mode("faithful"))
+    dt, dr = pose_delta(fa["T"], r.transformation)
+    assert dt < POSE_TOL_T and dr < POSE_TOL_R, (dt, dr)
+    assert [l["id"] for l in r.levels] == [5, 4, 3, 2, 1, 0]
+    assert [l["valid_pixels"] for l in r.levels] == [l["valid_pixels"] for l in fa["levels"]]
+    gt, gr = pose_delta(pair["T_true"], np.linalg.inv(r.transformation))
+    assert gt < 5e-3 and gr < 2e-3                      # and it is the true motion
 
 
 def test_degenerate_inputs(engine, oracle, full_pairs):

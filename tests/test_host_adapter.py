@@ -49,6 +49,10 @@ def test_adapter_headers_keep_the_reference_surface():
                  "LastIterationWithIncrement", "clearStatistics", "isNaN", "setIdentity", "MaxIterationsPerLevel", "UseInitialEstimate",
                  "IntensityDerivativeThreshold", "InfluenceFuntionType", "ScaleEstimatorParam"):
         assert name in hdr, name
+    ev = open(os.path.join(ROOT, "include", "dvo_slam", "tracking_result_evaluation.h")).read()
+    for name in ("class TrackingResultEvaluation", "class LogLikelihoodTrackingResultEvaluation", "class NormalizedLogLikelihoodTrackingResultEvaluation",
+                 "class EntropyRatioTrackingResultEvaluation", "ratioWithFirst", "ratioWithAverage", "void add("):
+        assert name in ev, name
     assert hdr.count("bool match(") == 4
     img = open(os.path.join(ROOT, "include", "dvo", "core", "rgbd_image.h")).read()
     for name in ("class RgbdCameraPyramid", "class RgbdImagePyramid", "class RgbdImage", "RgbdImagePyramidPtr create(", "void build(", "void compute(",
@@ -77,3 +81,12 @@ def test_adapter_matches_like_the_reference_callers(selftest_bin, tmp_path, orac
     assert np.allclose(out["second_t"], T[:3, 3], atol=1e-12)        # a copy-constructed tracker gives the same answer
     assert out["err_sum"] > 0 and out["level1_w"] == 320
     assert "Level: 3" in r.stderr and "Termination:" in r.stderr      # operator<< of Stats
+    # N1: LocalTracker's pair of alignments and the validator's proposal loop as one batched call each
+    assert out["batch_equal"] == 1 and out["proposals_equal"] == 1
+    # N4: keyframe-selection scores (tracking_result_evaluation.cpp:26-62) on identical results are exactly 1
+    assert out["entropy_ratio_first"] == 1.0 and out["entropy_ratio_avg"] == 1.0 and out["ll_ratio"] == 1.0 and out["nll_ratio"] == 1.0
+    info = np.array(fa["information"])
+    # Information follows the (chaotic, pair-bug-sensitive) scale estimate of the last iteration: entries agree to ~1e-2 of
+    # the largest one with FAITHFUL, i.e. log det to a few percent (measured 89.35 vs 90.49)
+    expected = np.log(np.linalg.det(info))
+    assert np.isfinite(out["logdet"]) and abs(out["logdet"] - expected) < 0.03 * abs(expected)

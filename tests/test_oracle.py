@@ -174,3 +174,15 @@ def test_initial_estimate_and_mu(oracle):
     dt, dr = pose_delta(g["faithful_T"], r["T"])
     assert dt < 4 * POSE_TOL_T and dr < 4 * POSE_TOL_R
     assert all(np.isfinite(it["prior"]) for it in r["iterations"])
+
+
+def test_bgr_to_grey_known_answers(oracle):
+    """OpenCV's published 8-bit BGR2GRAY (fixed point, 14-bit shift): the well-known grey values of the primaries."""
+    px = np.array([[[255, 0, 0], [0, 255, 0], [0, 0, 255], [255, 255, 255], [0, 0, 0], [12, 200, 77]]], dtype=np.uint8)
+    g = oracle.bgr_to_grey(px)[0]
+    assert g.tolist()[:5] == [29.0, 150.0, 76.0, 255.0, 0.0]
+    assert g[5] == float((12 * 1868 + 200 * 9617 + 77 * 4899 + 8192) >> 14)
+    rng = np.random.default_rng(5)
+    img = rng.integers(0, 256, size=(37, 53, 3), dtype=np.uint8)
+    ref = ((img[..., 0].astype(np.int64) * 1868 + img[..., 1].astype(np.int64) * 9617 + img[..., 2].astype(np.int64) * 4899 + 8192) >> 14)
+    assert np.array_equal(oracle.bgr_to_grey(img), ref.astype(np.float32))
