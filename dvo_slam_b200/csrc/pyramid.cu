@@ -17,7 +17,7 @@ __device__ __forceinline__ bool is_nan(float v) { return v != v; }
 // level l intensity = ((a+b)+c)+d)/4 of the 2x2 block of level l-1 (rgbd_image.cpp:38-55), into P0.x (the Z slot is
 // filled by the finish pass).  kFromInput: level 1 reads the input image, which is level 0's intensity.
 template <bool kFromInput>
-__global__ void k_pyr_intensity_down(const float* __restrict__ I0, size_t in_stride, float2* __restrict__ planes,
+__global__ void k_pyr_intensity_down(const float* __restrict__ I0, size_t in_stride, int aligned, float2* __restrict__ planes,
                                      size_t planes_per_image, size_t src_off, int sw, size_t dst_off, int dw, int dh) {
   int img = blockIdx.y;
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -26,9 +26,13 @@ __global__ void k_pyr_intensity_down(const float* __restrict__ I0, size_t in_str
   float2* D = planes + img * planes_per_image + dst_off;
   float a, b, c, d;
   if (kFromInput) {
-    const float2* r0 = reinterpret_cast<const float2*>(I0 + (size_t)img * in_stride + (size_t)(2 * y) * sw + 2 * x);
-    const float2 u = __ldg(r0), v = __ldg(r0 + sw / 2);    // sw is even: rows stay 8-byte aligned
-    a = u.x; b = u.y; c = v.x; d = v.y;
+    const float* p0 = I0 + (size_t)img * in_stride + (size_t)(2 * y) * sw + 2 * x;
+    if (aligned) {   // even width and image stride: every 2x2 block starts 8-byte aligned
+      const float2 u = __ldg(reinterpret_cast<const float2*>(p0)), v = __ldg(reinterpret_cast<const float2*>(p0 + sw));
+      a = u.x; b = u.y; c = v.x; d = v.y;
+    } else {
+      a = __ldg(p0); b = __ldg(p0 + 1); c = __ldg(p0 + sw); d = __ldg(p0 + sw + 1);
+    }
   } else {
     const float2* S = planes + img * planes_per_image + src_off;
     const float2* r0 = S + (size_t)(2 * y) * sw + 2 * x;
@@ -215,7 +219,8 @@ int pyramid_build_batch(dvo_b200_ctx* ctx, int n, const float* d_I, const float*
       q.w = L[l - 1].w / 2; q.h = L[l - 1].h / 2;
       q.fx = L[l - 1].fx * 0.5f; q.fy = L[l - 1].fy * 0.5f; q.ox = L[l - 1].ox * 0.5f; q.oy = L[l - 1].oy * 0.5f;
     }
-    if (q.w < 8 || q.h < 2 || (q.w & 1)) return set_error(ctx, DVO_B200_ERR_INVALID_ARGUMENT, "pyramid: level too small / odd width");
+    // odd sizes: the last column / row is dropped by the 2x2 mean exactly as in pyrDownMeanSmooth (rgbd_image.cpp:41)
+    if (q.w < 8 || q.h < 2) return set_error(ctx, DVO_B200_ERR_INVALID_ARGUMENT, "pyramid: level too small");
     q.n = q.w * q.h;
     q.words = (q.n + 31) / 32;
     q.plane_off = plane_f2; plane_f2 += 3 * (size_t)q.n;
@@ -250,8 +255,8 @@ int pyramid_build_batch(dvo_b200_ctx* ctx, int n, const float* d_I, const float*
       ctx->launches += 1;
       if (l == 0) continue;   // level 0 takes its intensity from the input image
       dim3 g((q.n + T - 1) / T, n);
-      if (l == 1) k_pyr_intensity_down<true><<<g, T, 0, st>>>(d_I, (size_t)w * h, planes, plane_f2, 0, L[0].w, q.plane_off, q.w, q.h);
-      else k_pyr_intensity_down<false><<<g, T, 0, st>>>(nullptr, 0, planes, plane_f2, L[l - 1].plane_off, L[l - 1].w, q.plane_off, q.w, q.h);
+      if (l == 1) k_pyr_intensity_down<true><<<g, T, 0, st>>>(d_I, (size_t)w * h, (((size_t)w * h) | (size_t)w) % 2 == 0 ? 1 : 0, planes, plane_f2, 0, L[0].w, q.plane_off, q.w, q.h);
+      else k_pyr_intensity_down<false><<<g, T, 0, st>>>(nullptr, 0, 0, planes, plane_f2, L[l - 1].plane_off, L[l - 1].w, q.plane_off, q.w, q.h);
       ctx->launches += 1;
     }
     for (int l = 0; l < levels; ++l) {

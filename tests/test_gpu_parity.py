@@ -248,6 +248,34 @@ def test_config5_1280x960_six_levels_with_damping(engine, oracle):
     assert gt < 5e-3 and gr < 2e-3                      # and it is the true motion
 
 
+def test_odd_image_sizes(engine, oracle):
+    """Sizes that are not multiples of 2^levels or 32: the 2x2 mean drops the last column / row like pyrDownMeanSmooth
+    (rgbd_image.cpp:41), rounds of 32 pixels end mid-row.  Pyramid bit-exact, alignment as MIRROR."""
+    from dvo_slam_b200 import synth
+    scfg = synth.SceneConfig(width=203, height=155, intrinsics=(164.0, 163.5, 101.3, 77.2))
+    pair = synth.make_pair(77, scfg)
+    K = pair["intrinsics"]
+    a = {k: pair[k].numpy() for k in ("I_ref", "Z_ref", "I_cur", "Z_cur")}
+    gp = (engine.pyramid(a["I_ref"], a["Z_ref"], K, 3), engine.pyramid(a["I_cur"], a["Z_cur"], K, 3))
+    op = (oracle.Pyramid(a["I_ref"], a["Z_ref"], K, 3), oracle.Pyramid(a["I_cur"], a["Z_cur"], K, 3))
+    for lvl, (w, h) in enumerate(((203, 155), (101, 77), (50, 38))):
+        got, want = gp[0].download(lvl), op[0].planes(lvl)
+        assert got.shape == (6, h, w) == want.shape
+        want[1][np.isnan(want).any(axis=0)] = np.nan               # device depth is masked where any channel is NaN
+        for c in range(6):
+            assert nan_equal(got[c], want[c]), (lvl, c)
+        assert gp[0].select(lvl)[0] == oracle.select(op[0], lvl)[0]
+    cfg, ocfg = _cfgs(oracle, 2, 0)
+    r = engine.match(gp[0], gp[1], cfg)
+    mi = oracle.match(op[0], op[1], ocfg, oracle.mode("mirror"))
+    fa = oracle.match(op[0], op[1], ocfg, oracle.mode("faithful"))
+    dt, dr = pose_delta(fa["T"], r.transformation)
+    assert dt < 4 * POSE_TOL_T and dr < 4 * POSE_TOL_R          # 203x155: a quarter of the resolution the tolerance is stated for
+    if [l["num_iterations"] for l in r.levels] == [l["num_iterations"] for l in mi["levels"]]:
+        dt, dr = pose_delta(mi["T"], r.transformation)
+        assert dt < 1e-4 and dr < 1e-4
+
+
 def test_degenerate_inputs(engine, oracle, full_pairs):
     a = full_pairs[3]
     cfg, ocfg = _cfgs(oracle, 4, 0)
