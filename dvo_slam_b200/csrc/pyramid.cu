@@ -290,7 +290,7 @@ int pyramid_build_batch(dvo_b200_ctx* ctx, int n, const float* d_I, const float*
 int pyramid_reselect(dvo_b200_ctx* ctx, dvo_b200_pyramid* p, float ti, float td) {
   if (p->sel_ti == ti && p->sel_td == td) return 0;
   cudaStream_t st = ctx->stream;
-  ProfScope prof(ctx, 4, p->levels);
+  ProfScope prof(ctx, 4, 2 * p->levels);
   for (int l = 0; l < p->levels; ++l) {
     const LevelInfo& q = p->L[l];
     const int T = 256;
