@@ -106,6 +106,7 @@ struct PairState {
   double nll_cur, prior_cur;
   int have_done;
   float precision[4];           // P_k (row-major), also P_{k-1} on entry of an iteration
+  float precision_prev[4];      // P_{k-1}: what the weights of the current iteration were computed with
   float ll;
   float kt[12];                 // K * float(estimate)[0:3,:]  (dense_tracking_impl.cpp:142-152)
   long long n;                  // valid constraints of the current iteration

@@ -21,16 +21,17 @@ constexpr unsigned kFullMask = 0xffffffffu;
 constexpr int kSegmentPixels = 256;     // pixels per warp segment (8 rounds of 32)
 constexpr int kSegmentsPerTile = 4;     // a 128-thread CTA covers 4 consecutive segments = 1024 pixels
 
-// record planes of one pair at one level (scratch): E = (e.i, e.z), G = (e.idx, e.idy), H = (e.zdx, e.zdy), W = weight
+// record planes of one pair at one level (scratch): E = (e.i, e.z), G = (e.idx, e.idy), H = (e.zdx, e.zdy),
+// Z = depth of the reference point (28 B per pixel)
 struct RecordPlanes {
-  float2* E; float2* G; float2* H; float* W;
+  float2* E; float2* G; float2* H; float* Z;
 };
 __host__ __device__ __forceinline__ RecordPlanes record_planes(float* base, size_t n) {
   RecordPlanes r;
   r.E = reinterpret_cast<float2*>(base);
   r.G = r.E + n;
   r.H = r.G + n;
-  r.W = reinterpret_cast<float*>(r.H + n);
+  r.Z = reinterpret_cast<float*>(r.H + n);
   return r;
 }
 constexpr int kRecordFloatsPerPixel = 7;
@@ -227,20 +228,23 @@ __device__ __forceinline__ void cta_export_segments(const float (*sm_exp)[kSegEx
 
 // Student-t weight of computeWeightsSse (dense_tracking_impl.cpp:657-707): w = 7 / (5 + r^T P r), nu = 5;
 // w = 1 on the first iteration of a level (dense_tracking.cpp:286-289).
-__device__ __forceinline__ float student_weight(const StageConsts& c, float ei, float ez) {
-  if (c.first_iteration) return 1.0f;
-  const f2 q = fma2(bc(ez), c.Pb, mul2(bc(ei), c.Pa));        // (ei P00 + ez P10, ei P01 + ez P11)
+__device__ __forceinline__ float student_weight(bool first_iteration, f2 Pa, f2 Pb, float ei, float ez) {
+  if (first_iteration) return 1.0f;
+  const f2 q = fma2(bc(ez), Pb, mul2(bc(ei), Pa));        // (ei P00 + ez P10, ei P01 + ez P11)
   const float d = fmaf(lo(q), ei, hi(q) * ez);
   return 7.0f * rcp_fast(5.0f + d);
 }
+__device__ __forceinline__ float student_weight(const StageConsts& c, float ei, float ez) {
+  return student_weight(c.first_iteration != 0, c.Pa, c.Pb, ei, ez);
+}
 
-__device__ __forceinline__ void store_record(const RecordPlanes& rec, int idx, int n, bool valid, f2 E, f2 G, f2 H, float wgt) {
+__device__ __forceinline__ void store_record(const RecordPlanes& rec, int idx, int n, bool valid, f2 E, f2 G, f2 H, float z) {
   if (idx < n) {
     if (valid) {
       __stcs(rec.E + idx, make_float2(lo(E), hi(E)));    // st.global.cs: streamed, evict-first in L2
       __stcs(rec.G + idx, make_float2(lo(G), hi(G)));
       __stcs(rec.H + idx, make_float2(lo(H), hi(H)));
-      __stcs(rec.W + idx, wgt);
+      __stcs(rec.Z + idx, z);
     } else {
       const float nanf_ = __int_as_float(0x7fc00000);
       __stcs(rec.E + idx, make_float2(nanf_, nanf_));
@@ -367,7 +371,9 @@ __device__ __forceinline__ void stage_a_segment(const PairLevel& pl, const Stage
       const bool v = finish_pixel(pcur, tcur, c, E, G, H);
       const float ei = lo(E), ez = hi(E);
       const float wgt = student_weight(c, ei, ez);
-      store_record(rec, base + lane, end, v, E, G, H, wgt);   // end <= n: never touch another warp's pixels
+      // 4th plane = reference depth: stage B recomputes the weight (6 flops) instead of reading it plus the
+      // reference plane again.  end <= n: never touch another warp's pixels
+      store_record(rec, base + lane, end, v, E, G, H, pcur.z);
       if (!odd) { sv = v; sw = wgt; sei = ei; sez = ez; }
       else scale_round64(ss, lane, sv, sw, sei, sez, v, wgt, ei, ez);
       odd = !odd;
@@ -381,6 +387,8 @@ __device__ __forceinline__ void stage_a_segment(const PairLevel& pl, const Stage
 struct StageBConsts {
   float P00, P01, P10, P11;   // P_k
   float l, wd0, wd1;          // P_k = [1 l; 0 1]^T-style factors, see stage_b_segment
+  f2 Pa, Pb;                  // P_{k-1} as stage A used it for the weights
+  bool first_iteration;
 };
 
 constexpr int kNormalValues = 28;   // log-likelihood sum, 21 upper-triangular A (row-major), 6 b
@@ -427,7 +435,7 @@ __device__ __forceinline__ void stage_b_rank1(StageBAcc& acc, const f2 V[3], flo
 //   a = [1/z, 0, -x/z^2, a2 y, 1 - a2 x, -y/z], b = [0, 1/z, -y/z^2, b2 y - 1, -a3, x/z], c = [0, 0, 1, y, -x, 0].
 struct StageBInput {   // everything stage B reads for one pixel; loaded two rounds ahead of its use
   float2 e, g, h;
-  float w, z, tx, ty;
+  float z, tx, ty;
 };
 
 __device__ __forceinline__ StageBInput load_stage_b_input(const PairLevel& pl, const RecordPlanes& rec, int idx, int w,
@@ -437,8 +445,7 @@ __device__ __forceinline__ StageBInput load_stage_b_input(const PairLevel& pl, c
   in.e = __ldcs(rec.E + i);      // ld.global.cs: read once, do not keep in L2
   in.g = __ldcs(rec.G + i);
   in.h = __ldcs(rec.H + i);
-  in.w = __ldcs(rec.W + i);
-  in.z = __ldcs(pl.r0 + i).y;
+  in.z = __ldcs(rec.Z + i);      // the reference depth as stage A left it
   const int y = (int)__umulhi((unsigned)i, wmagic);
   const int x = i - y * w;
   in.tx = __ldg(pl.rtmpl + x);
@@ -496,8 +503,9 @@ __device__ __forceinline__ void stage_b_segment(const PairLevel& pl, const Stage
     V1[1] = fma2(bc(in.h.x), A23, fma2(bc(in.h.y), B23, NC23));
     V1[2] = fma2(bc(in.h.x), A45, fma2(bc(in.h.y), B45, NC45));
     // b -= J^T W r
-    stage_b_rank1(acc, V0, in.w * c.wd0, -fmaf(c.l, ez, ei));
-    stage_b_rank1(acc, V1, in.w * c.wd1, -ez);
+    const float wgt = student_weight(c.first_iteration, c.Pa, c.Pb, ei, ez);   // same operands, same operations as stage A
+    stage_b_rank1(acc, V0, wgt * c.wd0, -fmaf(c.l, ez, ei));
+    stage_b_rank1(acc, V1, wgt * c.wd1, -ez);
   }
 }
 
@@ -519,6 +527,9 @@ __device__ __forceinline__ void load_stage_b_consts(const PairState& st, StageBC
   c.l = c.P01 / c.P00;
   c.wd0 = c.P00;
   c.wd1 = c.P11 - c.P01 * c.l;
+  c.Pa = pk(__ldcg(&st.precision_prev[0]), __ldcg(&st.precision_prev[1]));
+  c.Pb = pk(__ldcg(&st.precision_prev[2]), __ldcg(&st.precision_prev[3]));
+  c.first_iteration = __ldcg(&st.iteration) == 0;
 }
 
 }  // namespace dvo_b200

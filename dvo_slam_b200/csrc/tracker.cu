@@ -204,6 +204,7 @@ __device__ __noinline__ void pair_mid_warp(PairState& st, int pair, const float*
       // precision = covariance.inverse() (Eigen 2x2 inverse, dense_tracking.cpp:295), float, unfused
       float det = __fsub_rn(__fmul_rn(C0, C3), __fmul_rn(C1, C1));
       float invdet = __fdiv_rn(1.0f, det);
+      for (int i = 0; i < 4; ++i) st.precision_prev[i] = st.precision[i];
       st.precision[0] = __fmul_rn(C3, invdet);
       st.precision[1] = __fmul_rn(-C1, invdet);
       st.precision[2] = __fmul_rn(-C1, invdet);
