@@ -15,10 +15,6 @@
 namespace dvo_b200 {
 
 constexpr int kMaxLevels = DVO_B200_MAX_LEVELS;
-constexpr int kTilePixels = 1024;   // pixels per CTA tile (contiguous in row-major order)
-constexpr int kTileThreads = 256;   // 8 warps x 4 rounds x 32 lanes
-constexpr int kScaleExportFloats = 12;
-constexpr int kNormalPartialFloats = 28;  // ll-sum, 21 upper-triangular A, 6 b
 
 // ---- device image layout --------------------------------------------------------------------
 // Per image, per level l: three float2 planes of h_l*w_l elements, row-major, no row padding:
@@ -123,19 +119,13 @@ struct PairState {
   double result_T[16], result_info[36], result_ll;
 };
 
-struct ScaleSeg {               // monoid element of the pairwise scale sum (see tracker.cu)
-  int n;
-  float S0[3], S1[3];
-  float wf, wl, ol[3];
-};
-
 struct Workspace {              // per-ctx scratch for a lock-step batch
   PairLevel* d_pair_level = nullptr;
   PairState* d_state = nullptr;
-  float* d_records = nullptr;        // per pair 6 planes of N floats {ei, ez, gx, gy, hx, hy}
-  float* d_scale_export = nullptr;   // per pair, per tile: kScaleExportFloats
-  int* d_tile_base = nullptr;        // per pair, per tile: exclusive prefix of valid counts
-  float* d_normal_partial = nullptr; // per pair, per tile: kNormalPartialFloats
+  float* d_records = nullptr;        // per squad: record planes E, G, H (float2) and Z (float) of the pair in flight
+  float* d_scale_export = nullptr;   // per squad, per CTA: scale summary (kCtaExportFloats)
+  int* d_tile_base = nullptr;        // per squad, per CTA: exclusive prefix of valid counts
+  float* d_normal_partial = nullptr; // per squad, per CTA: log-likelihood sum, 21 upper-triangular A, 6 b
   int* d_active = nullptr;           // number of pairs still active on the level
   dvo_b200_iteration_stats* d_iter_log = nullptr;
   int* h_active = nullptr;           // pinned

@@ -18,8 +18,9 @@
 namespace dvo_b200 {
 
 constexpr unsigned kFullMask = 0xffffffffu;
-constexpr int kSegmentPixels = 256;     // pixels per warp segment (8 rounds of 32)
-constexpr int kSegmentsPerTile = 4;     // a 128-thread CTA covers 4 consecutive segments = 1024 pixels
+constexpr int kSegmentPixels = 256;     // pixels per warp segment on the test-hook path (8 rounds of 32); the persistent
+                                        // kernel sizes its segments per level (LevelPlan in tracker.cu)
+constexpr int kSegmentsPerTile = 4;     // warps per CTA: a CTA covers 4 consecutive segments
 
 // record planes of one pair at one level (scratch): E = (e.i, e.z), G = (e.idx, e.idy), H = (e.zdx, e.zdy),
 // Z = depth of the reference point (28 B per pixel)

@@ -4,12 +4,14 @@
 // Per Gauss-Newton iteration the reference makes five passes over the points
 // (computeResidualsSse, computeWeightsSse, computeScaleSse, computeCompleteDataLogLikelihood and the
 // normal-equation loop, dense_tracking.cpp:271-343).  Precision P_k is a global reduction that the
-// log-likelihood and J^T W J depend on, so there are exactly two data-parallel stages:
-//   stage A (k_residual): warp/interpolate/residual/occlusion test, Student-t weight from P_{k-1},
-//                         pairwise scale sums, residual record kept for stage B
-//   stage B (k_normal):   log-likelihood terms and the 21+6 normal-equation coefficients with W = w*P_k
-// with one tiny per-pair kernel after each (k_pair_mid: P_k; k_pair_end: accept test, 6x6 LDL^T solve,
-// SE(3) update, termination logic).
+// log-likelihood and J^T W J depend on, so there are exactly two data-parallel stages (stages.cuh):
+//   stage A: warp/interpolate/residual/occlusion test, Student-t weight from P_{k-1}, pairwise scale
+//            sums, residual record kept for stage B
+//   stage B: log-likelihood terms and the 21+6 normal-equation coefficients with W = w*P_k
+// each followed by a small per-pair step (pair_mid_warp: P_k; pair_end_cta: accept test, 6x6 LDL^T
+// solve, SE(3) update, termination logic).  match() runs them inside ONE persistent cooperative
+// kernel per pyramid level (k_level_persistent); the four plain kernels k_residual / k_pair_mid /
+// k_normal / k_pair_end launch the same device functions for the test hooks (residual image, linearize).
 #include "common.cuh"
 #include "stages.cuh"
 
