@@ -110,7 +110,8 @@ def test_bench_reference_arm_runs_on_cpu():
 
 def test_bench_product_arm_fails_loudly_without_a_device():
     """The measured arm has no CPU fallback: without a CUDA device it exits non-zero and says why."""
-    import torch
+    import subprocess
+    import sys
     if torch.cuda.is_available():
         pytest.skip("a CUDA device is present")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
