@@ -105,8 +105,8 @@ int dvo_b200_create(int device, void* stream, dvo_b200_ctx** out) {
     ctx->own_stream = true;
   }
   if (getenv("DVO_B200_TIMING")) {
-    cudaMalloc((void**)&ctx->d_dbg, sizeof(unsigned long long) * 64);
-    cudaMemset(ctx->d_dbg, 0, sizeof(unsigned long long) * 64);
+    cudaMalloc((void**)&ctx->d_dbg, sizeof(unsigned long long) * 128);
+    cudaMemset(ctx->d_dbg, 0, sizeof(unsigned long long) * 128);
   }
   *out = ctx;
   return 0;
@@ -119,8 +119,9 @@ int dvo_b200_destroy(dvo_b200_ctx* ctx) {
   drain_profile(ctx);
   for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
   Workspace& ws = ctx->ws;
-  cudaFree(ws.d_pair_level); cudaFree(ws.d_state); cudaFree(ws.d_records); cudaFree(ws.d_scale_export);
-  cudaFree(ws.d_tile_base); cudaFree(ws.d_normal_partial); cudaFree(ws.d_active); cudaFree(ws.d_iter_log); cudaFree(ws.d_squads);
+  cudaFree(ws.d_pair_level); cudaFree(ws.d_state); cudaFree(ws.d_row_exports); cudaFree(ws.d_row_base);
+  cudaFree(ws.d_cta_exports); cudaFree(ws.d_cta_base); cudaFree(ws.d_normal_partial); cudaFree(ws.d_dump);
+  cudaFree(ws.d_iter_log); cudaFree(ws.d_squads);
   if (ws.h_active) cudaFreeHost(ws.h_active);
   pool_close(ctx);
   cudaFree(ctx->d_stage);
@@ -137,7 +138,7 @@ void* dvo_b200_stream(dvo_b200_ctx* ctx) { return ctx ? (void*)ctx->stream : nul
 int dvo_b200_synchronize(dvo_b200_ctx* ctx) {
   if (!ctx) return DVO_B200_ERR_INVALID_ARGUMENT;
   DVO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  return 0;
+  return check_level_flags(ctx);   // a timeout inside dvo_b200_match_batch_device surfaces here
 }
 
 const char* dvo_b200_last_error(dvo_b200_ctx* ctx) { return ctx ? ctx->last_error.c_str() : "null context"; }
@@ -229,13 +230,13 @@ int dvo_b200_pyramid_create_raw(dvo_b200_ctx* ctx, const uint8_t* grey, const ui
 
 int dvo_b200_pyramid_retain(dvo_b200_pyramid* p) {
   if (!p) return DVO_B200_ERR_INVALID_ARGUMENT;
-  p->refcount++;
+  p->refcount.fetch_add(1, std::memory_order_relaxed);
   return 0;
 }
 
 int dvo_b200_pyramid_release(dvo_b200_pyramid* p) {
   if (!p) return DVO_B200_ERR_INVALID_ARGUMENT;
-  if (--p->refcount == 0) {
+  if (p->refcount.fetch_sub(1, std::memory_order_acq_rel) == 1) {
     // No synchronisation: the slab returns to the owning ctx's pool and is only ever rewritten by
     // work enqueued later on that ctx's stream (stream order protects queued readers).  A second
     // ctx that uses this pyramid holds a reference until its (blocking) match call has returned.
@@ -261,14 +262,22 @@ int dvo_b200_pyramid_download(dvo_b200_ctx* ctx, const dvo_b200_pyramid* p, int3
   cudaSetDevice(ctx->device);
   const LevelInfo& L = p->L[level];
   size_t N = L.n;
-  std::vector<float> tmp(6 * N);
+  const size_t plane = (size_t)L.pitch * L.h;      // float2 elements per plane, rows padded to the pitch
+  std::vector<float> tmp(6 * plane);
   DVO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  DVO_CUDA(ctx, cudaMemcpy(tmp.data(), p->planes + L.plane_off, sizeof(float) * 6 * N, cudaMemcpyDeviceToHost));
-  ctx->d2h_bytes += sizeof(float) * 6 * N;
-  for (int pl = 0; pl < 3; ++pl)
-    for (size_t i = 0; i < N; ++i) {
-      planes6[(2 * pl) * N + i] = tmp[pl * 2 * N + 2 * i];
-      planes6[(2 * pl + 1) * N + i] = tmp[pl * 2 * N + 2 * i + 1];
+  DVO_CUDA(ctx, cudaMemcpy(tmp.data(), p->planes + L.plane_off, sizeof(float) * 6 * plane, cudaMemcpyDeviceToHost));
+  ctx->d2h_bytes += sizeof(float) * 6 * plane;
+  // device planes: P0 = (I, Z'), P1 = (Ix, Iy), P2 = (I, Z).  The depth gradients are not stored (the tracker forms
+  // them from P2 on the fly): restate calculateDerivativeX/Y<float> on the true depth (rgbd_image.cpp:419-472).
+  auto Zt = [&](int y, int x) { return tmp[4 * plane + 2 * ((size_t)y * L.pitch + x) + 1]; };
+  for (int y = 0; y < L.h; ++y)
+    for (int x = 0; x < L.w; ++x) {
+      const size_t o = 2 * ((size_t)y * L.pitch + x), i = (size_t)y * L.w + x;
+      planes6[0 * N + i] = tmp[o]; planes6[1 * N + i] = tmp[o + 1];
+      planes6[2 * N + i] = tmp[2 * plane + o]; planes6[3 * N + i] = tmp[2 * plane + o + 1];
+      const int xp = x > 0 ? x - 1 : 0, xn = x < L.w - 1 ? x + 1 : L.w - 1, yp = y > 0 ? y - 1 : 0, yn = y < L.h - 1 ? y + 1 : L.h - 1;
+      const float dzx = Zt(y, xn) - Zt(y, xp), dzy = Zt(yn, x) - Zt(yp, x);
+      planes6[4 * N + i] = dzx * 0.5f; planes6[5 * N + i] = dzy * 0.5f;
     }
   return 0;
 }
@@ -344,15 +353,19 @@ int dvo_b200_profile_read(dvo_b200_ctx* ctx, double ms_out[8], int64_t launches_
   cudaSetDevice(ctx->device);
   drain_profile(ctx);
   if (ctx->d_dbg) {   // developer timing dump (DVO_B200_TIMING=1)
-    unsigned long long h[64];
+    unsigned long long h[128];
     cudaStreamSynchronize(ctx->stream);
     cudaMemcpy(h, ctx->d_dbg, sizeof(h), cudaMemcpyDeviceToHost);
     static const char* names[8] = {"stageA", "stageB", "waitA", "waitB", "mid", "end", "queue", "total"};
     for (int l = 0; l < 8; ++l) {
-      if (!h[8 * l + 7]) continue;
+      const unsigned long long* v = h + 16 * l;
+      if (!v[7]) continue;
       fprintf(stderr, "[dvo_b200 timing] level-slot %d:", l);
-      for (int i = 0; i < 8; ++i) fprintf(stderr, " %s=%.1f%%", names[i], 100.0 * (double)h[8 * l + i] / (double)h[8 * l + 7]);
-      fprintf(stderr, " (cta-ms total %.1f)\n", (double)h[8 * l + 7] * 1e-6);
+      for (int i = 0; i < 8; ++i) fprintf(stderr, " %s=%.1f%%", names[i], 100.0 * (double)v[i] / (double)v[7]);
+      fprintf(stderr, " (cta-ms total %.1f)\n", (double)v[7] * 1e-6);
+      fprintf(stderr, "[dvo_b200 timing]   consumer warp 0: wait-full %.1f%% of stage A, %.1f%% of stage B; producer: descriptor %.1f%%, "
+                      "wait-empty %.1f%% of its stage time\n", 100.0 * (double)v[9] / (double)(v[8] + 1), 100.0 * (double)v[11] / (double)(v[10] + 1),
+              100.0 * (double)v[12] / (double)(v[14] + v[15] + 1), 100.0 * (double)v[13] / (double)(v[14] + v[15] + 1));
     }
     if (reset) cudaMemset(ctx->d_dbg, 0, sizeof(h));
   }

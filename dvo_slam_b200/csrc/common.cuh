@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -17,22 +18,38 @@ namespace dvo_b200 {
 constexpr int kMaxLevels = DVO_B200_MAX_LEVELS;
 
 // ---- device image layout --------------------------------------------------------------------
-// Per image, per level l: three float2 planes of h_l*w_l elements, row-major, no row padding:
-//   P0 = (I, Z')   P1 = (Ix, Iy)   P2 = (Zx, Zy)
+// Per image, per level l: four float2 planes of h_l rows, row pitch = w_l rounded up to even (every row
+// starts 16-byte aligned, which the bulk-copy engine requires of its sources):
+//   P0 = (I, Z')   P1 = (Ix, Iy)   P2 = (I, Z)   P3 = (I, Zsel)
 // Z' is the depth with NaN wherever ANY of the six channels is NaN at that pixel: a bilinear tap
 // on such a pixel makes the reference reject the point (cmpunord over the 8-vector,
 // dense_tracking_impl.cpp:261) and a reference point there fails isPointOk (point_selection.h:63-66),
 // so one NaN test on the interpolated Z' replaces the reference's test on all lanes.
 // The 8-channel AoS "acceleration" image of the reference (rgbd_image.cpp:534-543) exists only to
-// make CPU gathers contiguous; pairs of channels as float2 give 8-byte gathers and let the
-// reference image be read as two planes (16 B/pixel) and the current as three (24 B/pixel).
+// make CPU gathers contiguous.  The tracker stages rectangular windows of ONE float2 plane of the
+// current image in shared memory: P0 for the residual/weight/scale stage, P2 (true depth) for the
+// linearisation stage, which forms the four gradient channels of every bilinear tap from the staged
+// (I, Z) neighbours with the very operations of calculateDerivativeX/Y (rgbd_image.cpp:419-472), so
+// gradient planes of the current image are never read (the depth gradients are not even stored).
+// Zsel is the depth where the pixel belongs to the reference point list of PointSelection::select
+// (point_selection.cpp:89-152; the odd last point that computeResidualsSse skips excluded) and NaN
+// elsewhere: the reference side of an alignment reads P3 and P1 and needs no mask lookup -- an
+// unselected point projects to NaN and fails the bounds test like any other rejected point.
 struct LevelInfo {
-  int w, h, n, words;          // words = ceil(n/32) selection-mask words
+  int w, h, n, words;          // n = w*h pixels, words = ceil(n/32) selection-mask words (linear index y*w+x)
+  int pitch;                   // row pitch of the planes in float2 elements (w rounded up to even)
+  int nbands, nstrips;         // tiles of kTileW x kTileH reference pixels: nbands x nstrips
   float fx, fy, ox, oy;        // IntrinsicMatrix of this level (intrinsic_matrix.cpp:90-93: whole K * 0.5)
-  size_t plane_off;            // float2 offset of P0 inside dvo_b200_pyramid::planes (P1 = +n, P2 = +2n)
+  size_t plane_off;            // float2 offset of P0 inside dvo_b200_pyramid::planes (P_k = + k*pitch*h)
   size_t mask_off;             // uint32 offset inside sel_mask
   size_t tmpl_off;             // float offset of tx[w] then ty[h] inside tmpl
+  size_t range_off;            // float2 offset of the per-tile depth range {zmin, zmax} inside tile_range
 };
+
+// tile geometry of the level kernel (tracker.cu) and of the per-tile depth ranges (pyramid.cu)
+constexpr int kTileW = 128;    // reference pixels per tile row: 4 warp rounds
+constexpr int kTileH = 7;      // tile rows = consumer warps of a CTA (warp q walks row q of every tile of a strip); 7 consumers +
+                               // 1 producer warp = 256 threads, two CTAs per SM at 128 registers per thread
 
 struct Slab;
 // Pool of released slabs of one context, keyed by size (release -> reuse instead of cudaFree).  Pyramids are
@@ -59,7 +76,7 @@ struct Slab {                  // one cudaMalloc shared by a batch of pyramids
 // opaque handle types of the C ABI
 struct dvo_b200_pyramid {
   dvo_b200_ctx* ctx = nullptr;
-  int refcount = 1;
+  std::atomic<int> refcount{1};   // retain/release may come from any host thread (boost::shared_ptr semantics)
   int levels = 0;
   dvo_b200::LevelInfo L[dvo_b200::kMaxLevels];
   dvo_b200::Slab* slab = nullptr;
@@ -67,6 +84,7 @@ struct dvo_b200_pyramid {
   uint32_t* sel_mask = nullptr;  // device: selection bitmasks of all levels (default thresholds)
   int* sel_info = nullptr;       // device: per level {S, last selected linear pixel index}
   float* tmpl = nullptr;         // device: per level tx[w], ty[h] point-cloud template (rgbd_image.cpp:197-198)
+  float2* tile_range = nullptr;  // device: per level, per tile {min, max} of the non-NaN Z' (min > max: none)
   float sel_ti = 0.f, sel_td = 0.f;  // thresholds the masks were built with
   uint64_t id = 0;
 };
@@ -75,11 +93,12 @@ namespace dvo_b200 {
 
 // ---- per-pair device state ---------------------------------------------------------------------
 struct PairLevel {              // what one alignment reads at the current level (uploaded per level)
-  const float2* r0; const float2* r1;  // reference P0, P1
+  const float2* r0; const float2* r1;  // reference P3 (I, Zsel), P1 (Ix, Iy)
   const uint32_t* rmask;               // reference selection mask
   const int* rsel;                     // {S, last selected pixel}
   const float* rtmpl;                  // tx[w], ty[h]
-  const float2* c0; const float2* c1; const float2* c2;  // current P0..P2
+  const float2* rrange;                // per-tile depth range of the reference
+  const float2* c0; const float2* c3;  // current P0 (I, Z') and P2 (I, Z)
   float cfx, cfy, cox, coy;            // current-image intrinsics (dense_tracking.cpp:212)
   long long max_valid_pixels;          // PointSelection::getMaximumNumberOfPoints
 };
@@ -119,18 +138,20 @@ struct PairState {
   double result_T[16], result_info[36], result_ll;
 };
 
-struct Workspace {              // per-ctx scratch for a lock-step batch
+struct Workspace {              // per-ctx scratch of the level kernel
   PairLevel* d_pair_level = nullptr;
   PairState* d_state = nullptr;
-  float* d_records = nullptr;        // per squad: record planes E, G, H (float2) and Z (float) of the pair in flight
-  float* d_scale_export = nullptr;   // per squad, per CTA: scale summary (kCtaExportFloats)
-  int* d_tile_base = nullptr;        // per squad, per CTA: exclusive prefix of valid counts
+  float* d_row_exports = nullptr;    // per squad: one scale summary per image row (kSegExportFloats)
+  int* d_row_base = nullptr;         // per squad, per row: valid points before the row inside its CTA
+  float* d_cta_exports = nullptr;    // per squad, per CTA: scale summary
+  int* d_cta_base = nullptr;         // per squad, per CTA: exclusive prefix of valid counts
   float* d_normal_partial = nullptr; // per squad, per CTA: log-likelihood sum, 21 upper-triangular A, 6 b
-  int* d_active = nullptr;           // number of pairs still active on the level
+  float* d_dump = nullptr;           // test hook: seven residual-record planes of one level
   dvo_b200_iteration_stats* d_iter_log = nullptr;
-  int* h_active = nullptr;           // pinned
+  int* h_active = nullptr;           // pinned: per level, the kernel's error flag
   char* d_squads = nullptr;          // persistent kernel: SquadState[nsquads] + {queue head, error flag}
-  size_t cap_pairs = 0, cap_records = 0, cap_export = 0, cap_segbase = 0, cap_partial = 0, cap_squads = 0, cap_iter_log = 0;
+  size_t cap_pairs = 0, cap_row_exports = 0, cap_row_base = 0, cap_cta_exports = 0, cap_cta_base = 0, cap_partial = 0,
+         cap_squads = 0, cap_iter_log = 0, cap_dump = 0;
 };
 
 }  // namespace dvo_b200
@@ -143,6 +164,7 @@ struct dvo_b200_ctx {
   bool own_stream = false;
   std::string last_error;
   int64_t launches = 0, h2d_bytes = 0, d2h_bytes = 0;
+  int pending_level_flags = 0;          // levels whose error flag has been copied to pinned memory but not yet checked
   uint64_t next_pyramid_id = 1;
   dvo_b200::Workspace ws;
   std::shared_ptr<dvo_b200::SlabPool> pool;   // pooled device slabs (see SlabPool)
@@ -189,6 +211,7 @@ int ensure_stage(dvo_b200_ctx* ctx, size_t dev_bytes, size_t host_bytes);
 int tracker_match_batch(dvo_b200_ctx* ctx, const dvo_b200_config* cfg, int n, dvo_b200_pyramid* const* refs,
                         dvo_b200_pyramid* const* curs, const double* T_init, dvo_b200_result* h_results,
                         void* d_results, dvo_b200_iteration_stats* iter_stats, int max_iter_stats);
+int check_level_flags(dvo_b200_ctx* ctx);   // after a stream synchronisation: did a level kernel report a timeout?
 int tracker_linearize(dvo_b200_ctx* ctx, const dvo_b200_config* cfg, dvo_b200_pyramid* ref, dvo_b200_pyramid* cur,
                       int level, const double* T, int use_weights, const float* prev_precision, int64_t* count,
                       float* precision_out, float* ll_out, double* A_out, double* b_out, float* planes7);

@@ -16,9 +16,11 @@ __device__ __forceinline__ bool is_nan(float v) { return v != v; }
 
 // level l intensity = ((a+b)+c)+d)/4 of the 2x2 block of level l-1 (rgbd_image.cpp:38-55), into P0.x (the Z slot is
 // filled by the finish pass).  kFromInput: level 1 reads the input image, which is level 0's intensity.
+// sp / dp: row pitch of the source / destination planes (float2 elements).
 template <bool kFromInput>
 __global__ void k_pyr_intensity_down(const float* __restrict__ I0, size_t in_stride, int aligned, float2* __restrict__ planes,
-                                     size_t planes_per_image, size_t src_off, int sw, size_t dst_off, int dw, int dh) {
+                                     size_t planes_per_image, size_t src_off, int sw, int sp, size_t dst_off, int dw, int dh,
+                                     int dp) {
   int img = blockIdx.y;
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= dw * dh) return;
@@ -35,25 +37,27 @@ __global__ void k_pyr_intensity_down(const float* __restrict__ I0, size_t in_str
     }
   } else {
     const float2* S = planes + img * planes_per_image + src_off;
-    const float2* r0 = S + (size_t)(2 * y) * sw + 2 * x;
-    const float2* r1 = r0 + sw;
+    const float2* r0 = S + (size_t)(2 * y) * sp + 2 * x;
+    const float2* r1 = r0 + sp;
     a = r0[0].x; b = r0[1].x; c = r1[0].x; d = r1[1].x;
   }
   float s = __fadd_rn(a, b);
   s = __fadd_rn(s, c);
   s = __fadd_rn(s, d);
-  D[idx] = make_float2(s * 0.25f, 0.f);
+  D[(size_t)y * dp + x] = make_float2(s * 0.25f, 0.f);
 }
 
-// gradients (clamped central differences), masked depth, default selection mask for one level.
+// gradients (clamped central differences), masked and true depth, default selection mask and reference plane
+// (I, Zsel: depth where the pixel is selected, NaN elsewhere) for one level.
 // Depth of level l is the pure subsample chain of level 0 (rgbd_image.cpp:127-139): Z_l(y,x) = Z_0(y<<l, x<<l).
 // Level 0 reads its intensity straight from the input image I0 (no intermediate copy); the other levels read the
 // intensity that k_pyr_intensity_down left in P0.x.  The selection count / last selected index are derived from
-// the masks afterwards (k_sel_info): no atomics here.
+// the masks afterwards (k_sel_info): no atomics here.  Threads walk the linear pixel index y*w+x (the order of the
+// selection mask); the planes are addressed with the row pitch.
 template <bool kLevel0>
 __global__ void __launch_bounds__(256)
 k_pyr_finish(const float* __restrict__ I0, const float* __restrict__ Z0, int w0, int n0, float2* __restrict__ planes,
-             size_t planes_per_image, size_t plane_off, int w, int h, int level,
+             size_t planes_per_image, size_t plane_off, int w, int h, int pitch, int level,
              uint32_t* __restrict__ masks, size_t mask_words_per_image, size_t mask_off, float ti, float td) {
   const int img = blockIdx.y;
   const int n = w * h;
@@ -62,9 +66,11 @@ k_pyr_finish(const float* __restrict__ I0, const float* __restrict__ Z0, int w0,
   bool sel = false;
   if (in) {
     const int y = idx / w, x = idx - y * w;
+    const size_t plane = (size_t)pitch * h;
     float2* P0 = planes + img * planes_per_image + plane_off;
-    float2* P1 = P0 + n;
-    float2* P2 = P1 + n;
+    float2* P1 = P0 + plane;
+    float2* P2 = P1 + plane;
+    float2* P3 = P2 + plane;   // P2 = (I, Z), P3 = (I, Zsel); the depth gradients are not stored
     const float* Z = Z0 + (size_t)img * n0;
     const int xp = max(x - 1, 0), xn = min(x + 1, w - 1), yp = max(y - 1, 0), yn = min(y + 1, h - 1);
     float I, ixp, ixn, iyp, iyn;
@@ -73,7 +79,9 @@ k_pyr_finish(const float* __restrict__ I0, const float* __restrict__ Z0, int w0,
       I = __ldg(Ii + idx); ixp = __ldg(Ii + y * w + xp); ixn = __ldg(Ii + y * w + xn);
       iyp = __ldg(Ii + yp * w + x); iyn = __ldg(Ii + yn * w + x);
     } else {
-      I = P0[idx].x; ixp = P0[y * w + xp].x; ixn = P0[y * w + xn].x; iyp = P0[yp * w + x].x; iyn = P0[yn * w + x].x;
+      const size_t row = (size_t)y * pitch;
+      I = P0[row + x].x; ixp = P0[row + xp].x; ixn = P0[row + xn].x;
+      iyp = P0[(size_t)yp * pitch + x].x; iyn = P0[(size_t)yn * pitch + x].x;
     }
     const float ix = (ixn - ixp) * 0.5f;
     const float iy = (iyn - iyp) * 0.5f;
@@ -83,14 +91,47 @@ k_pyr_finish(const float* __restrict__ I0, const float* __restrict__ Z0, int w0,
     const float zy = (__ldg(Z + (size_t)(yn << level) * w0 + (x << level)) - __ldg(Z + (size_t)(yp << level) * w0 + (x << level))) * 0.5f;
     const bool bad = is_nan(I) || is_nan(ix) || is_nan(iy) || is_nan(z) || is_nan(zx) || is_nan(zy);
     const float zm = bad ? __int_as_float(0x7fc00000) : z;
-    P0[idx] = make_float2(I, zm);
-    P1[idx] = make_float2(ix, iy);
-    P2[idx] = make_float2(zx, zy);
+    const size_t o = (size_t)y * pitch + x;
     // ValidPointAndGradientThresholdPredicate::isPointOk (point_selection.h:63-66)
     sel = !bad && (fabsf(ix) > ti || fabsf(iy) > ti || fabsf(zx) > td || fabsf(zy) > td);
+    const float nanv = __int_as_float(0x7fc00000);
+    P0[o] = make_float2(I, zm);
+    P1[o] = make_float2(ix, iy);
+    P2[o] = make_float2(I, z);
+    P3[o] = make_float2(I, sel ? z : nanv);
+    if (x == w - 1 && pitch > w) {   // the pad column of an odd width: never selected, never a valid tap
+      P0[o + 1] = make_float2(0.f, nanv); P1[o + 1] = make_float2(0.f, 0.f);
+      P2[o + 1] = make_float2(0.f, nanv); P3[o + 1] = make_float2(0.f, nanv);
+    }
   }
   const unsigned m = __ballot_sync(0xffffffffu, sel);
   if ((threadIdx.x & 31) == 0 && idx < ((n + 31) / 32) * 32) masks[img * mask_words_per_image + mask_off + (idx >> 5)] = m;
+}
+
+// {min, max} of the non-NaN Z' of every tile of kTileW x kTileH pixels (one warp per tile).  The level kernel
+// projects the tile's corner rays at both depths to bound the window of the current image its taps fall into.
+__global__ void k_tile_range(const float2* __restrict__ planes, size_t planes_per_image, size_t plane_off, int w, int h,
+                             int pitch, int nbands, int ntiles, float2* __restrict__ ranges, size_t ranges_per_image,
+                             size_t range_off) {
+  const int img = blockIdx.y;
+  const int tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (tile >= ntiles) return;
+  const int lane = threadIdx.x & 31;
+  const int s = tile / nbands, b = tile - s * nbands;
+  const float2* P0 = planes + img * planes_per_image + plane_off;
+  float lo = 3.0e38f, hi = -3.0e38f;
+  const int x0 = b * kTileW, x1 = min(x0 + kTileW, w), y0 = s * kTileH, y1 = min(y0 + kTileH, h);
+  for (int y = y0; y < y1; ++y)
+    for (int x = x0 + lane; x < x1; x += 32) {
+      const float z = P0[(size_t)y * pitch + x].y;
+      if (z == z) { lo = fminf(lo, z); hi = fmaxf(hi, z); }
+    }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, off));
+    hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, off));
+  }
+  if (lane == 0) ranges[img * ranges_per_image + range_off + tile] = make_float2(lo, hi);
 }
 
 // {S, last selected linear index} of one (image, level) from its selection mask: one warp each
@@ -115,13 +156,36 @@ __global__ void k_sel_info(const uint32_t* __restrict__ masks, size_t mask_words
   }
 }
 
-// recompute only the selection mask of one level for non-default thresholds
-__global__ void k_reselect(const float2* __restrict__ P0, int n, uint32_t* __restrict__ mask, float ti, float td) {
+// computeResidualsSse walks the point list two at a time and skips the last point of an odd list
+// (dense_tracking_impl.cpp:169): that point is unselected in the reference plane.  Runs after k_sel_info.
+__global__ void k_drop_odd_last(float2* __restrict__ planes, size_t planes_per_image, size_t plane_off, int w, int h, int pitch,
+                                const int* __restrict__ sel_info, int sel_info_per_image, int level, int nimg) {
+  const int img = blockIdx.x * blockDim.x + threadIdx.x;
+  if (img >= nimg) return;
+  const int S = sel_info[img * sel_info_per_image + 2 * level], last = sel_info[img * sel_info_per_image + 2 * level + 1];
+  if ((S & 1) && last >= 0) {
+    const int y = last / w, x = last - y * w;
+    float2* P3 = planes + img * planes_per_image + plane_off + 3 * (size_t)pitch * h;
+    P3[(size_t)y * pitch + x].y = __int_as_float(0x7fc00000);
+  }
+}
+
+// recompute the selection mask and the reference plane of one level for non-default thresholds
+__global__ void k_reselect(float2* __restrict__ P0, int w, int h, int pitch, uint32_t* __restrict__ mask, float ti,
+                           float td) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = w * h;
   bool sel = false;
   if (idx < n) {
-    float2 a = P0[idx], b = P0[n + idx], c = P0[2 * (size_t)n + idx];
-    sel = !is_nan(a.y) && (fabsf(b.x) > ti || fabsf(b.y) > ti || fabsf(c.x) > td || fabsf(c.y) > td);
+    const int y = idx / w, x = idx - y * w;
+    const size_t plane = (size_t)pitch * h, o = (size_t)y * pitch + x;
+    const float2* P2 = P0 + 2 * plane;
+    const int xp = max(x - 1, 0), xn = min(x + 1, w - 1), yp = max(y - 1, 0), yn = min(y + 1, h - 1);
+    const float2 a = P0[o], b = P0[plane + o];
+    const float zx = (P2[(size_t)y * pitch + xn].y - P2[(size_t)y * pitch + xp].y) * 0.5f;
+    const float zy = (P2[(size_t)yn * pitch + x].y - P2[(size_t)yp * pitch + x].y) * 0.5f;
+    sel = !is_nan(a.y) && (fabsf(b.x) > ti || fabsf(b.y) > ti || fabsf(zx) > td || fabsf(zy) > td);
+    P0[3 * plane + o] = make_float2(a.x, sel ? a.y : __int_as_float(0x7fc00000));
   }
   unsigned m = __ballot_sync(0xffffffffu, sel);
   if ((threadIdx.x & 31) == 0 && idx < ((n + 31) / 32) * 32) mask[idx >> 5] = m;
@@ -211,7 +275,7 @@ int pyramid_build_batch(dvo_b200_ctx* ctx, int n, const float* d_I, const float*
   if (n <= 0 || levels < 1 || levels > kMaxLevels || w < 32 || h < 2)
     return set_error(ctx, DVO_B200_ERR_INVALID_ARGUMENT, "pyramid: bad geometry");
   LevelInfo L[kMaxLevels];
-  size_t plane_f2 = 0, mask_words = 0, tmpl_floats = 0;
+  size_t plane_f2 = 0, mask_words = 0, tmpl_floats = 0, range_f2 = 0;
   for (int l = 0; l < levels; ++l) {
     LevelInfo& q = L[l];
     if (l == 0) { q.w = w; q.h = h; q.fx = fx; q.fy = fy; q.ox = ox; q.oy = oy; }
@@ -221,21 +285,29 @@ int pyramid_build_batch(dvo_b200_ctx* ctx, int n, const float* d_I, const float*
     }
     // odd sizes: the last column / row is dropped by the 2x2 mean exactly as in pyrDownMeanSmooth (rgbd_image.cpp:41)
     if (q.w < 8 || q.h < 2) return set_error(ctx, DVO_B200_ERR_INVALID_ARGUMENT, "pyramid: level too small");
+    // the level kernel splits a linear pixel index with one multiply-high (tracker.cu): exact only below this bound
+    if ((uint64_t)q.w * q.h >= (1ull << 30)) return set_error(ctx, DVO_B200_ERR_INVALID_ARGUMENT, "pyramid: image too large");
     q.n = q.w * q.h;
     q.words = (q.n + 31) / 32;
-    q.plane_off = plane_f2; plane_f2 += 3 * (size_t)q.n;
+    q.pitch = (q.w + 1) & ~1;
+    q.nbands = (q.w + kTileW - 1) / kTileW;
+    q.nstrips = (q.h + kTileH - 1) / kTileH;
+    q.plane_off = plane_f2; plane_f2 += 4 * (size_t)q.pitch * q.h;
     q.mask_off = mask_words; mask_words += q.words;
     q.tmpl_off = tmpl_floats; tmpl_floats += q.w + q.h;
+    q.range_off = range_f2; range_f2 += (size_t)q.nbands * q.nstrips;
   }
   plane_f2 = align_up(plane_f2, 32);          // keep every image 256-byte aligned
   mask_words = align_up(mask_words, 64);
-  tmpl_floats = align_up(tmpl_floats, 64);
+  tmpl_floats = align_up(tmpl_floats + kTileW, 64);   // lanes past a partial band read (and discard) up to kTileW floats beyond tx[w]
+  range_f2 = align_up(range_f2, 32);
   const int sel_ints = 2 * kMaxLevels;
   size_t bytes_planes = (size_t)n * plane_f2 * sizeof(float2);
   size_t bytes_masks = (size_t)n * mask_words * sizeof(uint32_t);
   size_t bytes_tmpl = (size_t)n * tmpl_floats * sizeof(float);
   size_t bytes_sel = align_up((size_t)n * sel_ints * sizeof(int), 256);
-  size_t total = bytes_planes + bytes_masks + bytes_tmpl + bytes_sel;
+  size_t bytes_range = (size_t)n * range_f2 * sizeof(float2);
+  size_t total = bytes_planes + bytes_masks + bytes_tmpl + bytes_sel + bytes_range;
   Slab* slab = acquire_slab(ctx, total);
   if (!slab) return set_error(ctx, DVO_B200_ERR_OUT_OF_MEMORY, "pyramid: cudaMalloc failed");
   char* base = (char*)slab->base;
@@ -243,10 +315,11 @@ int pyramid_build_batch(dvo_b200_ctx* ctx, int n, const float* d_I, const float*
   uint32_t* masks = (uint32_t*)(base + bytes_planes);
   float* tmpl = (float*)(base + bytes_planes + bytes_masks);
   int* sel = (int*)(base + bytes_planes + bytes_masks + bytes_tmpl);
+  float2* ranges = (float2*)(base + bytes_planes + bytes_masks + bytes_tmpl + bytes_sel);
 
   cudaStream_t st = ctx->stream;
   {
-    ProfScope prof(ctx, 3, 4 * levels - 1);
+    ProfScope prof(ctx, 3, 6 * levels - 1);
     const int T = 256;
     for (int l = 0; l < levels; ++l) {
       const LevelInfo& q = L[l];
@@ -255,17 +328,21 @@ int pyramid_build_batch(dvo_b200_ctx* ctx, int n, const float* d_I, const float*
       ctx->launches += 1;
       if (l == 0) continue;   // level 0 takes its intensity from the input image
       dim3 g((q.n + T - 1) / T, n);
-      if (l == 1) k_pyr_intensity_down<true><<<g, T, 0, st>>>(d_I, (size_t)w * h, (((size_t)w * h) | (size_t)w) % 2 == 0 ? 1 : 0, planes, plane_f2, 0, L[0].w, q.plane_off, q.w, q.h);
-      else k_pyr_intensity_down<false><<<g, T, 0, st>>>(nullptr, 0, 0, planes, plane_f2, L[l - 1].plane_off, L[l - 1].w, q.plane_off, q.w, q.h);
+      if (l == 1) k_pyr_intensity_down<true><<<g, T, 0, st>>>(d_I, (size_t)w * h, (((size_t)w * h) | (size_t)w) % 2 == 0 ? 1 : 0, planes, plane_f2, 0, L[0].w, L[0].pitch, q.plane_off, q.w, q.h, q.pitch);
+      else k_pyr_intensity_down<false><<<g, T, 0, st>>>(nullptr, 0, 0, planes, plane_f2, L[l - 1].plane_off, L[l - 1].w, L[l - 1].pitch, q.plane_off, q.w, q.h, q.pitch);
       ctx->launches += 1;
     }
     for (int l = 0; l < levels; ++l) {
       const LevelInfo& q = L[l];
       dim3 g((q.words * 32 + T - 1) / T, n);
-      if (l == 0) k_pyr_finish<true><<<g, T, 0, st>>>(d_I, d_Z, w, w * h, planes, plane_f2, q.plane_off, q.w, q.h, l, masks, mask_words, q.mask_off, ti, td);
-      else k_pyr_finish<false><<<g, T, 0, st>>>(d_I, d_Z, w, w * h, planes, plane_f2, q.plane_off, q.w, q.h, l, masks, mask_words, q.mask_off, ti, td);
+      if (l == 0) k_pyr_finish<true><<<g, T, 0, st>>>(d_I, d_Z, w, w * h, planes, plane_f2, q.plane_off, q.w, q.h, q.pitch, l, masks, mask_words, q.mask_off, ti, td);
+      else k_pyr_finish<false><<<g, T, 0, st>>>(d_I, d_Z, w, w * h, planes, plane_f2, q.plane_off, q.w, q.h, q.pitch, l, masks, mask_words, q.mask_off, ti, td);
       k_sel_info<<<n, 32, 0, st>>>(masks, mask_words, q.mask_off, q.words, sel, sel_ints, l);
-      ctx->launches += 2;
+      k_drop_odd_last<<<(n + 127) / 128, 128, 0, st>>>(planes, plane_f2, q.plane_off, q.w, q.h, q.pitch, sel, sel_ints, l, n);
+      const int ntiles = q.nbands * q.nstrips;
+      k_tile_range<<<dim3((ntiles + 7) / 8, n), 256, 0, st>>>(planes, plane_f2, q.plane_off, q.w, q.h, q.pitch, q.nbands, ntiles,
+                                                              ranges, range_f2, q.range_off);
+      ctx->launches += 4;
     }
   }
   DVO_CUDA(ctx, cudaGetLastError());
@@ -273,13 +350,14 @@ int pyramid_build_batch(dvo_b200_ctx* ctx, int n, const float* d_I, const float*
   DVO_CUDA(ctx, cudaEventRecord(slab->ready, st));
   for (int i = 0; i < n; ++i) {
     dvo_b200_pyramid* p = new dvo_b200_pyramid;
-    p->ctx = ctx; p->refcount = 1; p->levels = levels;
+    p->ctx = ctx; p->refcount.store(1); p->levels = levels;
     std::memcpy(p->L, L, sizeof(LevelInfo) * levels);
     p->slab = slab; slab->refs++;
     p->planes = planes + (size_t)i * plane_f2;
     p->sel_mask = masks + (size_t)i * mask_words;
     p->sel_info = sel + (size_t)i * sel_ints;
     p->tmpl = tmpl + (size_t)i * tmpl_floats;
+    p->tile_range = ranges + (size_t)i * range_f2;
     p->sel_ti = ti; p->sel_td = td;
     p->id = ctx->next_pyramid_id++;
     out[i] = p;
@@ -290,13 +368,14 @@ int pyramid_build_batch(dvo_b200_ctx* ctx, int n, const float* d_I, const float*
 int pyramid_reselect(dvo_b200_ctx* ctx, dvo_b200_pyramid* p, float ti, float td) {
   if (p->sel_ti == ti && p->sel_td == td) return 0;
   cudaStream_t st = ctx->stream;
-  ProfScope prof(ctx, 4, 2 * p->levels);
+  ProfScope prof(ctx, 4, 3 * p->levels);
   for (int l = 0; l < p->levels; ++l) {
     const LevelInfo& q = p->L[l];
     const int T = 256;
-    k_reselect<<<(q.words * 32 + T - 1) / T, T, 0, st>>>(p->planes + q.plane_off, q.n, p->sel_mask + q.mask_off, ti, td);
+    k_reselect<<<(q.words * 32 + T - 1) / T, T, 0, st>>>(p->planes + q.plane_off, q.w, q.h, q.pitch, p->sel_mask + q.mask_off, ti, td);
     k_sel_info<<<1, 32, 0, st>>>(p->sel_mask, 0, q.mask_off, q.words, p->sel_info, 0, l);
-    ctx->launches += 2;
+    k_drop_odd_last<<<1, 32, 0, st>>>(p->planes, 0, q.plane_off, q.w, q.h, q.pitch, p->sel_info, 0, l, 1);
+    ctx->launches += 3;
   }
   DVO_CUDA(ctx, cudaGetLastError());
   p->sel_ti = ti; p->sel_td = td;

@@ -1,16 +1,36 @@
 // stages.cuh -- the two data-parallel stages of one Gauss-Newton iteration of
-// dvo::DenseTracker::match() as warp-level device functions (used by every kernel in tracker.cu).
+// dvo::DenseTracker::match() as warp-level device functions over shared-memory tiles
+// (used by the level kernel in tracker.cu).
 //
-//   stage A (stage_a_segment): computeResidualsSse + computeWeightsSse + computeScaleSse
-//                              (dense_tracking_impl.cpp:133-393, 657-707, 590-638)
-//   stage B (stage_b_segment): computeCompleteDataLogLikelihood + Jacobians + normal equations
-//                              (dense_tracking_impl.cpp:406-425, dense_tracking.cpp:333-342, 448-476,
-//                               least_squares.cpp:58-64)
+//   stage A: computeResidualsSse + computeWeightsSse + computeScaleSse
+//            (dense_tracking_impl.cpp:133-393, 657-707, 590-638)
+//   stage B: computeCompleteDataLogLikelihood + Jacobians + normal equations
+//            (dense_tracking_impl.cpp:406-425, dense_tracking.cpp:333-342, 448-476, least_squares.cpp:58-64)
 //
-// A warp owns a contiguous run of pixels (a "segment", row-major order) and walks it 32 pixels at a
-// time.  All arithmetic that decides validity is explicit round-to-nearest fp32 in a fixed order
-// (packed f32x2 where two channels share an operation), mirrored bit for bit by the oracle's MIRROR
-// mode; sums use whatever contraction the compiler picks.
+// Data movement.  The reference image is cut into tiles of kTileW x kTileH pixels; a CTA owns whole
+// strips (kTileH full image rows) and walks their tiles band by band.  For every tile a producer warp
+// asks the bulk-copy engine (cp.async.bulk, the TMA unit) for
+//   * the tile's rows of the reference planes (P0; in stage B also P1), and
+//   * the WINDOW of the current image the tile's bilinear taps fall into: its bounding box follows from
+//     projecting the tile's four corner rays at the minimum and maximum depth of the tile (a projective map
+//     keeps the convex hull), plus the one-pixel halo the central differences need,
+// into one of kStages shared-memory stage buffers and arms an mbarrier with the byte count; the eight
+// consumer warps (warp q <-> tile row q) wait on it, compute from shared memory and release the buffer
+// through a second mbarrier, on which the producer waits before it refills the buffer.  Nothing is written back: stage B recomputes the residual of stage A from the
+// staged tile (same operations, same bits) instead of reading a record, so per pixel and iteration the
+// kernel moves 8 (ref P0) + 8 x window overlap (cur P0) bytes in stage A and 16 + 8 x overlap in stage B.
+// A tap outside the staged window (window larger than the buffer, point behind the camera, ...) is
+// gathered from global memory by the same code through generic pointers: the window is a cache, never a
+// correctness condition.
+//
+// The gradient channels of the current image are formed from the staged (I, Z) neighbours of each tap:
+// (P[x+1] - P[x-1]) * 0.5 with clamped indices is exactly calculateDerivativeX/Y (rgbd_image.cpp:419-472);
+// the factor 0.5 is a power of two and is folded into the constants that multiply the blended gradient,
+// so every rounding step equals the one the precomputed gradient planes would give.
+//
+// All arithmetic that decides validity is explicit round-to-nearest fp32 in a fixed order (packed f32x2
+// where two channels share an operation), mirrored bit for bit by the oracle's MIRROR mode; sums use
+// whatever contraction the compiler picks.
 #pragma once
 #include "common.cuh"
 #include "f32x2.cuh"
@@ -18,140 +38,369 @@
 namespace dvo_b200 {
 
 constexpr unsigned kFullMask = 0xffffffffu;
-constexpr int kSegmentPixels = 256;     // pixels per warp segment on the test-hook path (8 rounds of 32); the persistent
-                                        // kernel sizes its segments per level (LevelPlan in tracker.cu)
-constexpr int kSegmentsPerTile = 4;     // warps per CTA: a CTA covers 4 consecutive segments
+constexpr int kConsumerWarps = kTileH;                    // warp q walks row q of every tile
+constexpr int kCtaThreads = (kConsumerWarps + 1) * 32;    // + one producer warp
+#ifndef DVO_WIN_COLS
+#define DVO_WIN_COLS 152
+#endif
+#ifndef DVO_WIN_ROWS
+#define DVO_WIN_ROWS 24
+#endif
+#ifndef DVO_STAGES
+#define DVO_STAGES 2
+#endif
+constexpr int kWinCols = DVO_WIN_COLS;                    // window capacity: kTileW + 24 columns
+constexpr int kWinRows = DVO_WIN_ROWS;                    //                  kTileH + 17 rows
+constexpr int kStages = DVO_STAGES;
 
-// record planes of one pair at one level (scratch): E = (e.i, e.z), G = (e.idx, e.idy), H = (e.zdx, e.zdy),
-// Z = depth of the reference point (28 B per pixel)
-struct RecordPlanes {
-  float2* E; float2* G; float2* H; float* Z;
-};
-__host__ __device__ __forceinline__ RecordPlanes record_planes(float* base, size_t n) {
-  RecordPlanes r;
-  r.E = reinterpret_cast<float2*>(base);
-  r.G = r.E + n;
-  r.H = r.G + n;
-  r.Z = reinterpret_cast<float*>(r.H + n);
-  return r;
+// ---- mbarrier / bulk-copy primitives (PTX ISA 8.6, sm_100a) -----------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
-constexpr int kRecordFloatsPerPixel = 7;
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.release.cta.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.release.cta.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned parity) {
+  unsigned ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a lost transaction must never hang the GPU.  try_wait suspends in hardware for a
+// system-dependent time before it reports failure, so the loop is not a busy spin.
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity, int* error_flag) {
+  unsigned spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (((++spins) & 0xfffu) == 0u) {
+      if (*reinterpret_cast<volatile int*>(error_flag)) break;
+      if (spins > (1u << 24)) { atomicExch(error_flag, 2); break; }
+    }
+  }
+}
+// global -> shared bulk copy of `bytes` (multiple of 16, both addresses 16-byte aligned); completion is
+// counted on `bar` (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// explicit 32-bit shared-memory loads (immediate offsets fold into the instruction; no generic-address arithmetic).
+// volatile: they stay between the mbarrier wait that makes the tile visible and the arrive that releases it.
+template <int kOff>
+__device__ __forceinline__ f2 lds_f2(unsigned addr) {
+  f2 v;
+  asm volatile("ld.shared.b64 %0, [%1+%2];" : "=l"(v) : "r"(addr), "n"(kOff));
+  return v;
+}
+__device__ __forceinline__ f2 lds_f2_at(unsigned addr) {
+  f2 v;
+  asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(addr));
+  return v;
+}
+
+// Loop-invariant addresses and constants that the compiler would otherwise re-derive from special registers and
+// kernel parameters in every round (S2R + a dozen integer ops): pin them in a register.
+__device__ __forceinline__ unsigned pin(unsigned v) { asm volatile("" : "+r"(v)); return v; }
+__device__ __forceinline__ float pin(float v) { asm volatile("" : "+f"(v)); return v; }
+template <typename T>
+__device__ __forceinline__ const T* pin(const T* p) { asm volatile("" : "+l"(p)); return p; }
+
+// ---- shared-memory stage buffers -----------------------------------------------------------------------
+struct TileDesc {          // written by the producer before it arms the full barrier of the stage
+  int skip;                // 1: no pixel of the tile can be valid (no reference depth, or the window misses the image)
+  int bx0, row_lo;         // image column of window column 0; (virtual, -1 .. h) image row of window row 0
+  int ulo, ucount;         // a tap (u0, v0) is served by the window iff (unsigned)(u0 - ulo) < ucount
+  int vlo, vcount;         //                                       and (unsigned)(v0 - vlo) < vcount
+  int pad_;
+};
+struct __align__(128) StageBuf {
+  float2 ref0[kTileH][kTileW];       // reference P0 rows of the tile
+  float2 ref1[kTileH][kTileW];       // reference P1 rows (stage B)
+  float2 win[kWinRows][kWinCols];    // window of the current image (P0 in stage A, P3 in stage B)
+};
+struct TilePipe {
+  StageBuf buf[kStages];
+  unsigned long long full[kStages], empty[kStages];
+  TileDesc desc[kStages];
+};
+
+// developer timing (DVO_B200_TIMING=1): cycles one warp of the CTA spends waiting on the pipeline
+struct PipeTiming {
+  unsigned long long wait_full_a = 0, wait_full_b = 0, wait_empty = 0, produce = 0, rounds_a = 0, rounds_b = 0;
+  bool on = false;
+};
+
+// geometry of one pyramid level and this CTA's share of it
+struct LevelGeom {
+  int w, h, n, pitch;       // pixels, row pitch of the planes (float2)
+  int nbands, nstrips;
+  int strip0, strip1;       // this CTA's strips [strip0, strip1)
+};
 
 // ---- per pair-iteration constants ---------------------------------------------------------------
 struct StageConsts {
   f2 k0, k1, k2, k3;          // (kt[0],kt[4]) (kt[1],kt[5]) (kt[2],kt[6]) (kt[3],kt[7]): rows X and Y of K*T
   float k8, k9, k10, k11;     // row Z
   f2 Pa, Pb;                  // precision used for the weights: (P00,P01), (P10,P11)
-  f2 cg, fxy;                 // (0.5 fx/255, 0.5 fy/255), (fx, fy)   (dense_tracking.cpp:215-220)
+  f2 cgh, cg, fxyh;           // (0.25 fx/255, 0.25 fy/255), (0.5 fx/255, 0.5 fy/255), (0.5 fx, 0.5 fy)  (dense_tracking.cpp:215-220)
   float c_i, ubx, uby;
   int first_iteration;
-  int drop_idx;               // linear index of the odd selected point that is skipped, or -1
 };
 
-__device__ __forceinline__ void load_stage_consts(const PairState& st, const PairLevel& pl, int w, int h, StageConsts& c) {
+__device__ __forceinline__ void load_stage_consts(const PairState& st, const PairLevel& pl, int w, int h, bool weights_from_prev,
+                                                  StageConsts& c) {
   // PairState is rewritten between stages by another SM (persistent kernel): read it through L2 (ld.cg)
   float kt[12], P[4];
 #pragma unroll
   for (int i = 0; i < 12; ++i) kt[i] = __ldcg(&st.kt[i]);
+  // stage A runs before P_k exists: `precision` still holds P_{k-1}; stage B runs after, P_{k-1} is in precision_prev
 #pragma unroll
-  for (int i = 0; i < 4; ++i) P[i] = __ldcg(&st.precision[i]);
+  for (int i = 0; i < 4; ++i) P[i] = weights_from_prev ? __ldcg(&st.precision_prev[i]) : __ldcg(&st.precision[i]);
   c.k0 = pk(kt[0], kt[4]); c.k1 = pk(kt[1], kt[5]); c.k2 = pk(kt[2], kt[6]); c.k3 = pk(kt[3], kt[7]);
   c.k8 = kt[8]; c.k9 = kt[9]; c.k10 = kt[10]; c.k11 = kt[11];
   c.Pa = pk(P[0], P[1]); c.Pb = pk(P[2], P[3]);
-  c.cg = pk(__fdiv_rn(__fmul_rn(0.5f, pl.cfx), 255.0f), __fdiv_rn(__fmul_rn(0.5f, pl.cfy), 255.0f));
-  c.fxy = pk(pl.cfx, pl.cfy);
+  const float cgx = __fdiv_rn(__fmul_rn(0.5f, pl.cfx), 255.0f), cgy = __fdiv_rn(__fmul_rn(0.5f, pl.cfy), 255.0f);
+  c.cg = pk(cgx, cgy);
+  c.cgh = pk(0.5f * cgx, 0.5f * cgy);                  // exact: the 0.5 of the central difference, folded in
+  c.fxyh = pk(0.5f * pl.cfx, 0.5f * pl.cfy);
   c.c_i = 1.0f / 255.0f;
-  c.ubx = (float)(w - 2); c.uby = (float)(h - 2);
+  c.ubx = pin((float)(w - 2)); c.uby = pin((float)(h - 2));
   c.first_iteration = __ldcg(&st.iteration) == 0;
-  int S = pl.rsel[0];
-  c.drop_idx = (S & 1) ? pl.rsel[1] : -1;   // odd S: last selected point skipped (dense_tracking_impl.cpp:169)
 }
 
-// Reference-side inputs of one pixel, loaded one round ahead of their use.
-struct RefPixel {
-  f2 a;        // (I_r, Z_r)
-  f2 g;        // (Ix_r, Iy_r)
-  float tx, ty;
-};
-
-__device__ __forceinline__ RefPixel load_ref_pixel(const PairLevel& pl, int idx, int w, unsigned wmagic, int n) {
-  RefPixel r;
-  const int i = min(idx, n - 1);                   // lanes past the end of the image read a valid address
-  { const float2 v = __ldcs(pl.r0 + i); r.a = pk(v.x, v.y); }   // reference planes are streamed once per iteration
-  { const float2 v = __ldcs(pl.r1 + i); r.g = pk(v.x, v.y); }
-  const int y = (int)__umulhi((unsigned)i, wmagic);   // i / w (exact for i*w < 2^32)
-  const int x = i - y * w;
-  r.tx = __ldg(pl.rtmpl + x);
-  r.ty = __ldg(pl.rtmpl + w + y);
-  return r;
+// ---- producer duty: one warp stages one tile ---------------------------------------------------------------
+// Tiles are numbered per CTA since the kernel started (`t`): buffer = t % kStages, mbarrier phase parity =
+// (t / kStages) & 1.  The warp waits until all consumers have released the buffer's previous tile.
+template <bool kStageB>
+__device__ __noinline__ void produce_tile(TilePipe& tp, const PairLevel& pl, const LevelGeom& g, const StageConsts& c, int s, int b,
+                                          unsigned t, int* error_flag, PipeTiming& tm) {
+  const int lane = threadIdx.x & 31;
+  const float2* cur = kStageB ? pl.c3 : pl.c0;
+  const int bufi = t % kStages;
+  const long long tp0 = tm.on ? clock64() : 0;
+  StageBuf& sb = tp.buf[bufi];
+  const int y0 = s * kTileH, rows = min(kTileH, g.h - y0);
+  const int x0 = b * kTileW, bw = min(kTileW, g.w - x0);
+  const unsigned ref_row_bytes = (unsigned)((bw + 1) & ~1) * 8u;
+  // ---- window of the current image: corner rays x {zmin, zmax} (lane & 7 selects the corner) ----
+  const float2 zr = __ldg(pl.rrange + (size_t)s * g.nbands + b);
+  TileDesc d;
+  d.skip = 0; d.bx0 = 0; d.row_lo = 0; d.ulo = 0; d.ucount = 0; d.vlo = 0; d.vcount = 0; d.pad_ = 0;
+  int ncols = 0, nrows = 0;
+  if (!(zr.x <= zr.y)) {
+    d.skip = 1;                       // no non-NaN reference depth: nothing is selected in this tile
+  } else {
+    const float z = (lane & 4) ? zr.y : zr.x;
+    const float tx = __ldg(pl.rtmpl + ((lane & 1) ? x0 + bw - 1 : x0));
+    const float ty = __ldg(pl.rtmpl + g.w + ((lane & 2) ? y0 + rows - 1 : y0));
+    const float px = tx * z, py = ty * z;
+    const f2 XY = fma2(c.k0, bc(px), fma2(c.k1, bc(py), fma2(c.k2, bc(z), c.k3)));
+    const float Zt = fmaf(c.k8, px, fmaf(c.k9, py, fmaf(c.k10, z, c.k11)));
+    const float iz = 1.0f / Zt;
+    float umin = lo(XY) * iz, vmin = hi(XY) * iz, umax = umin, vmax = vmin;
+    bool front = Zt > 1e-6f && umin == umin && vmin == vmin;
+#pragma unroll
+    for (int off = 1; off < 8; off <<= 1) {
+      umin = fminf(umin, __shfl_xor_sync(kFullMask, umin, off)); umax = fmaxf(umax, __shfl_xor_sync(kFullMask, umax, off));
+      vmin = fminf(vmin, __shfl_xor_sync(kFullMask, vmin, off)); vmax = fmaxf(vmax, __shfl_xor_sync(kFullMask, vmax, off));
+    }
+    front = __all_sync(kFullMask, front);
+    // clamp before the float -> int conversions; the slack below covers the rounding of the per-pixel projection
+    umin = fmaxf(umin, -8.f); vmin = fmaxf(vmin, -8.f); umax = fminf(umax, (float)g.w + 8.f); vmax = fminf(vmax, (float)g.h + 8.f);
+    if (!front) {
+      // a corner behind the camera: the hull argument does not hold; stage no window, every tap is gathered
+    } else if (umax < -1.f || vmax < -1.f || umin > (float)g.w || vmin > (float)g.h) {
+      d.skip = 1;                     // the whole tile projects outside the current image
+    } else {
+      const int col_lo = max((int)floorf(umin) - 2, 0), col_hi = min((int)floorf(umax) + 3, g.w - 1);
+      int row_lo = max((int)floorf(vmin) - 2, -1), row_hi = min((int)floorf(vmax) + 3, g.h);
+      int bx0 = col_lo & ~1;
+      ncols = (col_hi + 2 - bx0) & ~1;              // even count covering [bx0, col_hi]
+      if (ncols > kWinCols) { bx0 += ((ncols - kWinCols) / 2) & ~1; ncols = kWinCols; }
+      nrows = row_hi - row_lo + 1;
+      if (nrows > kWinRows) { row_lo += (nrows - kWinRows) / 2; nrows = kWinRows; }
+      if (ncols < 4 || nrows < 4) { ncols = 0; nrows = 0; }
+      else {
+        d.bx0 = bx0; d.row_lo = row_lo;
+        // columns are clamped per tap (max(u0-1, 0), min(u0+2, w-1)); rows -1 and h are staged as replicas
+        d.ulo = bx0 == 0 ? 0 : bx0 + 1;
+        const int uhi = (bx0 + ncols - 1 >= g.w - 1) ? g.w - 2 : bx0 + ncols - 3;
+        d.ucount = max(uhi - d.ulo + 1, 0);
+        d.vlo = row_lo + 1;
+        d.vcount = max(nrows - 3, 0);
+      }
+    }
+  }
+  const unsigned win_row_bytes = (unsigned)ncols * 8u;
+  const unsigned total = d.skip ? 0u : (unsigned)rows * ref_row_bytes * (kStageB ? 2u : 1u) + (unsigned)nrows * win_row_bytes;
+  // the descriptor is ready: now wait until the consumers have released the buffer's previous tile
+  const long long tp1 = tm.on ? clock64() : 0;
+  mbar_wait(&tp.empty[bufi], ((t / kStages) & 1u) ^ 1u, error_flag);
+  if (tm.on) { const long long tp2 = clock64(); tm.produce += tp1 - tp0; tm.wait_empty += tp2 - tp1; }
+  if (lane == 0) {
+    tp.desc[bufi] = d;
+    if (total) mbar_arrive_expect_tx(&tp.full[bufi], total);
+    else mbar_arrive(&tp.full[bufi]);
+  }
+  __syncwarp();
+  if (!d.skip) {
+    if (lane < rows) {
+      const size_t off = (size_t)(y0 + lane) * g.pitch + x0;
+      bulk_g2s(&sb.ref0[lane][0], pl.r0 + off, ref_row_bytes, &tp.full[bufi]);
+      if (kStageB) bulk_g2s(&sb.ref1[lane][0], pl.r1 + off, ref_row_bytes, &tp.full[bufi]);
+    }
+    if (lane < nrows) {
+      const int yy = min(max(d.row_lo + lane, 0), g.h - 1);
+      bulk_g2s(&sb.win[lane][0], cur + (size_t)yy * g.pitch + d.bx0, win_row_bytes, &tp.full[bufi]);
+    }
+  }
 }
 
-// The residual record of one reference pixel (computeResidualsSse, dense_tracking_impl.cpp:133-393) is
-// computed in three steps so that the twelve bilinear taps of round r+1 are in flight while round r
-// is blended:
+// ---- per-pixel geometry --------------------------------------------------------------------------------
+// The residual record of one reference pixel (computeResidualsSse, dense_tracking_impl.cpp:133-393):
 //   project_pixel : point (x,y,z) = (tx*z, ty*z, z); (X,Y,Z') = fma chains over the rows of K*T;
-//                   (u,v) = (X,Y)*rcp_rn(Z'); bounds 0<=u<=w-2, 0<=v<=h-2; truncation -> tap index, weights
-//   load_taps     : the four neighbours in the three float2 planes of the current image
-//   finish_pixel  : bilinear blend, residual weights of dense_tracking.cpp:215-220, NaN test (line 261),
+//                   (u,v) = (X,Y)*rcp_rn(Z'); bounds 0<=u<=w-2, 0<=v<=h-2; truncation -> tap index, weights.
+//                   z = NaN (pixel not in the reference point list) fails the bounds test.
+//   taps          : the four neighbours (stage B: twelve, for the central differences) from the staged window
+//   blend         : bilinear blend, residual weights of dense_tracking.cpp:215-220, NaN test (line 261),
 //                   occlusion test (line 275).  E = (e.i, e.z), G = (e.idx, e.idy), H = (e.zdx, e.zdy).
-// Branch-free: a rejected point reads tap 0 and is flagged invalid.
+// Branch-free: a rejected point reads a safe location and is flagged invalid.
 struct PixelProjection {
   f2 f, gq;        // (fu, fv), (gu, gv)
-  f2 g;            // (Ix_r, Iy_r)
-  float Zt, z, Ir;
-  int b;           // index of the upper-left tap
+  float Zt;
+  int u0, v0;      // upper-left tap
   bool inb;
 };
-struct PixelTaps {
-  f2 p00, p10, p01, p11, q00, q10, q01, q11, s00, s10, s01, s11;
-};
 
-__device__ __forceinline__ PixelProjection project_pixel(const RefPixel& r, bool selected, int w, const StageConsts& c) {
+__device__ __forceinline__ PixelProjection project_pixel(float tx, float ty, float z, const StageConsts& c) {
   PixelProjection p;
-  const float z = hi(r.a);
-  const f2 pxy = mul2(pk(r.tx, r.ty), bc(z));
+  const f2 pxy = mul2(pk(tx, ty), bc(z));
   const float px = lo(pxy), py = hi(pxy);
   const f2 XY = fma2(c.k0, bc(px), fma2(c.k1, bc(py), fma2(c.k2, bc(z), c.k3)));
   p.Zt = __fmaf_rn(c.k8, px, __fmaf_rn(c.k9, py, __fmaf_rn(c.k10, z, c.k11)));
   f2 uv = mul2(XY, bc(rcp_rn(p.Zt)));
   const float u = lo(uv), v = hi(uv);
-  p.inb = selected && u >= 0.f && u <= c.ubx && v >= 0.f && v <= c.uby;   // NaN compares false
+  p.inb = u >= 0.f && u <= c.ubx && v >= 0.f && v <= c.uby;   // NaN compares false
   uv = p.inb ? uv : 0ull;
   // truncation without conversions: for 0 <= t < 2^23, RZ(t + 2^23) carries floor(t) in its mantissa
   const f2 t = add2_rz(uv, bc(8388608.0f));
   p.f = sub2(uv, sub2(t, bc(8388608.0f)));
   p.gq = sub2(bc(1.0f), p.f);
-  const int u0 = __float_as_int(lo(t)) - 0x4b000000, v0 = __float_as_int(hi(t)) - 0x4b000000;
-  p.b = v0 * w + u0;
-  p.g = r.g; p.z = z; p.Ir = lo(r.a);
+  p.u0 = __float_as_int(lo(t)) - 0x4b000000;
+  p.v0 = __float_as_int(hi(t)) - 0x4b000000;
   return p;
 }
 
-__device__ __forceinline__ PixelTaps load_taps(const PairLevel& pl, int b, int w) {
-  PixelTaps t;
-  t.p00 = ldg_f2(pl.c0 + b); t.p10 = ldg_f2(pl.c0 + b + 1); t.p01 = ldg_f2(pl.c0 + b + w); t.p11 = ldg_f2(pl.c0 + b + w + 1);
-  t.q00 = ldg_f2(pl.c1 + b); t.q10 = ldg_f2(pl.c1 + b + 1); t.q01 = ldg_f2(pl.c1 + b + w); t.q11 = ldg_f2(pl.c1 + b + w + 1);
-  t.s00 = ldg_f2(pl.c2 + b); t.s10 = ldg_f2(pl.c2 + b + 1); t.s01 = ldg_f2(pl.c2 + b + w); t.s11 = ldg_f2(pl.c2 + b + w + 1);
-  return t;
+#define DVO_BLEND2(fu, fv, gu, gv, c00, c10, c01, c11) \
+  fma2(bc(fv), fma2(bc(fu), c11, mul2(bc(gu), c01)), mul2(bc(gv), fma2(bc(fu), c10, mul2(bc(gu), c00))))
+
+__device__ __forceinline__ f2 ld_f2(const float2* p) { const float2 v = *p; return pk(v.x, v.y); }
+
+// the staged window as one warp sees it during one tile
+struct WinView {
+  unsigned base;             // shared address of win[0][0] minus (row_lo * kWinCols + bx0) * 8: index with image coordinates
+  unsigned safe;             // shared address of win[1][1]: where rejected points read
+  const float2* plane;       // the same plane in global memory, for taps the window does not hold
+  int ulo, ucount, vlo, vcount;
+  int w, h, pitch;
+};
+constexpr int kWinRowBytes = kWinCols * 8;
+
+struct Taps4 { f2 c00, c10, c01, c11; };
+struct Taps12 { f2 c00, c10, c01, c11, l0, l1, r0, r1, t0, t1, b0, b1; };
+
+// the rare path: some lane's taps lie outside the staged window -> generic loads, from the window or from global memory
+// (inlined: a call inside the pixel loop would pin the accumulators to the calling convention's registers)
+__device__ __forceinline__ void gather_taps4(const WinView& wv, int u0, int v0, bool inb, bool hit, Taps4& t) {
+  const bool miss = inb && !hit;
+  const unsigned sa = (inb && hit) ? wv.base + (unsigned)(v0 * kWinCols + u0) * 8u : wv.safe;
+  const float2* p = miss ? wv.plane + (size_t)v0 * wv.pitch + u0 : reinterpret_cast<const float2*>(__cvta_shared_to_generic(sa));
+  const int rp = miss ? wv.pitch : kWinCols;
+  t.c00 = ld_f2(p); t.c10 = ld_f2(p + 1); t.c01 = ld_f2(p + rp); t.c11 = ld_f2(p + rp + 1);
+}
+__device__ __forceinline__ void gather_taps12(const WinView& wv, int u0, int v0, bool inb, bool hit, Taps12& t) {
+  const bool miss = inb && !hit;
+  const unsigned sa = (inb && hit) ? wv.base + (unsigned)(v0 * kWinCols + u0) * 8u : wv.safe;
+  const float2* p = miss ? wv.plane + (size_t)v0 * wv.pitch + u0 : reinterpret_cast<const float2*>(__cvta_shared_to_generic(sa));
+  const int rp = miss ? wv.pitch : kWinCols;
+  const int up = (miss && v0 == 0) ? 0 : -rp;                     // the window holds rows -1 and h as replicas
+  const int dn = (miss && v0 + 2 > wv.h - 1) ? rp : 2 * rp;
+  const int dl = u0 > 0 ? 1 : 0, dr = u0 + 2 <= wv.w - 1 ? 2 : 1;
+  t.c00 = ld_f2(p); t.c10 = ld_f2(p + 1); t.c01 = ld_f2(p + rp); t.c11 = ld_f2(p + rp + 1);
+  t.t0 = ld_f2(p + up); t.t1 = ld_f2(p + up + 1); t.b0 = ld_f2(p + dn); t.b1 = ld_f2(p + dn + 1);
+  t.l0 = ld_f2(p - dl); t.l1 = ld_f2(p + rp - dl); t.r0 = ld_f2(p + dr); t.r1 = ld_f2(p + rp + dr);
 }
 
-__device__ __forceinline__ bool finish_pixel(const PixelProjection& p, const PixelTaps& t, const StageConsts& c, f2& E, f2& G, f2& H) {
+// depthStdDevZ (dense_tracking_impl.cpp:122-128)
+__device__ __forceinline__ float depth_sigma(float z) {
+  const float s = __fsub_rn(z, 0.4f);
+  return __fmaf_rn(__fmul_rn(0.0019f, s), s, 0.0012f);
+}
+
+// Stage A pixel: (e.i, e.z) and validity from the four taps of (I, Z').
+__device__ __forceinline__ bool residual_pixel(const PixelProjection& p, const WinView& wv, float Ir, float z, const StageConsts& c,
+                                               float& ei, float& ez) {
+  const bool hit = (unsigned)(p.u0 - wv.ulo) < (unsigned)wv.ucount && (unsigned)(p.v0 - wv.vlo) < (unsigned)wv.vcount;
+  f2 c00, c10, c01, c11;
+  if (!__any_sync(kFullMask, p.inb && !hit)) {
+    const unsigned a = p.inb ? wv.base + (unsigned)(p.v0 * kWinCols + p.u0) * 8u : wv.safe;
+    c00 = lds_f2<0>(a); c10 = lds_f2<8>(a); c01 = lds_f2<kWinRowBytes>(a); c11 = lds_f2<kWinRowBytes + 8>(a);
+  } else {
+    Taps4 t;
+    gather_taps4(wv, p.u0, p.v0, p.inb, hit, t);
+    c00 = t.c00; c10 = t.c10; c01 = t.c01; c11 = t.c11;
+  }
   const float fu = lo(p.f), fv = hi(p.f), gu = lo(p.gq), gv = hi(p.gq);
-#define DVO_BLEND2(c00, c10, c01, c11) \
-  fma2(bc(fv), fma2(bc(fu), c11, mul2(bc(gu), c01)), mul2(bc(gv), fma2(bc(fu), c10, mul2(bc(gu), c00))))
-  const f2 IZ = DVO_BLEND2(t.p00, t.p10, t.p01, t.p11);
-  const f2 Gc = DVO_BLEND2(t.q00, t.q10, t.q01, t.q11);
-  const f2 Hc = DVO_BLEND2(t.s00, t.s10, t.s01, t.s11);
-#undef DVO_BLEND2
+  const f2 IZ = DVO_BLEND2(fu, fv, gu, gv, c00, c10, c01, c11);
+  const float Zc = hi(IZ);
+  ez = __fsub_rn(Zc, p.Zt);
+  ei = __fmaf_rn(c.c_i, lo(IZ), __fmul_rn(-c.c_i, Ir));
+  return p.inb && Zc == Zc && ez > __fmul_rn(-20.0f, depth_sigma(z));
+}
+
+// Stage B pixel: the full record from twelve taps of (I, Z): centre 2x2, the columns left and right of it and the
+// rows above and below it.
+__device__ __forceinline__ bool record_pixel(const PixelProjection& p, const WinView& wv, float Ir, float z, f2 gref,
+                                             const StageConsts& c, f2& E, f2& G, f2& H) {
+  const bool hit = (unsigned)(p.u0 - wv.ulo) < (unsigned)wv.ucount && (unsigned)(p.v0 - wv.vlo) < (unsigned)wv.vcount;
+  Taps12 t;
+  if (!__any_sync(kFullMask, p.inb && !hit)) {
+    const unsigned a = p.inb ? wv.base + (unsigned)(p.v0 * kWinCols + p.u0) * 8u : wv.safe;
+    t.c00 = lds_f2<0>(a); t.c10 = lds_f2<8>(a); t.c01 = lds_f2<kWinRowBytes>(a); t.c11 = lds_f2<kWinRowBytes + 8>(a);
+    t.t0 = lds_f2<-kWinRowBytes>(a); t.t1 = lds_f2<-kWinRowBytes + 8>(a);
+    t.b0 = lds_f2<2 * kWinRowBytes>(a); t.b1 = lds_f2<2 * kWinRowBytes + 8>(a);
+    const unsigned al = a - (p.u0 > 0 ? 8u : 0u);                  // clamped column u0-1
+    const unsigned ar = a + (p.u0 + 2 <= wv.w - 1 ? 16u : 8u);     // clamped column u0+2
+    t.l0 = lds_f2<0>(al); t.l1 = lds_f2<kWinRowBytes>(al); t.r0 = lds_f2<0>(ar); t.r1 = lds_f2<kWinRowBytes>(ar);
+  } else {
+    gather_taps12(wv, p.u0, p.v0, p.inb, hit, t);
+  }
+  const float fu = lo(p.f), fv = hi(p.f), gu = lo(p.gq), gv = hi(p.gq);
+  const f2 IZ = DVO_BLEND2(fu, fv, gu, gv, t.c00, t.c10, t.c01, t.c11);
+  // 2 x central differences of (I, Z) at the four taps: x direction, y direction
+  const f2 DX = DVO_BLEND2(fu, fv, gu, gv, sub2(t.c10, t.l0), sub2(t.r0, t.c00), sub2(t.c11, t.l1), sub2(t.r1, t.c01));
+  const f2 DY = DVO_BLEND2(fu, fv, gu, gv, sub2(t.c01, t.t0), sub2(t.c11, t.t1), sub2(t.b0, t.c00), sub2(t.b1, t.c10));
   const float Zc = hi(IZ);
   const float ez = __fsub_rn(Zc, p.Zt);
-  const float s = __fsub_rn(p.z, 0.4f);
-  const float sig = __fmaf_rn(__fmul_rn(0.0019f, s), s, 0.0012f);    // depthStdDevZ (lines 122-128)
-  const float ei = __fmaf_rn(c.c_i, lo(IZ), __fmul_rn(-c.c_i, p.Ir));
+  const float ei = __fmaf_rn(c.c_i, lo(IZ), __fmul_rn(-c.c_i, Ir));
   E = pk(ei, ez);
-  G = fma2(c.cg, Gc, mul2(c.cg, p.g));
-  H = mul2(c.fxy, Hc);
-  return p.inb && Zc == Zc && ez > __fmul_rn(-20.0f, sig);
+  G = fma2(c.cgh, pk(lo(DX), lo(DY)), mul2(c.cg, gref));
+  H = mul2(c.fxyh, pk(hi(DX), hi(DY)));
+  // dense_tracking_impl.cpp:261: any NaN among the eight blended lanes rejects the point
+  const f2 nn = add2(add2(IZ, DX), DY);
+  const float probe = lo(nn) + hi(nn);
+  return p.inb && probe == probe && ez > __fmul_rn(-20.0f, depth_sigma(z));
 }
 
 // ---- pairwise scale sum ---------------------------------------------------------------------------
@@ -189,11 +438,10 @@ __host__ __device__ __forceinline__ SegT<T> combine_seg(const A& a, const B& b) 
 }
 
 constexpr int kSegExportFloats = 12;   // n (as int bits), S0[3], S1[3], wf, wl, ol[3]
-constexpr int kCtaExportFloats = 16;   // the CTA's four warp summaries combined (12) + the four warp counts (int bits)
 
 __device__ __forceinline__ SegT<double> load_seg_export(const float* e) {
   SegT<double> s;
-  // written by other SMs in the same kernel (persistent path): read through L2
+  // written by other warps / SMs in the same kernel: read through L2
   float v[kSegExportFloats];
 #pragma unroll
   for (int i = 0; i < kSegExportFloats; ++i) v[i] = __ldcg(e + i);
@@ -203,61 +451,66 @@ __device__ __forceinline__ SegT<double> load_seg_export(const float* e) {
   s.wf = v[7]; s.wl = v[8]; s.ol[0] = v[9]; s.ol[1] = v[10]; s.ol[2] = v[11];
   return s;
 }
+__device__ __forceinline__ void store_seg_export(const SegT<double>& s, float* e) {
+  e[0] = __int_as_float((int)s.n);
+  for (int k = 0; k < 3; ++k) { e[1 + k] = (float)s.S0[k]; e[4 + k] = (float)s.S1[k]; e[9 + k] = (float)s.ol[k]; }
+  e[7] = (float)s.wf; e[8] = (float)s.wl;
+}
 
-// Thread 0 of a CTA folds the four warp summaries (shared memory, in pixel order) into one CTA export.
-__device__ __forceinline__ void cta_export_segments(const float (*sm_exp)[kSegExportFloats], float* out) {
-  SegT<float> acc;
-  {
-    const float* e = sm_exp[0];
-    acc.n = __float_as_int(e[0]);
-    for (int k = 0; k < 3; ++k) { acc.S0[k] = e[1 + k]; acc.S1[k] = e[4 + k]; acc.ol[k] = e[9 + k]; }
-    acc.wf = e[7]; acc.wl = e[8];
+// One warp combines `count` segment exports (kSegExportFloats floats each, in row-major pixel order) into one and
+// writes the exclusive prefix of their valid counts to base_out[0..count) (rank base of each segment).
+struct SegCombineSmem {
+  SegT<double> lanes[32];
+  long long lane_base[32];
+};
+__device__ __forceinline__ SegT<double> combine_exports_warp(const float* e, int count, int* base_out, SegCombineSmem& sm) {
+  const int lane = threadIdx.x & 31;
+  const int chunk = (count + 31) / 32;
+  const int t0 = min(lane * chunk, count), t1 = min(t0 + chunk, count);
+  SegT<double> acc;
+  acc.n = 0; acc.wf = acc.wl = 0;
+  for (int k = 0; k < 3; ++k) acc.S0[k] = acc.S1[k] = acc.ol[k] = 0;
+  for (int t = t0; t < t1; ++t) acc = combine_seg<double>(acc, load_seg_export(e + (size_t)t * kSegExportFloats));
+  sm.lanes[lane] = acc;
+  {   // exclusive prefix of the lane counts
+    long long incl = acc.n;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      long long v = __shfl_up_sync(kFullMask, incl, off);
+      if (lane >= off) incl += v;
+    }
+    sm.lane_base[lane] = incl - acc.n;
   }
-  for (int q = 1; q < kSegmentsPerTile; ++q) {
-    const float* e = sm_exp[q];
-    SegT<float> b;
-    b.n = __float_as_int(e[0]);
-    for (int k = 0; k < 3; ++k) { b.S0[k] = e[1 + k]; b.S1[k] = e[4 + k]; b.ol[k] = e[9 + k]; }
-    b.wf = e[7]; b.wl = e[8];
-    acc = combine_seg<float>(acc, b);
+  __syncwarp();
+  for (int off = 1; off < 32; off <<= 1) {   // in-order tree combine
+    if ((lane & (2 * off - 1)) == 0) sm.lanes[lane] = combine_seg<double>(sm.lanes[lane], sm.lanes[lane + off]);
+    __syncwarp();
   }
-  out[0] = __int_as_float((int)acc.n);
-  for (int k = 0; k < 3; ++k) { out[1 + k] = acc.S0[k]; out[4 + k] = acc.S1[k]; out[9 + k] = acc.ol[k]; }
-  out[7] = acc.wf; out[8] = acc.wl;
-  for (int q = 0; q < kSegmentsPerTile; ++q) out[12 + q] = sm_exp[q][0];
+  long long run = sm.lane_base[lane];
+  for (int t = t0; t < t1; ++t) {
+    base_out[t] = (int)run;
+    run += __float_as_int(__ldcg(e + (size_t)t * kSegExportFloats));
+  }
+  const SegT<double> all = sm.lanes[0];
+  __syncwarp();
+  return all;
 }
 
 // Student-t weight of computeWeightsSse (dense_tracking_impl.cpp:657-707): w = 7 / (5 + r^T P r), nu = 5;
 // w = 1 on the first iteration of a level (dense_tracking.cpp:286-289).
-__device__ __forceinline__ float student_weight(bool first_iteration, f2 Pa, f2 Pb, float ei, float ez) {
-  if (first_iteration) return 1.0f;
-  const f2 q = fma2(bc(ez), Pb, mul2(bc(ei), Pa));        // (ei P00 + ez P10, ei P01 + ez P11)
+__device__ __forceinline__ float student_weight(const StageConsts& c, float ei, float ez) {
+  if (c.first_iteration) return 1.0f;
+  const f2 q = fma2(bc(ez), c.Pb, mul2(bc(ei), c.Pa));        // (ei P00 + ez P10, ei P01 + ez P11)
   const float d = fmaf(lo(q), ei, hi(q) * ez);
   return 7.0f * rcp_fast(5.0f + d);
 }
-__device__ __forceinline__ float student_weight(const StageConsts& c, float ei, float ez) {
-  return student_weight(c.first_iteration != 0, c.Pa, c.Pb, ei, ez);
-}
 
-__device__ __forceinline__ void store_record(const RecordPlanes& rec, int idx, int n, bool valid, f2 E, f2 G, f2 H, float z) {
-  if (idx < n) {
-    if (valid) {
-      __stcs(rec.E + idx, make_float2(lo(E), hi(E)));    // st.global.cs: streamed, evict-first in L2
-      __stcs(rec.G + idx, make_float2(lo(G), hi(G)));
-      __stcs(rec.H + idx, make_float2(lo(H), hi(H)));
-      __stcs(rec.Z + idx, z);
-    } else {
-      const float nanf_ = __int_as_float(0x7fc00000);
-      __stcs(rec.E + idx, make_float2(nanf_, nanf_));
-    }
-  }
-}
-
-// Running state of the pairwise scale sum of one warp segment (see the comment above SegT).
+// Running state of the pairwise scale sum of one image row walked by one warp (see the comment above SegT).
+// The row's sums are accumulated per lane in fp32 ((all, alternating-sign) packed per component) and leave the
+// warp once per row; everything after that (rows -> CTA -> squad) is combined in fp64, so the result does not
+// depend on how the rows are spread over CTAs.
 struct ScaleState {
-  // fp64 accumulators: the covariance is inverted and feeds accept/reject decisions, so the sums are kept
-  // independent of how the pixels are partitioned over warps (to ~1e-12) at the cost of 12 DADD per 64 pixels
-  double sall0, sall1, sall2, salt0, salt1, salt2;
+  f2 acc0, acc1, acc2;       // (sum, sum with the sign of the rank parity) of s * r r^T components 00, 01, 11
   float pw, po0, po1, po2;   // pending leader: the last valid point seen, waiting for the next valid weight
   float wfirst;
   int psign, cnt;
@@ -265,71 +518,53 @@ struct ScaleState {
 };
 
 __device__ __forceinline__ void scale_state_init(ScaleState& s) {
-  s.sall0 = s.sall1 = s.sall2 = s.salt0 = s.salt1 = s.salt2 = 0.0;
+  s.acc0 = s.acc1 = s.acc2 = 0ull;
   s.pw = s.po0 = s.po1 = s.po2 = 0.f; s.wfirst = 0.f; s.psign = 0; s.cnt = 0; s.pend = false;
 }
 
-// Adds the 64 points {pixel base+lane: (v0, w0, ei0, ez0)} then {pixel base+32+lane: (v1, ...)} to the state.
-__device__ __forceinline__ void scale_round64(ScaleState& st, int lane, bool v0, float w0, float ei0, float ez0,
-                                              bool v1, float w1, float ei1, float ez1) {
-  const unsigned lt_mask = (1u << lane) - 1u;
-  const unsigned m0 = __ballot_sync(kFullMask, v0), m1 = __ballot_sync(kFullMask, v1);
-  if ((m0 | m1) == 0u) return;
-  const float w1_first = __shfl_sync(kFullMask, w1, m1 ? __ffs(m1) - 1 : 0);        // first valid weight of the upper half
-  const float w_first = m0 ? __shfl_sync(kFullMask, w0, __ffs(m0) - 1) : w1_first;   // first valid weight of the round
+// Adds the 32 points {pixel base+lane: (v, w, ei, ez)} to the state.
+__device__ __forceinline__ void scale_round32(ScaleState& st, int lane, unsigned lt_mask, bool v, float w, float ei, float ez) {
+  const unsigned m = __ballot_sync(kFullMask, v);
+  if (m == 0u) return;
+  const float w_first = __shfl_sync(kFullMask, w, __ffs(m) - 1);   // first valid weight of the round
   if (st.cnt == 0) st.wfirst = w_first;
   {   // the pending leader of an earlier round pairs with the first valid point of this round
     const float s = st.pend ? st.pw + w_first : 0.f;
-    const float sa = __int_as_float(__float_as_int(s) ^ st.psign);
-    st.sall0 += (double)(s * st.po0); st.sall1 += (double)(s * st.po1); st.sall2 += (double)(s * st.po2);
-    st.salt0 += (double)(sa * st.po0); st.salt1 += (double)(sa * st.po1); st.salt2 += (double)(sa * st.po2);
+    const f2 ss = pk(s, __int_as_float(__float_as_int(s) ^ st.psign));
+    st.acc0 = fma2(ss, bc(st.po0), st.acc0); st.acc1 = fma2(ss, bc(st.po1), st.acc1); st.acc2 = fma2(ss, bc(st.po2), st.acc2);
   }
-  const unsigned above0 = (m0 >> lane) >> 1, above1 = (m1 >> lane) >> 1;
-  float wn0 = __shfl_sync(kFullMask, w0, above0 ? lane + __ffs(above0) : lane);
-  const float wn1 = __shfl_sync(kFullMask, w1, above1 ? lane + __ffs(above1) : lane);
-  wn0 = above0 ? wn0 : w1_first;
-  const bool next0 = above0 != 0u || m1 != 0u, next1 = above1 != 0u;
-  const int c0n = __popc(m0);
-  const int sg0 = ((st.cnt + __popc(m0 & lt_mask)) & 1) << 31;          // sign bit set for odd rank
-  const int sg1 = ((st.cnt + c0n + __popc(m1 & lt_mask)) & 1) << 31;
+  const unsigned above = (m >> lane) >> 1;
+  const float wn = __shfl_sync(kFullMask, w, above ? lane + __ffs(above) : lane);
+  const bool next = above != 0u;
+  const int sg = ((st.cnt + __popc(m & lt_mask)) & 1) << 31;          // sign bit set for odd rank
   // rejected points carry garbage (possibly NaN) residuals: zero them so that 0 * outer stays 0
-  const float xi0 = v0 ? ei0 : 0.f, xz0 = v0 ? ez0 : 0.f, xi1 = v1 ? ei1 : 0.f, xz1 = v1 ? ez1 : 0.f;
-  const float a0 = xi0 * xi0, a1 = xi0 * xz0, a2 = xz0 * xz0;
-  const float b0 = xi1 * xi1, b1 = xi1 * xz1, b2 = xz1 * xz1;
-  {
-    const float s = (v0 && next0) ? w0 + wn0 : 0.f;
-    const float sa = __int_as_float(__float_as_int(s) ^ sg0);
-    st.sall0 += (double)(s * a0); st.sall1 += (double)(s * a1); st.sall2 += (double)(s * a2);
-    st.salt0 += (double)(sa * a0); st.salt1 += (double)(sa * a1); st.salt2 += (double)(sa * a2);
-  }
-  {
-    const float s = (v1 && next1) ? w1 + wn1 : 0.f;
-    const float sa = __int_as_float(__float_as_int(s) ^ sg1);
-    st.sall0 += (double)(s * b0); st.sall1 += (double)(s * b1); st.sall2 += (double)(s * b2);
-    st.salt0 += (double)(sa * b0); st.salt1 += (double)(sa * b1); st.salt2 += (double)(sa * b2);
-  }
-  // new pending leader: the last valid point of the round
-  const bool np1 = v1 && !next1, np0 = v0 && !next0;
-  st.pend = np0 || np1;
-  st.pw = np1 ? w1 : (np0 ? w0 : st.pw);
-  st.po0 = np1 ? b0 : (np0 ? a0 : st.po0); st.po1 = np1 ? b1 : (np0 ? a1 : st.po1); st.po2 = np1 ? b2 : (np0 ? a2 : st.po2);
-  st.psign = np1 ? sg1 : (np0 ? sg0 : st.psign);
-  st.cnt += c0n + __popc(m1);
+  const float xi = v ? ei : 0.f, xz = v ? ez : 0.f;
+  const float a0 = xi * xi, a1 = xi * xz, a2 = xz * xz;
+  const float s = (v && next) ? w + wn : 0.f;
+  const f2 ss = pk(s, __int_as_float(__float_as_int(s) ^ sg));
+  st.acc0 = fma2(ss, bc(a0), st.acc0); st.acc1 = fma2(ss, bc(a1), st.acc1); st.acc2 = fma2(ss, bc(a2), st.acc2);
+  // new pending leader: the last valid point of the round (the values only matter in the lane that has `pend`)
+  st.pend = v && !next;
+  st.pw = w; st.po0 = a0; st.po1 = a1; st.po2 = a2; st.psign = sg;
+  st.cnt += __popc(m);
 }
 
 // warp-reduce the sums and write the segment summary (kSegExportFloats floats)
 __device__ __forceinline__ void scale_state_export(ScaleState& st, int lane, float* seg_out) {
+  float all0 = lo(st.acc0), alt0 = hi(st.acc0), all1 = lo(st.acc1), alt1 = hi(st.acc1), all2 = lo(st.acc2), alt2 = hi(st.acc2);
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) {
-    st.sall0 += __shfl_xor_sync(kFullMask, st.sall0, off); st.sall1 += __shfl_xor_sync(kFullMask, st.sall1, off);
-    st.sall2 += __shfl_xor_sync(kFullMask, st.sall2, off); st.salt0 += __shfl_xor_sync(kFullMask, st.salt0, off);
-    st.salt1 += __shfl_xor_sync(kFullMask, st.salt1, off); st.salt2 += __shfl_xor_sync(kFullMask, st.salt2, off);
+    all0 += __shfl_xor_sync(kFullMask, all0, off); alt0 += __shfl_xor_sync(kFullMask, alt0, off);
+    all1 += __shfl_xor_sync(kFullMask, all1, off); alt1 += __shfl_xor_sync(kFullMask, alt1, off);
+    all2 += __shfl_xor_sync(kFullMask, all2, off); alt2 += __shfl_xor_sync(kFullMask, alt2, off);
   }
   // leaders at even local rank belong to hypothesis 0, odd to hypothesis 1: S0 = (all + alt)/2, S1 = (all - alt)/2
   if (lane == 0) {
     seg_out[0] = __int_as_float(st.cnt);
-    seg_out[1] = (float)(0.5 * (st.sall0 + st.salt0)); seg_out[2] = (float)(0.5 * (st.sall1 + st.salt1)); seg_out[3] = (float)(0.5 * (st.sall2 + st.salt2));
-    seg_out[4] = (float)(0.5 * (st.sall0 - st.salt0)); seg_out[5] = (float)(0.5 * (st.sall1 - st.salt1)); seg_out[6] = (float)(0.5 * (st.sall2 - st.salt2));
+    seg_out[1] = (float)(0.5 * ((double)all0 + (double)alt0)); seg_out[2] = (float)(0.5 * ((double)all1 + (double)alt1));
+    seg_out[3] = (float)(0.5 * ((double)all2 + (double)alt2));
+    seg_out[4] = (float)(0.5 * ((double)all0 - (double)alt0)); seg_out[5] = (float)(0.5 * ((double)all1 - (double)alt1));
+    seg_out[6] = (float)(0.5 * ((double)all2 - (double)alt2));
     seg_out[7] = st.wfirst;
     if (st.cnt == 0) { seg_out[8] = 0.f; seg_out[9] = 0.f; seg_out[10] = 0.f; seg_out[11] = 0.f; }
   }
@@ -338,58 +573,79 @@ __device__ __forceinline__ void scale_state_export(ScaleState& st, int lane, flo
   }
 }
 
-// Stage A over the pixels [begin, end) of one pair (begin a multiple of 32): writes the residual
-// records and the segment summary (kSegExportFloats floats at `seg_out`).  The warp walks 32 pixels per
-// round as a two-deep software pipeline: while round r is blended, the twelve taps of round r+1 and the
-// reference-side loads of round r+2 are in flight.  The pairwise scale sum runs once per two rounds.
-__device__ __forceinline__ void stage_a_segment(const PairLevel& pl, const StageConsts& c, int w, unsigned wmagic, int n,
-                                                int begin, int end, const RecordPlanes& rec, float* seg_out) {
-  const int lane = threadIdx.x & 31;
-  ScaleState ss;
-  scale_state_init(ss);
-  if (begin < end) {
-    // prologue: project round 0 and issue its taps, load the reference data of round 1
-    RefPixel ref = load_ref_pixel(pl, begin + lane, w, wmagic, n);
-    unsigned sel = __ldg(pl.rmask + (begin >> 5));
-    PixelProjection proj = project_pixel(ref, ((sel >> lane) & 1u) && (begin + lane) != c.drop_idx, w, c);
-    PixelTaps taps = load_taps(pl, proj.b, w);
-    ref = load_ref_pixel(pl, begin + 32 + lane, w, wmagic, n);
-    sel = begin + 32 < end ? __ldg(pl.rmask + (begin >> 5) + 1) : 0u;
-    bool sv = false; float sw = 0.f, sei = 0.f, sez = 0.f;   // stashed even round
-    bool odd = false;
-#pragma unroll 1
-    for (int base = begin; base < end; base += 32) {
-      const PixelProjection pcur = proj;
-      const PixelTaps tcur = taps;
-      const int nb = base + 32;
-      if (nb < end) {   // warp-uniform
-        proj = project_pixel(ref, ((sel >> lane) & 1u) && (nb + lane) != c.drop_idx, w, c);
-        taps = load_taps(pl, proj.b, w);
-        ref = load_ref_pixel(pl, nb + 32 + lane, w, wmagic, n);
-        sel = nb + 32 < end ? __ldg(pl.rmask + (nb >> 5) + 1) : 0u;
-      }
-      f2 E, G, H;
-      const bool v = finish_pixel(pcur, tcur, c, E, G, H);
-      const float ei = lo(E), ez = hi(E);
-      const float wgt = student_weight(c, ei, ez);
-      // 4th plane = reference depth: stage B recomputes the weight (6 flops) instead of reading it plus the
-      // reference plane again.  end <= n: never touch another warp's pixels
-      store_record(rec, base + lane, end, v, E, G, H, pcur.z);
-      if (!odd) { sv = v; sw = wgt; sei = ei; sez = ez; }
-      else scale_round64(ss, lane, sv, sw, sei, sez, v, wgt, ei, ez);
-      odd = !odd;
-    }
-    if (odd) scale_round64(ss, lane, sv, sw, sei, sez, false, 0.f, 0.f, 0.f);
+// ---- consumers ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ WinView make_view(const StageBuf& sb, const TileDesc& d, const float2* plane, const LevelGeom& g) {
+  WinView wv;
+  const unsigned w0 = smem_u32(&sb.win[0][0]);
+  wv.base = pin(w0 - (unsigned)((d.row_lo * kWinCols + d.bx0) * 8));
+  wv.safe = pin(w0 + (unsigned)((kWinCols + 1) * 8));
+  wv.plane = plane;
+  wv.ulo = d.ulo; wv.ucount = d.ucount; wv.vlo = d.vlo; wv.vcount = d.vcount;
+  wv.w = g.w; wv.h = g.h; wv.pitch = g.pitch;
+  return wv;
+}
+
+// Stage A over this CTA's strips: warp q walks image row strip*kTileH + q band by band, carries the pairwise
+// scale state across the bands (they are consecutive pixels of the row) and writes one segment summary per row
+// to row_exports[y * kSegExportFloats].  Warp kConsumerWarps is the producer: it stages the same tiles, kStages ahead.
+__device__ __forceinline__ void stage_a_run(TilePipe& tp, const PairLevel& pl, const LevelGeom& g, const StageConsts& c,
+                                            float* row_exports, unsigned& tile_count, int* error_flag, PipeTiming& tm) {
+  const int lane = threadIdx.x & 31, q = threadIdx.x >> 5;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const int ntiles = (g.strip1 - g.strip0) * g.nbands;
+  const unsigned tbase = tile_count;
+  tile_count += ntiles;
+  if (q == kConsumerWarps) {   // the producer warp
+    int i = 0;
+    for (int s = g.strip0; s < g.strip1; ++s)
+      for (int b = 0; b < g.nbands; ++b, ++i) produce_tile<false>(tp, pl, g, c, s, b, tbase + i, error_flag, tm);
+    return;
   }
-  scale_state_export(ss, lane, seg_out);
+  int i = 0;
+  for (int s = g.strip0; s < g.strip1; ++s) {
+    const int y = s * kTileH + q;
+    const bool row_ok = y < g.h;
+    const float ty = __ldg(pl.rtmpl + g.w + min(y, g.h - 1));
+    ScaleState ss;
+    scale_state_init(ss);
+    for (int b = 0; b < g.nbands; ++b, ++i) {
+      const unsigned t = tbase + i;
+      const int bufi = t % kStages;
+      const long long tw0 = tm.on ? clock64() : 0;
+      mbar_wait(&tp.full[bufi], (t / kStages) & 1u, error_flag);
+      if (tm.on) tm.wait_full_a += clock64() - tw0;
+      const StageBuf& sb = tp.buf[bufi];
+      const TileDesc d = tp.desc[bufi];
+      if (row_ok && !d.skip) {
+        const WinView wv = make_view(sb, d, pl.c0, g);
+        const int x0 = b * kTileW, bw = min(kTileW, g.w - x0);
+        const int nr = (bw + 31) >> 5;
+        unsigned refa = pin(smem_u32(&sb.ref0[q][0]) + lane * 8);
+        const float* txp = pin(pl.rtmpl + x0 + lane);
+        const int xlim = bw - lane;        // lane's column r*32+lane is inside the band iff r*32 < xlim
+#pragma unroll 1
+        for (int r = 0; r < nr; ++r, refa += 256, txp += 32) {
+          const f2 rz = lds_f2_at(refa);
+          const float tx = __ldg(txp);
+          float z = hi(rz);
+          if (bw < kTileW) z = (r * 32 < xlim) ? z : __int_as_float(0x7fc00000);   // past a partial band: stale shared memory
+          const PixelProjection p = project_pixel(tx, ty, z, c);
+          float ei, ez;
+          const bool v = residual_pixel(p, wv, lo(rz), z, c, ei, ez);
+          scale_round32(ss, lane, lt_mask, v, student_weight(c, ei, ez), ei, ez);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tp.empty[bufi]);
+    }
+    if (row_ok) scale_state_export(ss, lane, row_exports + (size_t)y * kSegExportFloats);
+  }
 }
 
 // ---- stage B -----------------------------------------------------------------------------------------
 struct StageBConsts {
   float P00, P01, P10, P11;   // P_k
-  float l, wd0, wd1;          // P_k = [1 l; 0 1]^T-style factors, see stage_b_segment
-  f2 Pa, Pb;                  // P_{k-1} as stage A used it for the weights
-  bool first_iteration;
+  float l, wd0, wd1;          // P_k = [1 l; 0 1]^T-style factors, see stage_b_pixel
 };
 
 constexpr int kNormalValues = 28;   // log-likelihood sum, 21 upper-triangular A (row-major), 6 b
@@ -400,15 +656,14 @@ constexpr int kNormalValues = 28;   // log-likelihood sum, 21 upper-triangular A
 struct StageBAcc {
   f2 r0[3], r1[3], r2[2], r3[2], r4, r5;   // 12 pairs
   f2 b[3];
-  float prod;      // running product of (1 + 0.2 r^T P r) over this thread's kept points
-  float llsum;     // sum of logs flushed so far
+  float llsum;     // sum of log2(1 + 0.2 r^T P r) over this thread's kept points
 };
 
 __device__ __forceinline__ void stage_b_init(StageBAcc& a) {
 #pragma unroll
   for (int i = 0; i < 3; ++i) { a.r0[i] = 0; a.r1[i] = 0; a.b[i] = 0; }
   a.r2[0] = a.r2[1] = a.r3[0] = a.r3[1] = a.r4 = a.r5 = 0;
-  a.prod = 1.0f; a.llsum = 0.f;
+  a.llsum = 0.f;
 }
 
 // A += u v^T (upper triangle, column pairs) and b += u * s for one 6-vector given as three pairs V,
@@ -425,95 +680,132 @@ __device__ __forceinline__ void stage_b_rank1(StageBAcc& acc, const f2 V[3], flo
   acc.b[0] = fma2(U0, bc(s), acc.b[0]); acc.b[1] = fma2(U1, bc(s), acc.b[1]); acc.b[2] = fma2(U2, bc(s), acc.b[2]);
 }
 
-// Stage B over the pixels [begin, end): log-likelihood terms and normal equations with W = w * P_k.
-// rank_base: number of valid points before `begin` in row-major order; points with rank >= n_keep are
-// the dropped tail of computeCompleteDataLogLikelihood (dense_tracking_impl.cpp:413-422).
-//
+// One valid point: log-likelihood term and normal equations with W = w * P_k.
 // With l = P01/P00, d0 = P00, d1 = P11 - P01^2/P00:
 //   J^T P J = d0 j0' j0'^T + d1 J1 J1^T,  j0' = J0 + l J1,     J^T P r = d0 j0' (r0 + l r1) + d1 J1 r1
 // so each point contributes two rank-1 updates.  J rows at the untransformed reference point
 // (dense_tracking.cpp:448-476): J0 = gx a + gy b, J1 = hx a + hy b - c with
 //   a = [1/z, 0, -x/z^2, a2 y, 1 - a2 x, -y/z], b = [0, 1/z, -y/z^2, b2 y - 1, -a3, x/z], c = [0, 0, 1, y, -x, 0].
-struct StageBInput {   // everything stage B reads for one pixel; loaded two rounds ahead of its use
-  float2 e, g, h;
-  float z, tx, ty;
-};
-
-__device__ __forceinline__ StageBInput load_stage_b_input(const PairLevel& pl, const RecordPlanes& rec, int idx, int w,
-                                                          unsigned wmagic, int limit) {
-  StageBInput in;
-  const int i = min(idx, limit - 1);
-  in.e = __ldcs(rec.E + i);      // ld.global.cs: read once, do not keep in L2
-  in.g = __ldcs(rec.G + i);
-  in.h = __ldcs(rec.H + i);
-  in.z = __ldcs(rec.Z + i);      // the reference depth as stage A left it
-  const int y = (int)__umulhi((unsigned)i, wmagic);
-  const int x = i - y * w;
-  in.tx = __ldg(pl.rtmpl + x);
-  in.ty = __ldg(pl.rtmpl + w + y);
-  if (idx >= limit) in.e.x = __int_as_float(0x7fc00000);
-  return in;
+// Branch-free: a rejected point arrives with wgt = 0 and finite stand-in inputs, so it adds exact zeros.
+__device__ __forceinline__ void stage_b_pixel(StageBAcc& acc, const StageBConsts& c, float wgt, bool keep, float ei, float ez, f2 G,
+                                              f2 H, float z, float tx, float ty) {
+  // log-likelihood term: log(1 + 0.2 r^T P r); one MUFU.LG2 per point, scaled by ln 2 once at the end
+  const float d = (ei * c.P00 + ez * c.P10) * ei + (ei * c.P01 + ez * c.P11) * ez;
+  acc.llsum += __log2f(keep ? fmaf(0.2f, d, 1.0f) : 1.0f);
+  const float px = tx * z, py = ty * z;
+  const float zi = rcp_fast(z), zs = zi * zi;
+  const float a2 = -px * zs, b2 = -py * zs;
+  const float a3 = a2 * py;
+  const f2 A23 = pk(a2, a3), B23 = pk(b2, fmaf(b2, py, -1.0f));
+  const f2 A45 = pk(fmaf(-a2, px, 1.0f), -py * zi), B45 = pk(-a3, px * zi);
+  const f2 NC23 = pk(-1.0f, -py), NC45 = pk(px, 0.0f);     // -c[2..3], -c[4..5]
+  const f2 Gp = fma2(bc(c.l), H, G);                        // (gx + l hx, gy + l hy)
+  const float gx = lo(Gp), gy = hi(Gp), hx = lo(H), hy = hi(H);
+  f2 V0[3], V1[3];
+  V0[0] = mul2(Gp, bc(zi));
+  V0[1] = fma2(bc(gx), A23, fma2(bc(gy), B23, mul2(bc(c.l), NC23)));
+  V0[2] = fma2(bc(gx), A45, fma2(bc(gy), B45, mul2(bc(c.l), NC45)));
+  V1[0] = mul2(H, bc(zi));
+  V1[1] = fma2(bc(hx), A23, fma2(bc(hy), B23, NC23));
+  V1[2] = fma2(bc(hx), A45, fma2(bc(hy), B45, NC45));
+  // b -= J^T W r
+  stage_b_rank1(acc, V0, wgt * c.wd0, -fmaf(c.l, ez, ei));
+  stage_b_rank1(acc, V1, wgt * c.wd1, -ez);
 }
 
-__device__ __forceinline__ void stage_b_segment(const PairLevel& pl, const StageBConsts& c, int w, unsigned wmagic, int n,
-                                                int begin, int end, const RecordPlanes& rec, long long rank_base,
-                                                long long n_keep, bool need_rank, StageBAcc& acc) {
-  const int lane = threadIdx.x & 31;
+// optional per-pixel dump of the residual records (dvo_b200_residual_image): seven planes of n floats
+struct RecordDump {
+  float* planes;   // nullptr: off
+  int n;
+};
+__device__ __noinline__ void dump_record(const RecordDump& dump, size_t i, bool valid, f2 E, f2 G, f2 H, float z) {
+  const float nanv = __int_as_float(0x7fc00000);
+  float* p = dump.planes + i;
+  const size_t n = (size_t)dump.n;
+  p[0] = valid ? lo(E) : nanv; p[n] = valid ? hi(E) : nanv;
+  p[2 * n] = valid ? lo(G) : nanv; p[3 * n] = valid ? hi(G) : nanv;
+  p[4 * n] = valid ? lo(H) : nanv; p[5 * n] = valid ? hi(H) : nanv;
+  p[6 * n] = valid ? z : nanv;
+}
+
+// Stage B over this CTA's strips.  row_base[y]: number of valid points before row y inside this CTA (only read
+// when this CTA holds the tail of the point list); points with rank >= n_keep are the dropped tail of
+// computeCompleteDataLogLikelihood (dense_tracking_impl.cpp:413-422).
+template <bool kDump>
+__device__ __forceinline__ void stage_b_run(TilePipe& tp, const PairLevel& pl, const LevelGeom& g, const StageConsts& c,
+                                            const StageBConsts& cb, const int* row_base, long long cta_base, long long n_keep,
+                                            bool cta_has_tail, const RecordDump& dump, StageBAcc& acc, unsigned& tile_count,
+                                            int* error_flag, PipeTiming& tm) {
+  const int lane = threadIdx.x & 31, q = threadIdx.x >> 5;
   const unsigned lt_mask = (1u << lane) - 1u;
-  int seen = 0;
-  if (begin >= end) return;
-  // software pipeline: the loads of rounds r+1 and r+2 are in flight while round r is consumed
-  StageBInput in0 = load_stage_b_input(pl, rec, begin + lane, w, wmagic, end);
-  StageBInput in1 = load_stage_b_input(pl, rec, begin + 32 + lane, w, wmagic, end);
+  const int ntiles = (g.strip1 - g.strip0) * g.nbands;
+  const unsigned tbase = tile_count;
+  const int keep_rank = (int)max(min(n_keep - cta_base, (long long)0x7fffffff), (long long)-1);   // first dropped rank, CTA-relative
+  tile_count += ntiles;
+  if (q == kConsumerWarps) {   // the producer warp
+    int i = 0;
+    for (int s = g.strip0; s < g.strip1; ++s)
+      for (int b = 0; b < g.nbands; ++b, ++i) produce_tile<true>(tp, pl, g, c, s, b, tbase + i, error_flag, tm);
+    return;
+  }
+  int i = 0;
+  for (int s = g.strip0; s < g.strip1; ++s) {
+    const int y = s * kTileH + q;
+    const bool row_ok = y < g.h;
+    const float ty = __ldg(pl.rtmpl + g.w + min(y, g.h - 1));
+    int rank = 0;              // rank of the row's first point inside this CTA (n < 2^31)
+    if (cta_has_tail && row_ok) rank = __ldcg(row_base + y);
+    for (int b = 0; b < g.nbands; ++b, ++i) {
+      const unsigned t = tbase + i;
+      const int bufi = t % kStages;
+      const long long tw0 = tm.on ? clock64() : 0;
+      mbar_wait(&tp.full[bufi], (t / kStages) & 1u, error_flag);
+      if (tm.on) tm.wait_full_b += clock64() - tw0;
+      const StageBuf& sb = tp.buf[bufi];
+      const TileDesc d = tp.desc[bufi];
+      const int x0 = b * kTileW, bw = min(kTileW, g.w - x0);
+      if (row_ok && !d.skip) {
+        const WinView wv = make_view(sb, d, pl.c3, g);
+        const int nr = (bw + 31) >> 5;
+        unsigned refa = pin(smem_u32(&sb.ref0[q][0]) + lane * 8);
+        const float* txp = pin(pl.rtmpl + x0 + lane);
+        const int xlim = bw - lane;
 #pragma unroll 1
-  for (int base = begin; base < end; base += 32) {
-    const StageBInput in = in0;
-    in0 = in1;
-    in1 = load_stage_b_input(pl, rec, base + 64 + lane, w, wmagic, end);
-    const bool valid = in.e.x == in.e.x;
-    bool keep = valid;
-    if (need_rank) {   // warp-uniform: only the segments that contain the tail of the point list
-      const unsigned m = __ballot_sync(kFullMask, valid);
-      keep = valid && (rank_base + seen + __popc(m & lt_mask)) < n_keep;
-      seen += __popc(m);
+        for (int r = 0; r < nr; ++r, refa += 256, txp += 32) {
+          const f2 rz = lds_f2_at(refa);
+          const f2 gr = lds_f2<sizeof(float2) * kTileW * kTileH>(refa);     // ref1 follows ref0 in the stage buffer
+          const float tx = __ldg(txp);
+          float z = hi(rz);
+          if (bw < kTileW) z = (r * 32 < xlim) ? z : __int_as_float(0x7fc00000);
+          const PixelProjection p = project_pixel(tx, ty, z, c);
+          f2 E, G, H;
+          const bool valid = record_pixel(p, wv, lo(rz), z, gr, c, E, G, H);
+          bool keep = valid;
+          if (cta_has_tail) {   // warp-uniform
+            const unsigned m = __ballot_sync(kFullMask, valid);
+            keep = valid && (rank + __popc(m & lt_mask)) < keep_rank;
+            rank += __popc(m);
+          }
+          if (kDump && r * 32 < xlim) dump_record(dump, (size_t)y * g.w + x0 + r * 32 + lane, valid, E, G, H, z);
+          // rejected points: zero weight and finite stand-ins (their own values may be NaN)
+          const float ei = valid ? lo(E) : 0.f, ez = valid ? hi(E) : 0.f;
+          const float wall = student_weight(c, ei, ez);
+          const float wgt = valid ? wall : 0.f;
+          stage_b_pixel(acc, cb, wgt, keep, ei, ez, valid ? G : 0ull, valid ? H : 0ull, valid ? z : 1.0f, tx, ty);
+        }
+      } else if (kDump && row_ok) {
+        for (int xl = lane; xl < bw; xl += 32) dump_record(dump, (size_t)y * g.w + x0 + xl, false, 0ull, 0ull, 0ull, 0.f);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tp.empty[bufi]);
     }
-    if (!valid) continue;
-    const float ei = in.e.x, ez = in.e.y;
-    // log-likelihood term: log(1 + 0.2 r^T P r), accumulated as a product
-    const float d = (ei * c.P00 + ez * c.P10) * ei + (ei * c.P01 + ez * c.P11) * ez;
-    if (keep) {
-      acc.prod *= fmaf(0.2f, d, 1.0f);
-      if (acc.prod > 1e18f) { acc.llsum += __logf(acc.prod); acc.prod = 1.0f; }   // keep the product in range
-    }
-    const float z = in.z;
-    const float px = in.tx * z, py = in.ty * z;
-    const float zi = rcp_fast(z), zs = zi * zi;
-    const float a2 = -px * zs, b2 = -py * zs;
-    const float a3 = a2 * py;
-    const f2 A23 = pk(a2, a3), B23 = pk(b2, fmaf(b2, py, -1.0f));
-    const f2 A45 = pk(fmaf(-a2, px, 1.0f), -py * zi), B45 = pk(-a3, px * zi);
-    const f2 NC23 = pk(-1.0f, -py), NC45 = pk(px, 0.0f);     // -c[2..3], -c[4..5]
-    const f2 G = pk(in.g.x, in.g.y), H = pk(in.h.x, in.h.y);
-    const f2 Gp = fma2(bc(c.l), H, G);                        // (gx + l hx, gy + l hy)
-    const float gx = lo(Gp), gy = hi(Gp);
-    f2 V0[3], V1[3];
-    V0[0] = mul2(Gp, bc(zi));
-    V0[1] = fma2(bc(gx), A23, fma2(bc(gy), B23, mul2(bc(c.l), NC23)));
-    V0[2] = fma2(bc(gx), A45, fma2(bc(gy), B45, mul2(bc(c.l), NC45)));
-    V1[0] = mul2(H, bc(zi));
-    V1[1] = fma2(bc(in.h.x), A23, fma2(bc(in.h.y), B23, NC23));
-    V1[2] = fma2(bc(in.h.x), A45, fma2(bc(in.h.y), B45, NC45));
-    // b -= J^T W r
-    const float wgt = student_weight(c.first_iteration, c.Pa, c.Pb, ei, ez);   // same operands, same operations as stage A
-    stage_b_rank1(acc, V0, wgt * c.wd0, -fmaf(c.l, ez, ei));
-    stage_b_rank1(acc, V1, wgt * c.wd1, -ez);
   }
 }
 
 // flush the product of the pending log-likelihood terms and unpack: out[0] = ll sum,
 // out[1..21] = A upper triangle (row-major), out[22..27] = b
 __device__ __forceinline__ void stage_b_values(const StageBAcc& acc, float out[kNormalValues]) {
-  out[0] = acc.llsum + __logf(acc.prod);
+  out[0] = acc.llsum * 0.69314718055994531f;
   out[1] = lo(acc.r0[0]); out[2] = hi(acc.r0[0]); out[3] = lo(acc.r0[1]); out[4] = hi(acc.r0[1]); out[5] = lo(acc.r0[2]); out[6] = hi(acc.r0[2]);
   out[7] = hi(acc.r1[0]); out[8] = lo(acc.r1[1]); out[9] = hi(acc.r1[1]); out[10] = lo(acc.r1[2]); out[11] = hi(acc.r1[2]);
   out[12] = lo(acc.r2[0]); out[13] = hi(acc.r2[0]); out[14] = lo(acc.r2[1]); out[15] = hi(acc.r2[1]);
@@ -528,9 +820,6 @@ __device__ __forceinline__ void load_stage_b_consts(const PairState& st, StageBC
   c.l = c.P01 / c.P00;
   c.wd0 = c.P00;
   c.wd1 = c.P11 - c.P01 * c.l;
-  c.Pa = pk(__ldcg(&st.precision_prev[0]), __ldcg(&st.precision_prev[1]));
-  c.Pb = pk(__ldcg(&st.precision_prev[2]), __ldcg(&st.precision_prev[3]));
-  c.first_iteration = __ldcg(&st.iteration) == 0;
 }
 
 }  // namespace dvo_b200

@@ -5,13 +5,15 @@
 // (computeResidualsSse, computeWeightsSse, computeScaleSse, computeCompleteDataLogLikelihood and the
 // normal-equation loop, dense_tracking.cpp:271-343).  Precision P_k is a global reduction that the
 // log-likelihood and J^T W J depend on, so there are exactly two data-parallel stages (stages.cuh):
-//   stage A: warp/interpolate/residual/occlusion test, Student-t weight from P_{k-1}, pairwise scale
-//            sums, residual record kept for stage B
-//   stage B: log-likelihood terms and the 21+6 normal-equation coefficients with W = w*P_k
+//   stage A: warp/interpolate/residual/occlusion test, Student-t weight from P_{k-1}, pairwise scale sums
+//   stage B: the same residuals again plus gradients, log-likelihood terms and the 21+6 normal-equation
+//            coefficients with W = w*P_k
 // each followed by a small per-pair step (pair_mid_warp: P_k; pair_end_cta: accept test, 6x6 LDL^T
-// solve, SE(3) update, termination logic).  match() runs them inside ONE persistent cooperative
-// kernel per pyramid level (k_level_persistent); the four plain kernels k_residual / k_pair_mid /
-// k_normal / k_pair_end launch the same device functions for the test hooks (residual image, linearize).
+// solve, SE(3) update, termination logic).  Both stages read their inputs from shared-memory tiles that a
+// producer warp fills with bulk asynchronous copies (TMA unit) through an mbarrier pipeline; nothing but
+// per-row / per-CTA summaries is written.  match() runs everything inside ONE persistent cooperative
+// kernel per pyramid level (k_level_persistent); the test hooks (residual image, linearize) run the same
+// kernel for one pair and one iteration.
 #include "common.cuh"
 #include "stages.cuh"
 
@@ -27,11 +29,11 @@ namespace dvo_b200 {
 namespace {
 
 constexpr unsigned kFull = 0xffffffffu;
+constexpr int kEndWarps = 4;   // warps that sum the CTA partials in pair_end_cta
 
 struct LevelLaunch {
-  int w, h, n, ntiles;   // ntiles = CTAs of a stage launch (4 segments each)
-  int nseg;              // warp segments of kSegmentPixels pixels
-  unsigned wmagic;       // floor(2^32 / w) + 1: idx / w == __umulhi(idx, wmagic) for idx * w < 2^32
+  int w, h, n, pitch;
+  int nbands, nstrips;
   int level_index;   // position in Result.Statistics.Levels
   int level_id;      // pyramid level
   int max_iterations;
@@ -61,12 +63,12 @@ __device__ void prepare_iteration(PairState& st, const PairLevel& pl) {
   }
 }
 
-__device__ void log_iteration(dvo_b200_iteration_stats* ilog, int max_log, int pair, PairState& st, int level_id,
+__device__ void log_iteration(dvo_b200_iteration_stats* ilog, int max_log, int pair, PairState& st, int it_id, int level_id,
                               bool with_increment) {
   if (!ilog || st.iter_log_count >= max_log) { st.iter_log_count++; return; }
   dvo_b200_iteration_stats& e = ilog[(size_t)pair * max_log + st.iter_log_count++];
   e.level = level_id;
-  e.id = st.iteration;
+  e.id = it_id;
   e.valid_constraints = st.n;
   e.tdist_log_likelihood = st.nll_cur;
   for (int i = 0; i < 4; ++i) e.tdist_precision[i] = (double)st.precision[i];
@@ -113,64 +115,13 @@ __global__ void k_level_begin(PairState* states, const PairLevel* pls_src, PairL
   prepare_iteration(st, pl);
 }
 
-// ------------------------------------------------------------------------------------------------
-// stage A kernel: one warp per 256-pixel segment, four segments per CTA
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kSegmentsPerTile * 32)
-k_residual(const PairState* __restrict__ states, const PairLevel* __restrict__ pls, float* __restrict__ records,
-           float* __restrict__ seg_export, LevelLaunch lp) {
-  const int pair = blockIdx.y;
-  const PairState& st = states[pair];
-  if (!st.level_active) return;
-  const PairLevel pl = pls[pair];
-  StageConsts c;
-  load_stage_consts(st, pl, lp.w, lp.h, c);
-  const int warp = threadIdx.x >> 5;
-  const int seg = blockIdx.x * kSegmentsPerTile + warp;
-  const int begin = min(seg * kSegmentPixels, lp.n);
-  const int end = min(begin + kSegmentPixels, lp.n);
-  const RecordPlanes rec = record_planes(records + (size_t)pair * kRecordFloatsPerPixel * lp.n, lp.n);
-  __shared__ float sm_exp[kSegmentsPerTile][kSegExportFloats];
-  stage_a_segment(pl, c, lp.w, lp.wmagic, lp.n, begin, end, rec, sm_exp[warp]);
-  __syncthreads();
-  if (threadIdx.x == 0) cta_export_segments(sm_exp, seg_export + ((size_t)pair * lp.ntiles + blockIdx.x) * kCtaExportFloats);
-}
-
-struct PairMidSmem {
-  SegT<double> lanes[32];
-  long long lane_base[32];
-};
-
-// one warp per pair: combine the segment summaries in order -> covariance -> P_k (dense_tracking.cpp:276-295).
-// e: this pair's nseg segment exports; seg_base: this pair's exclusive prefix of valid counts (output).
-__device__ __noinline__ void pair_mid_warp(PairState& st, int pair, const float* e, int* seg_base, int ntiles, int* active,
-                              const LevelLaunch& lp, dvo_b200_iteration_stats* ilog, int max_log, PairMidSmem& sm) {
+// one warp per pair: combine the CTA summaries of the squad in order -> covariance -> P_k (dense_tracking.cpp:276-295).
+// e: the squad's g CTA exports; cta_base: exclusive prefix of their valid counts (output).
+__device__ __noinline__ void pair_mid_warp(PairState& st, int pair, const float* e, int* cta_base, int g, int* active,
+                                           const LevelLaunch& lp, dvo_b200_iteration_stats* ilog, int max_log, SegCombineSmem& sm) {
   const int lane = threadIdx.x & 31;
-  SegT<double>* lanes = sm.lanes;
-  long long* lane_base = sm.lane_base;
-  int chunk = (ntiles + 31) / 32;
-  int t0 = lane * chunk, t1 = min(t0 + chunk, ntiles);
-  SegT<double> acc;
-  acc.n = 0; acc.wf = acc.wl = 0;
-  for (int k = 0; k < 3; ++k) acc.S0[k] = acc.S1[k] = acc.ol[k] = 0;
-  for (int t = t0; t < t1; ++t) acc = combine_seg<double>(acc, load_seg_export(e + (size_t)t * kCtaExportFloats));
-  lanes[lane] = acc;
-  {   // exclusive prefix of the lane counts
-    long long incl = acc.n;
-#pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-      long long v = __shfl_up_sync(kFull, incl, off);
-      if (lane >= off) incl += v;
-    }
-    lane_base[lane] = incl - acc.n;
-  }
-  __syncwarp();
-  for (int off = 1; off < 32; off <<= 1) {   // in-order tree combine
-    if ((lane & (2 * off - 1)) == 0) lanes[lane] = combine_seg<double>(lanes[lane], lanes[lane + off]);
-    __syncwarp();
-  }
+  const SegT<double> all = combine_exports_warp(e, g, cta_base, sm);
   if (lane == 0) {
-    SegT<double> all = lanes[0];
     long long n = all.n;
     st.n = n;
     st.n_keep = (n / 50) * 50;
@@ -184,7 +135,7 @@ __device__ __noinline__ void pair_mid_warp(PairState& st, int pair, const float*
       st.termination = DVO_B200_TERM_TOO_FEW_CONSTRAINTS;
       st.phase_ok = 0;
       st.nll_cur = 0; st.prior_cur = 0;
-      log_iteration(ilog, max_log, pair, st, lp.level_id, false);
+      log_iteration(ilog, max_log, pair, st, st.iteration, lp.level_id, false);
       // post-loop checks of dense_tracking.cpp:359-363 still apply
       double m = 0; bool nanx = false;
       for (int i = 0; i < 6; ++i) { m = fmax(m, fabs(st.x[i])); nanx |= st.x[i] != st.x[i]; }
@@ -215,71 +166,6 @@ __device__ __noinline__ void pair_mid_warp(PairState& st, int pair, const float*
     }
   }
   __syncwarp();
-  // exclusive prefix of valid counts per tile (rank base for the log-likelihood tail drop)
-  long long run = lane_base[lane];
-  for (int t = t0; t < t1; ++t) {
-    seg_base[t] = (int)run;
-    run += __float_as_int(__ldcg(e + (size_t)t * kCtaExportFloats));
-  }
-  __syncwarp();
-}
-
-__global__ void k_pair_mid(PairState* states, const float* __restrict__ scale_export, int* __restrict__ tile_base,
-                           int ntiles, int* active, LevelLaunch lp, dvo_b200_iteration_stats* ilog, int max_log) {
-  const int pair = blockIdx.x;
-  PairState& st = states[pair];
-  if (!st.level_active) return;
-  __shared__ PairMidSmem sm;
-  pair_mid_warp(st, pair, scale_export + (size_t)pair * ntiles * kCtaExportFloats, tile_base + (size_t)pair * ntiles, ntiles,
-                active, lp, ilog, max_log, sm);
-}
-
-// ------------------------------------------------------------------------------------------------
-// stage B kernel: one warp per segment, CTA-level reduction of the 28 values in a fixed order
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kSegmentsPerTile * 32)
-k_normal(const PairState* __restrict__ states, const PairLevel* __restrict__ pls, const float* __restrict__ records,
-         const float* __restrict__ seg_export, const int* __restrict__ seg_base, float* __restrict__ partial,
-         LevelLaunch lp) {
-  const int pair = blockIdx.y, tile = blockIdx.x;
-  const PairState& st = states[pair];
-  if (!st.level_active || !st.phase_ok) return;
-  const PairLevel pl = pls[pair];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  StageBConsts c;
-  load_stage_b_consts(st, c);
-  const int seg = tile * kSegmentsPerTile + warp;
-  StageBAcc acc;
-  stage_b_init(acc);
-  if (seg < lp.nseg) {
-    const int begin = seg * kSegmentPixels;
-    const int end = min(begin + kSegmentPixels, lp.n);
-    const RecordPlanes rec = record_planes(const_cast<float*>(records) + (size_t)pair * kRecordFloatsPerPixel * lp.n, lp.n);
-    const float* ce = seg_export + ((size_t)pair * lp.ntiles + tile) * kCtaExportFloats;
-    long long base = seg_base[(size_t)pair * lp.ntiles + tile];
-    for (int k = 0; k < warp; ++k) base += __float_as_int(ce[12 + k]);
-    const int cnt = __float_as_int(ce[12 + warp]);
-    const bool need_rank = base + cnt > st.n_keep;    // only the segments holding the tail of the point list
-    stage_b_segment(pl, c, lp.w, lp.wmagic, lp.n, begin, end, rec, base, st.n_keep, need_rank, acc);
-  }
-  float v[kNormalValues];
-  stage_b_values(acc, v);
-  __shared__ float red[kSegmentsPerTile][kNormalValues];
-#pragma unroll
-  for (int i = 0; i < kNormalValues; ++i) {
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) v[i] += __shfl_xor_sync(kFull, v[i], off);
-  }
-  if (lane == 0) {
-#pragma unroll
-    for (int i = 0; i < kNormalValues; ++i) red[warp][i] = v[i];
-  }
-  __syncthreads();
-  if (threadIdx.x < kNormalValues) {
-    float s = 0.f;
-    for (int k = 0; k < kSegmentsPerTile; ++k) s += red[k][threadIdx.x];
-    partial[((size_t)pair * lp.ntiles + tile) * kNormalValues + threadIdx.x] = s;
-  }
 }
 
 // End of an iteration (dense_tracking.cpp:297-363): reduce the CTA partials, log-likelihood, accept test, solve,
@@ -289,7 +175,7 @@ k_normal(const PairState* __restrict__ states, const PairLevel* __restrict__ pls
 //   deferred : Revertable bookkeeping, statistics, the iteration log.  It finishes before this CTA arrives at
 //              the squad's next barrier, so the next P_k / end step (run by whichever CTA arrives last) sees it.
 struct PairEndSmem {
-  double part[kSegmentsPerTile][32];
+  double part[kEndWarps][32];
 };
 
 template <typename Release>
@@ -299,19 +185,19 @@ __device__ __noinline__ void pair_end_cta(PairState& st, const PairLevel& pl, in
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   {   // fp64 sum of the partials: warp q takes tiles q, q+4, ... with independent loads in flight
     double v = 0.0;
-    if (lane < kNormalValues) {
+    if (lane < kNormalValues && warp < kEndWarps) {
       const float* p = partial + lane;
       int t = warp;
-      for (; t + 3 * kSegmentsPerTile < ntiles; t += 4 * kSegmentsPerTile) {
+      for (; t + 3 * kEndWarps < ntiles; t += 4 * kEndWarps) {
         const float a0 = __ldcg(p + (size_t)t * kNormalValues);
-        const float a1 = __ldcg(p + (size_t)(t + kSegmentsPerTile) * kNormalValues);
-        const float a2 = __ldcg(p + (size_t)(t + 2 * kSegmentsPerTile) * kNormalValues);
-        const float a3 = __ldcg(p + (size_t)(t + 3 * kSegmentsPerTile) * kNormalValues);
+        const float a1 = __ldcg(p + (size_t)(t + kEndWarps) * kNormalValues);
+        const float a2 = __ldcg(p + (size_t)(t + 2 * kEndWarps) * kNormalValues);
+        const float a3 = __ldcg(p + (size_t)(t + 3 * kEndWarps) * kNormalValues);
         v += (double)a0; v += (double)a1; v += (double)a2; v += (double)a3;
       }
-      for (; t < ntiles; t += kSegmentsPerTile) v += (double)__ldcg(p + (size_t)t * kNormalValues);
+      for (; t < ntiles; t += kEndWarps) v += (double)__ldcg(p + (size_t)t * kNormalValues);
     }
-    sm.part[warp][lane] = v;
+    if (warp < kEndWarps) sm.part[warp][lane] = v;
   }
   __syncthreads();
   if (threadIdx.x != 0) return;
@@ -320,7 +206,7 @@ __device__ __noinline__ void pair_end_cta(PairState& st, const PairLevel& pl, in
   for (int i = 0; i < kNormalValues; ++i) {
     double v = sm.part[0][i];
 #pragma unroll
-    for (int q = 1; q < kSegmentsPerTile; ++q) v += sm.part[q][i];
+    for (int q = 1; q < kEndWarps; ++q) v += sm.part[q][i];
     vals[i] = v;
   }
 
@@ -347,6 +233,7 @@ __device__ __noinline__ void pair_end_cta(PairState& st, const PairLevel& pl, in
     for (int i = 0; i < 6; ++i) bvec[i] = vals[22 + i];
   }
   int iteration = st.iteration;
+  const int it_id = iteration;                     // IterationStats.Id = itctx_.Iteration before the increment (dense_tracking.cpp:251)
   if (accept) {
     double As[36], bs[6];
     for (int i = 0; i < 36; ++i) As[i] = A[i];
@@ -392,14 +279,14 @@ __device__ __noinline__ void pair_end_cta(PairState& st, const PairLevel& pl, in
   if (!accept) {
     st.initial = st.initial_old; st.estimate = st.estimate_old;   // dense_tracking.cpp:314-321
     st.termination = DVO_B200_TERM_LOG_LIKELIHOOD_DECREASED;
-    log_iteration(ilog, max_log, pair, st, lp.level_id, false);
+    log_iteration(ilog, max_log, pair, st, it_id, lp.level_id, false);
   } else {
     for (int i = 0; i < 6; ++i) st.x[i] = x[i];
     for (int i = 0; i < 36; ++i) st.A_done[i] = A[i];
     for (int i = 0; i < 6; ++i) st.A_done[i * 6 + i] += lp.mu;
     st.nll_done = st.nll_cur; st.prior_done = st.prior_cur; st.have_done = 1;
     ls.last_inc_n = st.n; ls.last_inc_nll = st.nll_cur;
-    log_iteration(ilog, max_log, pair, st, lp.level_id, true);
+    log_iteration(ilog, max_log, pair, st, it_id, lp.level_id, true);
     st.iteration = iteration;
   }
   if (level_done) {
@@ -419,33 +306,19 @@ __device__ __noinline__ void pair_end_cta(PairState& st, const PairLevel& pl, in
   }
 }
 
-__global__ void __launch_bounds__(kSegmentsPerTile * 32)
-k_pair_end(PairState* states, const PairLevel* pls, const float* __restrict__ partial, int ntiles,
-           int* active, LevelLaunch lp, dvo_b200_iteration_stats* ilog, int max_log) {
-  const int pair = blockIdx.x;
-  PairState& st = states[pair];
-  if (!st.level_active || !st.phase_ok) return;
-  __shared__ PairEndSmem sm;
-  pair_end_cta(st, pls[pair], pair, partial + (size_t)pair * ntiles * kNormalValues, ntiles, active, lp, ilog, max_log, sm, [] {});
-}
-
 // ------------------------------------------------------------------------------------------------
 // One persistent cooperative kernel per pyramid level.
 //
-// The grid is num_sms x C CTAs (C = resident CTAs per SM).  CTAs are grouped into squads of g CTAs
-// (g chosen per level so that a warp walks >= ~8 rounds of 32 pixels); a squad owns ONE frame pair at
-// a time and runs all its Gauss-Newton iterations on this level inside the kernel:
-//   stage A over the squad's warp segments -> squad barrier, the last CTA to arrive computes P_k
-//   (pair_mid_warp) -> stage B -> squad barrier, the last CTA reduces the partials, tests the
-//   log-likelihood, solves the 6x6 system and updates the pose (pair_end_cta) -> next iteration,
-// then takes the next pair from a global queue.  The residual records of the pair in flight live in a
-// per-squad scratch buffer that is rewritten every iteration and therefore stays in L2; the squads of
-// different resident-CTA slots share each SM, so one squad's barrier wait is hidden by the others.
+// The grid is num_sms x C CTAs (C = resident CTAs per SM, 2 with ~98 KB of shared memory each) of 8 warps.  CTAs are grouped into squads of g CTAs; a squad owns ONE frame pair at a time, each CTA a
+// contiguous range of strips (kTileH image rows), and runs all its Gauss-Newton iterations on this level inside the
+// kernel:
+//   stage A over the CTA's tiles -> per-row scale summaries -> CTA summary -> squad barrier, the last CTA to
+//   arrive computes P_k (pair_mid_warp) -> stage B -> CTA partial sums -> squad barrier, the last CTA reduces
+//   the partials, tests the log-likelihood, solves the 6x6 system and updates the pose (pair_end_cta) -> next
+//   iteration,
+// then takes the next pair from a global queue.  The two resident CTAs of an SM belong to different squads, so
+// one squad's barrier wait is hidden by the other.
 // ------------------------------------------------------------------------------------------------
-#ifndef DVO_PERSISTENT_CTAS_PER_SM
-#define DVO_PERSISTENT_CTAS_PER_SM 4   // resident 128-thread CTAs per SM the register budget is tuned for (128 regs/thread)
-#endif
-
 struct SquadState {
   int pair;
   unsigned arrive;
@@ -453,20 +326,30 @@ struct SquadState {
   int pad_[29];   // one 128-byte line per squad
 };
 
+struct LevelTail {      // shared memory after the tile pipeline
+  SegCombineSmem comb;
+  PairEndSmem end;
+  float red[kConsumerWarps][kNormalValues];
+  int s_flag[2];
+};
+constexpr size_t kLevelSmemBytes = sizeof(TilePipe) + sizeof(LevelTail);
+
 struct PersistentArgs {
   PairState* states;
   const PairLevel* pls;
-  float* records;
-  float* seg_export;
-  int* seg_base;
-  float* partial;
+  float* row_exports;     // per squad: h segment summaries (one per image row)
+  int* row_base;          // per squad: h exclusive prefixes of valid counts, relative to the owning CTA's first row
+  float* cta_exports;     // per squad: g segment summaries
+  int* cta_base;          // per squad: g exclusive prefixes
+  float* partial;         // per squad: g x kNormalValues
   SquadState* squads;
   int* next_pair;
   int* error_flag;
   dvo_b200_iteration_stats* ilog;
   int max_log;
+  float* dump;            // test hook: seven record planes of the (single) pair, or nullptr
   unsigned long long* dbg;   // optional: ns spent per CTA in {stage A, stage B, wait A, wait B, mid, end, queue, total}
-  int npairs, g, squads_per_slot, num_sms, rpw, nseg;
+  int npairs, g, nsquads, strips_per_cta;
   LevelLaunch lp;
 };
 
@@ -503,7 +386,7 @@ __device__ __forceinline__ void squad_wait(SquadState* sq, unsigned episode, int
   if (threadIdx.x == 0) {
     unsigned spins = 0;
     while (ld_acquire_u32(&sq->phase) < episode + 1u) {
-      __nanosleep(200);
+      __nanosleep(100);
       if (((++spins) & 4095u) == 0u) {
         if (*reinterpret_cast<volatile int*>(error_flag)) break;
         if (spins > (1u << 25)) { atomicExch(error_flag, 1); break; }   // ~ seconds: never hang the GPU
@@ -513,35 +396,40 @@ __device__ __forceinline__ void squad_wait(SquadState* sq, unsigned episode, int
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(kSegmentsPerTile * 32, DVO_PERSISTENT_CTAS_PER_SM)
+__global__ void __launch_bounds__(kCtaThreads, 2)
 k_level_persistent(PersistentArgs a) {
-  const int slot = blockIdx.x / a.num_sms, smi = blockIdx.x % a.num_sms;
-  const int sq_in_slot = smi / a.g;
-  if (sq_in_slot >= a.squads_per_slot) return;   // leftover CTAs of this slot
-  const int squad = slot * a.squads_per_slot + sq_in_slot;
-  const int rank = smi - sq_in_slot * a.g;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  TilePipe& tp = *reinterpret_cast<TilePipe*>(smem_raw);
+  LevelTail& lt = *reinterpret_cast<LevelTail*>(smem_raw + sizeof(TilePipe));
+
+  const int squad = blockIdx.x / a.g, rank = blockIdx.x - squad * a.g;
+  if (squad >= a.nsquads) return;   // leftover CTAs
   SquadState* sq = a.squads + squad;
   const LevelLaunch& lp = a.lp;
-  float* rec_base = a.records + (size_t)squad * kRecordFloatsPerPixel * lp.n;
-  float* exports = a.seg_export + (size_t)squad * a.g * kCtaExportFloats;
-  int* segbase = a.seg_base + (size_t)squad * a.g;
+  float* row_exports = a.row_exports + (size_t)squad * lp.h * kSegExportFloats;
+  int* row_base = a.row_base + (size_t)squad * lp.h;
+  float* cta_exports = a.cta_exports + (size_t)squad * a.g * kSegExportFloats;
+  int* cta_base = a.cta_base + (size_t)squad * a.g;
   float* partial = a.partial + (size_t)squad * a.g * kNormalValues;
-  const RecordPlanes rec = record_planes(rec_base, lp.n);
-
-  __shared__ PairMidSmem sm_mid;
-  __shared__ PairEndSmem sm_end;
-  __shared__ float red[kSegmentsPerTile][kNormalValues];
-  __shared__ float sm_exp[kSegmentsPerTile][kSegExportFloats];
-  __shared__ int s_flag[2];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int wk = rank * kSegmentsPerTile + warp;           // this warp's segment index inside the squad
-  const int R = (lp.n + 31) >> 5;
-  const int r0 = min(wk * a.rpw, R), r1 = min(r0 + a.rpw, R);
-  const int begin = r0 * 32, end = min(r1 * 32, lp.n);
+  LevelGeom geo;
+  geo.w = lp.w; geo.h = lp.h; geo.n = lp.n; geo.pitch = lp.pitch; geo.nbands = lp.nbands; geo.nstrips = lp.nstrips;
+  geo.strip0 = min(rank * a.strips_per_cta, lp.nstrips);
+  geo.strip1 = min(geo.strip0 + a.strips_per_cta, lp.nstrips);
+  const int row0 = min(geo.strip0 * kTileH, lp.h), row1 = min(geo.strip1 * kTileH, lp.h);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kStages; ++i) { mbar_init(&tp.full[i], 1); mbar_init(&tp.empty[i], kConsumerWarps); }
+    mbar_fence_init();
+  }
+  __syncthreads();
+  unsigned tile_count = 0;      // tiles staged / consumed by this CTA since the kernel started
   unsigned episode = 0;
   unsigned long long t_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t0 = 0, t1 = 0;
   const bool timing = a.dbg != nullptr && threadIdx.x == 0;
+  PipeTiming tm;
+  tm.on = a.dbg != nullptr && lane == 0 && (warp == 0 || warp == kConsumerWarps);   // one consumer warp and the producer
   const unsigned long long t_start = timing ? global_ns() : 0;
 #define DVO_TICK() do { if (timing) t0 = global_ns(); } while (0)
 #define DVO_TOCK(slot) do { if (timing) { t1 = global_ns(); t_acc[slot] += t1 - t0; t0 = t1; } } while (0)
@@ -549,7 +437,7 @@ k_level_persistent(PersistentArgs a) {
   for (;;) {
     DVO_TICK();
     // ---- take the next pair from the queue (the last CTA to arrive does it for the squad) ----
-    if (squad_arrive(sq, episode, a.g, s_flag)) {
+    if (squad_arrive(sq, episode, a.g, lt.s_flag)) {
       if (threadIdx.x == 0) {
         int p = atomicAdd(a.next_pair, 1);
         sq->pair = p < a.npairs ? p : -1;
@@ -570,16 +458,21 @@ k_level_persistent(PersistentArgs a) {
       // ---- stage A ----
       {
         StageConsts c;
-        load_stage_consts(st, pl, lp.w, lp.h, c);
-        stage_a_segment(pl, c, lp.w, lp.wmagic, lp.n, begin, end, rec, sm_exp[warp]);
-        __syncthreads();
-        if (threadIdx.x == 0) cta_export_segments(sm_exp, exports + (size_t)rank * kCtaExportFloats);
+        load_stage_consts(st, pl, lp.w, lp.h, false, c);
+        const long long ts0 = tm.on ? clock64() : 0;
+        stage_a_run(tp, pl, geo, c, row_exports, tile_count, a.error_flag, tm);
+        if (tm.on) tm.rounds_a += clock64() - ts0;
+      }
+      __syncthreads();
+      if (warp == 0) {   // this CTA's rows, in order -> one summary; row_base: rank of each row's first point inside the CTA
+        const SegT<double> mine = combine_exports_warp(row_exports + (size_t)row0 * kSegExportFloats, row1 - row0, row_base + row0, lt.comb);
+        if (lane == 0) store_seg_export(mine, cta_exports + (size_t)rank * kSegExportFloats);
       }
       DVO_TOCK(0);
-      if (squad_arrive(sq, episode, a.g, s_flag)) {
+      if (squad_arrive(sq, episode, a.g, lt.s_flag)) {
         DVO_TOCK(2);
         if (warp == 0) {
-          pair_mid_warp(st, pair, exports, segbase, a.g, nullptr, lp, a.ilog, a.max_log, sm_mid);
+          pair_mid_warp(st, pair, cta_exports, cta_base, a.g, nullptr, lp, a.ilog, a.max_log, lt.comb);
           if (lane == 0) squad_release(sq, episode);
         }
         __syncthreads();
@@ -594,15 +487,21 @@ k_level_persistent(PersistentArgs a) {
 
       // ---- stage B ----
       {
+        StageConsts c;
+        load_stage_consts(st, pl, lp.w, lp.h, true, c);
         StageBConsts cb;
         load_stage_b_consts(st, cb);
         StageBAcc acc;
         stage_b_init(acc);
         const long long n_keep = __ldcg(&st.n_keep);
-        long long base = __ldcg(&segbase[rank]);
-        for (int k = 0; k < warp; ++k) base += __float_as_int(sm_exp[k][0]);
-        const int cnt = __float_as_int(sm_exp[warp][0]);
-        stage_b_segment(pl, cb, lp.w, lp.wmagic, lp.n, begin, end, rec, base, n_keep, base + cnt > n_keep, acc);
+        const long long my_base = __ldcg(&cta_base[rank]);
+        const long long my_n = __float_as_int(__ldcg(cta_exports + (size_t)rank * kSegExportFloats));
+        RecordDump dump;
+        dump.planes = a.dump; dump.n = lp.n;
+        const long long ts0 = tm.on ? clock64() : 0;
+        if (a.dump) stage_b_run<true>(tp, pl, geo, c, cb, row_base, my_base, n_keep, my_base + my_n > n_keep, dump, acc, tile_count, a.error_flag, tm);
+        else stage_b_run<false>(tp, pl, geo, c, cb, row_base, my_base, n_keep, my_base + my_n > n_keep, dump, acc, tile_count, a.error_flag, tm);
+        if (tm.on) tm.rounds_b += clock64() - ts0;
         float v[kNormalValues];
         stage_b_values(acc, v);
 #pragma unroll
@@ -610,21 +509,21 @@ k_level_persistent(PersistentArgs a) {
 #pragma unroll
           for (int off = 16; off > 0; off >>= 1) v[i] += __shfl_xor_sync(kFull, v[i], off);
         }
-        if (lane == 0) {
+        if (lane == 0 && warp < kConsumerWarps) {
 #pragma unroll
-          for (int i = 0; i < kNormalValues; ++i) red[warp][i] = v[i];
-        }
-        __syncthreads();
-        if (threadIdx.x < kNormalValues) {
-          float s = 0.f;
-          for (int k = 0; k < kSegmentsPerTile; ++k) s += red[k][threadIdx.x];
-          partial[(size_t)rank * kNormalValues + threadIdx.x] = s;
+          for (int i = 0; i < kNormalValues; ++i) lt.red[warp][i] = v[i];
         }
       }
+      __syncthreads();
+      if (threadIdx.x < kNormalValues) {
+        float s = 0.f;
+        for (int k = 0; k < kConsumerWarps; ++k) s += lt.red[k][threadIdx.x];
+        partial[(size_t)rank * kNormalValues + threadIdx.x] = s;
+      }
       DVO_TOCK(1);
-      if (squad_arrive(sq, episode, a.g, s_flag)) {
+      if (squad_arrive(sq, episode, a.g, lt.s_flag)) {
         DVO_TOCK(3);
-        pair_end_cta(st, pl, pair, partial, a.g, nullptr, lp, a.ilog, a.max_log, sm_end, [&] { squad_release(sq, episode); });
+        pair_end_cta(st, pl, pair, partial, a.g, nullptr, lp, a.ilog, a.max_log, lt.end, [&] { squad_release(sq, episode); });
         __syncthreads();
         DVO_TOCK(5);
       } else {
@@ -639,6 +538,10 @@ k_level_persistent(PersistentArgs a) {
   if (timing) {
     t_acc[7] = global_ns() - t_start;
     for (int i = 0; i < 8; ++i) atomicAdd(a.dbg + i, t_acc[i]);
+  }
+  if (tm.on) {   // cycles: consumer warp 0 {stage A, wait full A, stage B, wait full B}, producer {descriptor, wait empty}
+    if (warp == 0) { atomicAdd(a.dbg + 8, tm.rounds_a); atomicAdd(a.dbg + 9, tm.wait_full_a); atomicAdd(a.dbg + 10, tm.rounds_b); atomicAdd(a.dbg + 11, tm.wait_full_b); }
+    else { atomicAdd(a.dbg + 12, tm.produce); atomicAdd(a.dbg + 13, tm.wait_empty); atomicAdd(a.dbg + 14, tm.rounds_a); atomicAdd(a.dbg + 15, tm.rounds_b); }
   }
 #undef DVO_TICK
 #undef DVO_TOCK
@@ -716,7 +619,8 @@ int grow(dvo_b200_ctx* ctx, T*& ptr, size_t& cap, size_t need) {
 }
 
 struct ScratchNeed {
-  size_t record_floats = 0, export_floats = 0, segbase_ints = 0, partial_floats = 0, squads = 0;
+  size_t row_export_floats = 0, row_base_ints = 0, cta_export_floats = 0, cta_base_ints = 0, partial_floats = 0, squads = 0;
+  size_t dump_floats = 0;
 };
 
 int ensure_workspace(dvo_b200_ctx* ctx, int npairs, const ScratchNeed& need, int max_log_per_pair) {
@@ -729,15 +633,14 @@ int ensure_workspace(dvo_b200_ctx* ctx, int npairs, const ScratchNeed& need, int
     ws.cap_pairs = npairs;
   }
   int rc;
-  if ((rc = grow(ctx, ws.d_records, ws.cap_records, need.record_floats))) return rc;
-  if ((rc = grow(ctx, ws.d_scale_export, ws.cap_export, need.export_floats))) return rc;
-  if ((rc = grow(ctx, ws.d_tile_base, ws.cap_segbase, need.segbase_ints))) return rc;
+  if ((rc = grow(ctx, ws.d_row_exports, ws.cap_row_exports, need.row_export_floats))) return rc;
+  if ((rc = grow(ctx, ws.d_row_base, ws.cap_row_base, need.row_base_ints))) return rc;
+  if ((rc = grow(ctx, ws.d_cta_exports, ws.cap_cta_exports, need.cta_export_floats))) return rc;
+  if ((rc = grow(ctx, ws.d_cta_base, ws.cap_cta_base, need.cta_base_ints))) return rc;
   if ((rc = grow(ctx, ws.d_normal_partial, ws.cap_partial, need.partial_floats))) return rc;
   if ((rc = grow(ctx, ws.d_squads, ws.cap_squads, need.squads * sizeof(SquadState)))) return rc;
-  if (!ws.d_active) {
-    DVO_CUDA(ctx, cudaMalloc((void**)&ws.d_active, sizeof(int) * 8));
-    DVO_CUDA(ctx, cudaMallocHost((void**)&ws.h_active, sizeof(int) * 8));
-  }
+  if ((rc = grow(ctx, ws.d_dump, ws.cap_dump, need.dump_floats))) return rc;
+  if (!ws.h_active) DVO_CUDA(ctx, cudaMallocHost((void**)&ws.h_active, sizeof(int) * 8));
   if (max_log_per_pair > 0) {
     size_t n = (size_t)npairs * max_log_per_pair;
     if ((rc = grow(ctx, ws.d_iter_log, ws.cap_iter_log, n))) return rc;
@@ -745,47 +648,50 @@ int ensure_workspace(dvo_b200_ctx* ctx, int npairs, const ScratchNeed& need, int
   return 0;
 }
 
+int ensure_geometry(dvo_b200_ctx* ctx) {
+  if (ctx->num_sms != 0) return 0;
+  cudaDeviceProp prop;
+  DVO_CUDA(ctx, cudaGetDeviceProperties(&prop, ctx->device));
+  DVO_CUDA(ctx, cudaFuncSetAttribute(k_level_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLevelSmemBytes));
+  int per_sm = 0;
+  DVO_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_level_persistent, kCtaThreads, kLevelSmemBytes));
+  if (per_sm < 1) return set_error(ctx, DVO_B200_ERR_CUDA, "persistent kernel does not fit on an SM");
+  ctx->ctas_per_sm = per_sm;
+  ctx->num_sms = prop.multiProcessorCount;
+  return 0;
+}
+
 // How one pyramid level is spread over the persistent grid.
 struct LevelPlan {
   int g;                // CTAs per squad
-  int squads_per_slot;  // num_sms / g
-  int nsquads;          // ctas_per_sm * squads_per_slot
-  int rpw;              // rounds of 32 pixels per warp
-  int nseg;             // warp segments per pair = g * kSegmentsPerTile
+  int nsquads;          // squads in the grid
+  int strips_per_cta;
 };
 
-LevelPlan plan_level(int n, int num_sms, int ctas_per_sm, int npairs) {
-  LevelPlan p;
-  const int R = (n + 31) / 32;
-  const int warps = kSegmentsPerTile;
-  // Squad size.  Small squads keep many pairs in flight and amortise the two barriers and the serial P_k / solve
-  // sections of an iteration over long warp segments (`target` rounds of 32 pixels per warp and stage); but the
+LevelPlan plan_level(int nstrips, int nbands, int num_sms, int ctas_per_sm, int npairs) {
+  // A squad of g CTAs gives each CTA spc = ceil(nstrips / g) strips.  Small squads keep many pairs in flight and
+  // amortise the two barriers and the serial P_k / solve sections of an iteration over more tiles per CTA; but the
   // batch is processed in waves of nsquads pairs, and a last wave that is mostly empty wastes more than that.
   // Pairs are handed out from a queue, so a level takes about (pairs per squad + tail) x time per pair, where the
-  // tail (pairs that need two or three times the mean number of iterations) is worth a bit more than one pair
-  // and the time per pair goes with (rounds per warp + per-iteration overhead in round units).  Pick the number
-  // of squads per resident-CTA slot that minimises that among the sizes near the target.
-  static const int target = [] { const char* e = getenv("DVO_B200_RPW"); int v = e ? atoi(e) : 0; return v > 0 ? v : 128; }();
-  const int overhead = 16;
-  const int k_max = std::max(1, (npairs + ctas_per_sm - 1) / ctas_per_sm);   // few pairs: fewer, larger squads (latency)
-  int best_k = 1;
+  // tail (pairs that need two or three times the mean number of iterations) is worth a bit more than one pair and
+  // the time per pair goes with (tiles per CTA + per-iteration overhead in tile units).
+  const char* env = getenv("DVO_B200_STRIPS_PER_CTA");     // developer override (experiments)
+  const int forced_spc = env ? atoi(env) : 0;
+  const int grid = num_sms * ctas_per_sm;
+  const double overhead_tiles = 3.0;
+  LevelPlan best{1, 1, nstrips};
   double best_cost = -1.0;
-  for (int k = 1; k <= std::min(num_sms, k_max); ++k) {
-    const int g = num_sms / k;
-    const int rpw = (R + g * warps - 1) / (g * warps);
-    if (rpw > target + target / 2 && k > 1) break;    // rpw grows with k
-    const double per_squad = (double)npairs / ((double)ctas_per_sm * k);
-    const double cost = (std::max(per_squad, 1.0) + 1.2) * (rpw + overhead);
-    if (best_cost < 0 || cost < best_cost - 1e-9) { best_cost = cost; best_k = k; }
+  for (int spc = 1; spc <= nstrips; ++spc) {
+    const int g = (nstrips + spc - 1) / spc;
+    if (g > grid) continue;
+    if (spc > 1 && (nstrips + spc - 2) / (spc - 1) == g) continue;   // same g as the previous spc: more work per CTA, nothing gained
+    const int nsquads = std::min(grid / g, std::max(npairs, 1));
+    const double per_squad = (double)npairs / nsquads;
+    double cost = (std::max(per_squad, 1.0) + (npairs > nsquads ? 1.2 : 0.0)) * ((double)spc * nbands + overhead_tiles);
+    if (forced_spc > 0) cost = std::abs(spc - forced_spc);
+    if (best_cost < 0 || cost < best_cost - 1e-9) { best_cost = cost; best = LevelPlan{g, nsquads, spc}; }
   }
-  const int k = best_k;
-  int g = num_sms / k;
-  p.g = g;
-  p.squads_per_slot = k;
-  p.nsquads = ctas_per_sm * p.squads_per_slot;
-  p.rpw = (R + g * warps - 1) / (g * warps);
-  p.nseg = g * warps;
-  return p;
+  return best;
 }
 
 int check_batch(dvo_b200_ctx* ctx, const dvo_b200_config* cfg, int n, dvo_b200_pyramid* const* refs,
@@ -815,25 +721,64 @@ void fill_pair_levels(PairLevel* h, int n, dvo_b200_pyramid* const* refs, dvo_b2
     const LevelInfo& rl = r->L[level];
     const LevelInfo& cl = c->L[level];
     PairLevel& q = h[i];
-    q.r0 = r->planes + rl.plane_off; q.r1 = q.r0 + rl.n;
+    const size_t plane = (size_t)rl.pitch * rl.h;
+    q.r0 = r->planes + rl.plane_off + 3 * plane; q.r1 = r->planes + rl.plane_off + plane;
     q.rmask = r->sel_mask + rl.mask_off;
     q.rsel = r->sel_info + 2 * level;
     q.rtmpl = r->tmpl + rl.tmpl_off;
-    q.c0 = c->planes + cl.plane_off; q.c1 = q.c0 + cl.n; q.c2 = q.c1 + cl.n;
+    q.rrange = r->tile_range + rl.range_off;
+    q.c0 = c->planes + cl.plane_off; q.c3 = q.c0 + 2 * plane;
     q.cfx = cl.fx; q.cfy = cl.fy; q.cox = cl.ox; q.coy = cl.oy;
     // PointSelection::getMaximumNumberOfPoints (point_selection.cpp:68-71)
     q.max_valid_pixels = (long long)(size_t)((double)r->L[0].n * pow(0.25, (double)level));
   }
 }
 
-int upload_pair_levels(dvo_b200_ctx* ctx, int n, dvo_b200_pyramid* const* refs, dvo_b200_pyramid* const* curs, int level) {
-  size_t bytes = sizeof(PairLevel) * n;
-  int rc = ensure_stage(ctx, 0, bytes);
-  if (rc) return rc;
-  DVO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // previous use of the pinned stage has drained
-  fill_pair_levels((PairLevel*)ctx->h_stage, n, refs, curs, level);
-  DVO_CUDA(ctx, cudaMemcpyAsync(ctx->ws.d_pair_level, ctx->h_stage, bytes, cudaMemcpyHostToDevice, ctx->stream));
-  ctx->h2d_bytes += bytes;
+LevelLaunch make_level_launch(const LevelInfo& L, const dvo_b200_config* cfg, int li, int level) {
+  LevelLaunch lp;
+  lp.w = L.w; lp.h = L.h; lp.n = L.n; lp.pitch = L.pitch; lp.nbands = L.nbands; lp.nstrips = L.nstrips;
+  lp.level_index = li; lp.level_id = level; lp.max_iterations = cfg->max_iterations_per_level;
+  lp.first_level = li == 0; lp.use_initial_estimate = cfg->use_initial_estimate;
+  lp.precision = cfg->precision; lp.mu = cfg->mu;
+  return lp;
+}
+
+void add_need(ScratchNeed& need, const LevelInfo& L, const LevelPlan& pl) {
+  need.row_export_floats = std::max(need.row_export_floats, (size_t)pl.nsquads * L.h * kSegExportFloats);
+  need.row_base_ints = std::max(need.row_base_ints, (size_t)pl.nsquads * L.h);
+  need.cta_export_floats = std::max(need.cta_export_floats, (size_t)pl.nsquads * pl.g * kSegExportFloats);
+  need.cta_base_ints = std::max(need.cta_base_ints, (size_t)pl.nsquads * pl.g);
+  need.partial_floats = std::max(need.partial_floats, (size_t)pl.nsquads * pl.g * kNormalValues);
+  need.squads = std::max(need.squads, (size_t)pl.nsquads + 1);
+}
+
+// enqueue the persistent kernel of one level (squad states zeroed first); `tail` receives {queue head, error flag}
+int launch_level(dvo_b200_ctx* ctx, const LevelLaunch& lp, const LevelPlan& plan, int npairs, int max_log, float* dump, int li,
+                 int** tail_out) {
+  Workspace& ws = ctx->ws;
+  cudaStream_t st = ctx->stream;
+  // squad states, queue head and error flag (last SquadState slot) start at zero
+  DVO_CUDA(ctx, cudaMemsetAsync(ws.d_squads, 0, sizeof(SquadState) * (plan.nsquads + 1), st));
+  PersistentArgs pa;
+  pa.states = ws.d_state; pa.pls = ws.d_pair_level;
+  pa.row_exports = ws.d_row_exports; pa.row_base = ws.d_row_base; pa.cta_exports = ws.d_cta_exports; pa.cta_base = ws.d_cta_base;
+  pa.partial = ws.d_normal_partial;
+  pa.squads = reinterpret_cast<SquadState*>(ws.d_squads);
+  int* tail = reinterpret_cast<int*>(pa.squads + plan.nsquads);
+  pa.next_pair = tail; pa.error_flag = tail + 1;
+  pa.ilog = ws.d_iter_log; pa.max_log = max_log;
+  pa.dump = dump;
+  pa.dbg = ctx->d_dbg ? ctx->d_dbg + 16 * li : nullptr;
+  pa.npairs = npairs; pa.g = plan.g; pa.nsquads = plan.nsquads; pa.strips_per_cta = plan.strips_per_cta;
+  pa.lp = lp;
+  {
+    ProfScope prof(ctx, 0);
+    void* args[] = {&pa};
+    DVO_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)k_level_persistent, dim3(ctx->num_sms * ctx->ctas_per_sm),
+                                              dim3(kCtaThreads), args, kLevelSmemBytes, st));
+    ctx->launches++;
+  }
+  *tail_out = tail;
   return 0;
 }
 
@@ -848,25 +793,11 @@ int tracker_match_batch(dvo_b200_ctx* ctx, const dvo_b200_config* cfg, int n, dv
   Workspace& ws = ctx->ws;
   const int last = cfg->last_level, first = cfg->first_level;
   const int max_log = iter_stats ? max_iter_stats : 0;
-  // persistent grid geometry
-  if (ctx->num_sms == 0) {
-    cudaDeviceProp prop;
-    DVO_CUDA(ctx, cudaGetDeviceProperties(&prop, ctx->device));
-    ctx->num_sms = prop.multiProcessorCount;
-    int per_sm = 0;
-    DVO_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_level_persistent, kSegmentsPerTile * 32, 0));
-    if (per_sm < 1) return set_error(ctx, DVO_B200_ERR_CUDA, "persistent kernel does not fit on an SM");
-    ctx->ctas_per_sm = per_sm;
-  }
+  if ((rc = ensure_geometry(ctx))) return rc;
   ScratchNeed need;
   for (int level = first; level >= last; --level) {
-    const int nl = refs[0]->L[level].n;
-    LevelPlan pl = plan_level(nl, ctx->num_sms, ctx->ctas_per_sm, n);
-    need.record_floats = std::max(need.record_floats, (size_t)pl.nsquads * kRecordFloatsPerPixel * nl);
-    need.export_floats = std::max(need.export_floats, (size_t)pl.nsquads * pl.g * kCtaExportFloats);
-    need.segbase_ints = std::max(need.segbase_ints, (size_t)pl.nsquads * pl.g);
-    need.partial_floats = std::max(need.partial_floats, (size_t)pl.nsquads * pl.g * kNormalValues);
-    need.squads = std::max(need.squads, (size_t)pl.nsquads + 1);
+    const LevelInfo& L = refs[0]->L[level];
+    add_need(need, L, plan_level(L.nstrips, L.nbands, ctx->num_sms, ctx->ctas_per_sm, n));
   }
   rc = ensure_workspace(ctx, n, need, max_log);
   if (rc) return rc;
@@ -894,39 +825,18 @@ int tracker_match_batch(dvo_b200_ctx* ctx, const dvo_b200_config* cfg, int n, dv
   ctx->h2d_bytes += desc_bytes + init_bytes;
 
   for (int i = 0; i < 8; ++i) ws.h_active[i] = 0;
+  if (max_log > 0) DVO_CUDA(ctx, cudaMemsetAsync(ws.d_iter_log, 0, sizeof(dvo_b200_iteration_stats) * (size_t)n * max_log, st));
   for (int level = first, li = 0; level >= last; --level, ++li) {
     const LevelInfo& L = refs[0]->L[level];
-    LevelLaunch lp;
-    lp.w = L.w; lp.h = L.h; lp.n = L.n; lp.nseg = (L.n + kSegmentPixels - 1) / kSegmentPixels; lp.ntiles = (lp.nseg + kSegmentsPerTile - 1) / kSegmentsPerTile;
-    lp.wmagic = (unsigned)((1ull << 32) / (unsigned)L.w) + 1u;
-    lp.level_index = li; lp.level_id = level; lp.max_iterations = cfg->max_iterations_per_level;
-    lp.first_level = li == 0; lp.use_initial_estimate = cfg->use_initial_estimate;
-    lp.precision = cfg->precision; lp.mu = cfg->mu;
-    const LevelPlan plan = plan_level(L.n, ctx->num_sms, ctx->ctas_per_sm, n);
-    // squad states, queue head and error flag (last SquadState slot) start at zero
-    DVO_CUDA(ctx, cudaMemsetAsync(ws.d_squads, 0, sizeof(SquadState) * (plan.nsquads + 1), st));
+    const LevelLaunch lp = make_level_launch(L, cfg, li, level);
+    const LevelPlan plan = plan_level(L.nstrips, L.nbands, ctx->num_sms, ctx->ctas_per_sm, n);
     {
       ProfScope prof(ctx, 2);
       k_level_begin<<<(n + 63) / 64, 64, 0, st>>>(ws.d_state, h_desc + (size_t)li * n, ws.d_pair_level, d_Tinit, n, lp);
       ctx->launches++;
     }
-    PersistentArgs pa;
-    pa.states = ws.d_state; pa.pls = ws.d_pair_level; pa.records = ws.d_records; pa.seg_export = ws.d_scale_export;
-    pa.seg_base = ws.d_tile_base; pa.partial = ws.d_normal_partial;
-    pa.squads = reinterpret_cast<SquadState*>(ws.d_squads);
-    int* tail = reinterpret_cast<int*>(pa.squads + plan.nsquads);
-    pa.next_pair = tail; pa.error_flag = tail + 1;
-    pa.ilog = ws.d_iter_log; pa.max_log = max_log;
-    pa.dbg = ctx->d_dbg ? ctx->d_dbg + 8 * li : nullptr;
-    pa.npairs = n; pa.g = plan.g; pa.squads_per_slot = plan.squads_per_slot; pa.num_sms = ctx->num_sms; pa.rpw = plan.rpw;
-    pa.nseg = plan.nseg; pa.lp = lp;
-    {
-      ProfScope prof(ctx, 0);
-      void* args[] = {&pa};
-      DVO_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)k_level_persistent, dim3(ctx->num_sms * ctx->ctas_per_sm),
-                                                dim3(kSegmentsPerTile * 32), args, 0, st));
-      ctx->launches++;
-    }
+    int* tail = nullptr;
+    if ((rc = launch_level(ctx, lp, plan, n, max_log, nullptr, li, &tail))) return rc;
     DVO_CUDA(ctx, cudaMemcpyAsync(&ws.h_active[level_flag_slot(li)], tail + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
   }
   // results
@@ -942,6 +852,7 @@ int tracker_match_batch(dvo_b200_ctx* ctx, const dvo_b200_config* cfg, int n, dv
     ctx->launches++;
   }
   DVO_CUDA(ctx, cudaGetLastError());
+  ctx->pending_level_flags = first - last + 1;   // checked at the next synchronisation point (device-results variant)
   if (h_results) {
     size_t bytes = sizeof(dvo_b200_result) * n;
     if (bytes > ctx->h_results_bytes) {
@@ -959,12 +870,30 @@ int tracker_match_batch(dvo_b200_ctx* ctx, const dvo_b200_config* cfg, int n, dv
     DVO_CUDA(ctx, cudaStreamSynchronize(st));
     std::memcpy(h_results, ctx->h_results, bytes);
     ctx->d2h_bytes += bytes;
-    for (int li = 0; li <= first - last && li < 8; ++li)
-      if (ws.h_active[li] != 0) return set_error(ctx, DVO_B200_ERR_CUDA, "persistent level kernel: squad barrier timed out");
+    return check_level_flags(ctx);
   }
   return 0;
 }
 
+// The persistent kernels report a barrier / transaction timeout through a flag copied to pinned memory after every level.
+// Call after the stream has been synchronised.
+int check_level_flags(dvo_b200_ctx* ctx) {
+  Workspace& ws = ctx->ws;
+  const int nl = ctx->pending_level_flags;
+  ctx->pending_level_flags = 0;
+  if (!ws.h_active) return 0;
+  for (int li = 0; li < nl && li < 8; ++li)
+    if (ws.h_active[li] != 0) {
+      const int code = ws.h_active[li];
+      ws.h_active[li] = 0;
+      return set_error(ctx, DVO_B200_ERR_CUDA, code == 2 ? "persistent level kernel: bulk-copy transaction timed out"
+                                                         : "persistent level kernel: squad barrier timed out");
+    }
+  return 0;
+}
+
+// Test hooks (dvo_b200_residual_image, dvo_b200_linearize): ONE Gauss-Newton iteration of the level kernel for one
+// pair at a fixed transform: stage A, P_k, stage B (optionally dumping the residual records), end step.
 int tracker_linearize(dvo_b200_ctx* ctx, const dvo_b200_config* cfg, dvo_b200_pyramid* ref, dvo_b200_pyramid* cur,
                       int level, const double* T, int use_weights, const float* prev_precision, int64_t* count,
                       float* precision_out, float* ll_out, double* A_out, double* b_out, float* planes7) {
@@ -978,72 +907,53 @@ int tracker_linearize(dvo_b200_ctx* ctx, const dvo_b200_config* cfg, dvo_b200_py
   cudaStream_t st = ctx->stream;
   Workspace& ws = ctx->ws;
   const LevelInfo& L = ref->L[level];
+  if ((rc = ensure_geometry(ctx))) return rc;
+  const LevelPlan plan = plan_level(L.nstrips, L.nbands, ctx->num_sms, ctx->ctas_per_sm, 1);
   {
-    const size_t nseg = (L.n + kSegmentPixels - 1) / kSegmentPixels;
     ScratchNeed need;
-    need.record_floats = (size_t)kRecordFloatsPerPixel * L.n;
-    need.export_floats = nseg * kCtaExportFloats;
-    need.segbase_ints = nseg;
-    need.partial_floats = nseg * kNormalValues;
-    need.squads = 2;
+    add_need(need, L, plan);
+    if (planes7) need.dump_floats = 7 * (size_t)L.n;
     if ((rc = ensure_workspace(ctx, 1, need, 0))) return rc;
   }
   if ((rc = pyramid_reselect(ctx, ref, cfg->intensity_derivative_threshold, cfg->depth_derivative_threshold))) return rc;
-  LevelLaunch lp;
-  lp.w = L.w; lp.h = L.h; lp.n = L.n; lp.nseg = (L.n + kSegmentPixels - 1) / kSegmentPixels; lp.ntiles = (lp.nseg + kSegmentsPerTile - 1) / kSegmentsPerTile;
-    lp.wmagic = (unsigned)((1ull << 32) / (unsigned)L.w) + 1u;
-  lp.level_index = 0; lp.level_id = level; lp.max_iterations = 1 << 30; lp.first_level = 1;
-  lp.use_initial_estimate = 0; lp.precision = 0.0; lp.mu = 0.0;
-  if ((rc = upload_pair_levels(ctx, 1, refs, curs, level))) return rc;
-  if ((rc = ensure_stage(ctx, 1024, 1024))) return rc;
+  LevelLaunch lp = make_level_launch(L, &c, 0, level);
+  lp.max_iterations = use_weights ? 2 : 1;    // k_set_state starts at iteration 1 / 0: exactly one iteration runs
+  lp.first_level = 1; lp.use_initial_estimate = 0; lp.precision = 0.0; lp.mu = 0.0;
+  if ((rc = ensure_stage(ctx, 1024, sizeof(PairLevel) + 1024))) return rc;
+  DVO_CUDA(ctx, cudaStreamSynchronize(st));
+  fill_pair_levels((PairLevel*)ctx->h_stage, 1, refs, curs, level);
+  DVO_CUDA(ctx, cudaMemcpyAsync(ws.d_pair_level, ctx->h_stage, sizeof(PairLevel), cudaMemcpyHostToDevice, st));
   DVO_CUDA(ctx, cudaStreamSynchronize(st));
   std::memcpy(ctx->h_stage, T, sizeof(double) * 16);
   float pp[4] = {0, 0, 0, 0};
   if (use_weights && prev_precision) std::memcpy(pp, prev_precision, sizeof(pp));
   std::memcpy((char*)ctx->h_stage + 128, pp, sizeof(pp));
   DVO_CUDA(ctx, cudaMemcpyAsync(ctx->d_stage, ctx->h_stage, 256, cudaMemcpyHostToDevice, st));
-  ws.h_active[0] = 1;
-  DVO_CUDA(ctx, cudaMemcpyAsync(ws.d_active, ws.h_active, sizeof(int), cudaMemcpyHostToDevice, st));
+  ctx->h2d_bytes += sizeof(PairLevel) + 256;
   k_set_state<<<1, 1, 0, st>>>(ws.d_state, ws.d_pair_level, (const double*)ctx->d_stage,
                                (const float*)((char*)ctx->d_stage + 128), use_weights, lp);
-  dim3 grid(lp.ntiles, 1);
-  k_residual<<<grid, kSegmentsPerTile * 32, 0, st>>>(ws.d_state, ws.d_pair_level, ws.d_records, ws.d_scale_export, lp);
-  k_pair_mid<<<1, 32, 0, st>>>(ws.d_state, ws.d_scale_export, ws.d_tile_base, lp.ntiles, ws.d_active, lp, nullptr, 0);
-  ctx->launches += 3;
-  if (!planes7) {
-    k_normal<<<grid, kSegmentsPerTile * 32, 0, st>>>(ws.d_state, ws.d_pair_level, ws.d_records, ws.d_scale_export, ws.d_tile_base,
-                                                     ws.d_normal_partial, lp);
-    k_pair_end<<<1, kSegmentsPerTile * 32, 0, st>>>(ws.d_state, ws.d_pair_level, ws.d_normal_partial, lp.ntiles, ws.d_active, lp, nullptr, 0);
-    ctx->launches += 2;
-  }
+  ctx->launches += 1;
+  int* tail = nullptr;
+  ws.h_active[0] = 0;
+  if ((rc = launch_level(ctx, lp, plan, 1, 0, planes7 ? ws.d_dump : nullptr, 0, &tail))) return rc;
+  DVO_CUDA(ctx, cudaMemcpyAsync(&ws.h_active[0], tail + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
   DVO_CUDA(ctx, cudaGetLastError());
   PairState* hs = nullptr;
   if ((rc = ensure_stage(ctx, 0, sizeof(PairState) + 64))) return rc;
   hs = (PairState*)ctx->h_stage;
   DVO_CUDA(ctx, cudaMemcpyAsync(hs, ws.d_state, sizeof(PairState), cudaMemcpyDeviceToHost, st));
   DVO_CUDA(ctx, cudaStreamSynchronize(st));
+  ctx->pending_level_flags = 1;
+  if ((rc = check_level_flags(ctx))) return rc;
   if (count) *count = hs->n;
   if (precision_out) std::memcpy(precision_out, hs->precision, sizeof(float) * 4);
   if (ll_out) *ll_out = hs->ll;
   if (A_out) std::memcpy(A_out, hs->A, sizeof(double) * 36);
   if (b_out) std::memcpy(b_out, hs->b, sizeof(double) * 6);
   if (planes7) {
-    // records: 6 planes + weight; return {ei, ez, gx, gy, hx, hy, z_ref}; invalid -> NaN in every plane
-    size_t N = L.n;
-    std::vector<float> rec(7 * N), p0(2 * N);
-    DVO_CUDA(ctx, cudaMemcpy(rec.data(), ws.d_records, sizeof(float) * 7 * N, cudaMemcpyDeviceToHost));
-    DVO_CUDA(ctx, cudaMemcpy(p0.data(), ref->planes + L.plane_off, sizeof(float) * 2 * N, cudaMemcpyDeviceToHost));
-    ctx->d2h_bytes += sizeof(float) * 9 * N;
-    const float nanv = std::numeric_limits<float>::quiet_NaN();
-    // scratch layout: float2 planes E = (e.i, e.z), G = (e.idx, e.idy), H = (e.zdx, e.zdy), then W
-    for (size_t i = 0; i < N; ++i) {
-      bool valid = rec[2 * i] == rec[2 * i];
-      for (int pl = 0; pl < 3; ++pl) {
-        planes7[(2 * pl) * N + i] = valid ? rec[pl * 2 * N + 2 * i] : nanv;
-        planes7[(2 * pl + 1) * N + i] = valid ? rec[pl * 2 * N + 2 * i + 1] : nanv;
-      }
-      planes7[6 * N + i] = valid ? p0[2 * i + 1] : nanv;
-    }
+    // {ei, ez, gx, gy, hx, hy, z_ref}; invalid -> NaN in every plane
+    DVO_CUDA(ctx, cudaMemcpy(planes7, ws.d_dump, sizeof(float) * 7 * (size_t)L.n, cudaMemcpyDeviceToHost));
+    ctx->d2h_bytes += sizeof(float) * 7 * (size_t)L.n;
   }
   return 0;
 }

@@ -1,7 +1,8 @@
 """ctypes binding of oracle/liboracle.so -- TEST INFRASTRUCTURE ONLY (see oracle/dvo_oracle.h).
 
 May be imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
-legs; never by the product package dvo_slam_b200/.  PARITY UNPINNED (no reference goldens exist).
+legs; never by the product package dvo_slam_b200/.  The reference ships no goldens; the FAITHFUL mode is pinned,
+bit for bit, against the reference's own SSE translation units compiled into oracle/_ref (tests/test_reference_pin.py).
 """
 from __future__ import annotations
 
@@ -239,3 +240,52 @@ def convert_raw_depth(raw_u16, scale):
     out = np.empty(raw.shape, dtype=np.float32)
     lib().orc_convert_raw_depth(raw.ctypes.data_as(C.POINTER(C.c_uint16)), _fptr(out), raw.size, scale)
     return out
+
+
+# ---- oracle/_ref: the reference's own SSE translation units (see oracle/Makefile, oracle/ref_driver.cpp) ----------
+_REF_DIR = os.path.join(_HERE, "_ref")
+_ref = {}
+
+
+def ref_available(variant: str = "") -> bool:
+    return os.path.exists(os.path.join(_REF_DIR, f"libdvo_ref{variant}.so"))
+
+
+def ref_lib(variant: str = ""):
+    """libdvo_ref.so = /root/reference/dvo_core/src/{dense_tracking_impl,core/math_sse,core/intrinsic_matrix}.cpp compiled
+    unmodified + ref_driver.cpp (-O2; variant "_O3" = the reference's own optimisation level).  Built by `make -C oracle ref`
+    where /root/reference exists; the built files travel."""
+    if variant not in _ref:
+        L = C.CDLL(os.path.join(_REF_DIR, f"libdvo_ref{variant}.so"))
+        fp, dp = C.POINTER(C.c_float), C.POINTER(C.c_double)
+        L.ref_linearize.restype = C.c_int64
+        L.ref_linearize.argtypes = [fp, fp, C.c_int, C.c_int, fp, dp, C.c_float, C.c_float, C.c_int, fp, C.POINTER(C.c_int64), fp,
+                                    C.POINTER(C.c_int32), fp, fp, fp, fp, fp, fp]
+        _ref[variant] = L
+    return _ref[variant]
+
+
+def ref_linearize(ref_planes6, cur_planes6, K, T, use_weights=False, prev_precision=None, ti=0.0, td=0.0, variant=""):
+    """One Gauss-Newton linearisation computed by the reference's own object code.  planes6: (6, h, w) float32."""
+    rp = np.ascontiguousarray(ref_planes6, dtype=np.float32)
+    cp = np.ascontiguousarray(cur_planes6, dtype=np.float32)
+    _, h, w = rp.shape
+    N = h * w
+    K4 = np.ascontiguousarray(np.asarray(K, dtype=np.float32))
+    T = np.ascontiguousarray(np.asarray(T, dtype=np.float64).reshape(16))
+    pp = np.ascontiguousarray(np.asarray(prev_precision if prev_precision is not None else np.zeros(4), dtype=np.float32).reshape(4))
+    nsel = C.c_int64()
+    res = np.zeros((N, 2), dtype=np.float32)
+    idx = np.zeros(N, dtype=np.int32)
+    rec = np.zeros((N, 12), dtype=np.float32)
+    wts = np.zeros(N, dtype=np.float32)
+    P = np.zeros(4, dtype=np.float32)
+    ll = C.c_float()
+    A = np.zeros(36, dtype=np.float32)
+    b = np.zeros(6, dtype=np.float32)
+    n = ref_lib(variant).ref_linearize(_fptr(rp), _fptr(cp), w, h, _fptr(K4), _dptr(T), ti, td, int(use_weights), _fptr(pp), C.byref(nsel),
+                                _fptr(res), idx.ctypes.data_as(C.POINTER(C.c_int32)), _fptr(rec), _fptr(wts), _fptr(P), C.byref(ll),
+                                _fptr(A), _fptr(b))
+    n = int(n)
+    return {"n": n, "n_selected": int(nsel.value), "residuals": res[:n], "index": idx[:n], "records": rec[:n], "weights": wts[:n],
+            "precision": P.reshape(2, 2), "ll": ll.value, "A": A.reshape(6, 6), "b": b}

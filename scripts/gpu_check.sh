@@ -1,0 +1,11 @@
+#!/bin/bash
+# one GPU call: parity tests (fail fast), then a short bench; everything lands in gpurun_out/
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv > gpurun_out/smi.txt 2>&1
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1
+echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
+tail -30 gpurun_out/pytest_gpu.log
+if [ "$1" = "bench" ]; then
+  timeout 600 python bench.py > gpurun_out/bench_dev.json 2> gpurun_out/bench_dev.err
+  echo "bench exit $?"; cat gpurun_out/bench_dev.json; tail -5 gpurun_out/bench_dev.err
+fi
