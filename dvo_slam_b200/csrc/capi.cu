@@ -105,8 +105,9 @@ int dvo_b200_create(int device, void* stream, dvo_b200_ctx** out) {
     ctx->own_stream = true;
   }
   if (getenv("DVO_B200_TIMING")) {
-    cudaMalloc((void**)&ctx->d_dbg, sizeof(unsigned long long) * 128);
-    cudaMemset(ctx->d_dbg, 0, sizeof(unsigned long long) * 128);
+    cudaMalloc((void**)&ctx->d_dbg, sizeof(unsigned long long) * 192);
+    cudaMemset(ctx->d_dbg, 0, sizeof(unsigned long long) * 192);
+    for (int l = 0; l < 8; ++l) { unsigned long long big = ~0ull; cudaMemcpy(ctx->d_dbg + 128 + 8 * l + 6, &big, 8, cudaMemcpyHostToDevice); }
   }
   *out = ctx;
   return 0;
@@ -353,7 +354,7 @@ int dvo_b200_profile_read(dvo_b200_ctx* ctx, double ms_out[8], int64_t launches_
   cudaSetDevice(ctx->device);
   drain_profile(ctx);
   if (ctx->d_dbg) {   // developer timing dump (DVO_B200_TIMING=1)
-    unsigned long long h[128];
+    unsigned long long h[192];
     cudaStreamSynchronize(ctx->stream);
     cudaMemcpy(h, ctx->d_dbg, sizeof(h), cudaMemcpyDeviceToHost);
     static const char* names[8] = {"stageA", "stageB", "waitA", "waitB", "mid", "end", "queue", "total"};
@@ -366,12 +367,25 @@ int dvo_b200_profile_read(dvo_b200_ctx* ctx, double ms_out[8], int64_t launches_
       fprintf(stderr, "[dvo_b200 timing]   consumer warp 0: wait-full %.1f%% of stage A, %.1f%% of stage B; producer: descriptor %.1f%%, "
                       "wait-empty %.1f%% of its stage time\n", 100.0 * (double)v[9] / (double)(v[8] + 1), 100.0 * (double)v[11] / (double)(v[10] + 1),
               100.0 * (double)v[12] / (double)(v[14] + v[15] + 1), 100.0 * (double)v[13] / (double)(v[14] + v[15] + 1));
+      const unsigned long long* u = h + 128 + 8 * l;
+      if (u[0]) fprintf(stderr, "[dvo_b200 timing]   tiles %llu (inexact %.2f%%, skipped %.2f%%), stage-B rounds of inexact tiles %.2f%%; CTA lifetime of the last launch-set: "
+                                "max %.3f ms, min %.3f ms\n", u[0], 100.0 * (double)u[1] / (double)u[0], 100.0 * (double)u[2] / (double)u[0],
+                        100.0 * (double)u[4] / (double)(u[3] + 1), (double)u[5] * 1e-6, (double)u[6] * 1e-6);
     }
-    if (reset) cudaMemset(ctx->d_dbg, 0, sizeof(h));
+    if (reset) {
+      cudaMemset(ctx->d_dbg, 0, sizeof(h));
+      for (int l = 0; l < 8; ++l) { unsigned long long big = ~0ull; cudaMemcpy(ctx->d_dbg + 128 + 8 * l + 6, &big, 8, cudaMemcpyHostToDevice); }
+    }
   }
-  for (int i = 0; i < 8; ++i) {
-    if (ms_out) ms_out[i] = ctx->prof_ms[i];
-    if (launches_out) launches_out[i] = ctx->prof_launches[i];
+  if (getenv("DVO_B200_TIMING")) {   // developer: device time of the level kernels, per level of the match (coarse -> fine)
+    fprintf(stderr, "[dvo_b200 timing] level kernels, ms per launch:");
+    for (int i = 8; i < 16; ++i)
+      if (ctx->prof_launches[i]) fprintf(stderr, " %.3f", ctx->prof_ms[i] / (double)ctx->prof_launches[i]);
+    fprintf(stderr, "\n");
+  }
+  for (int i = 0; i < 16; ++i) {
+    if (i < 8 && ms_out) ms_out[i] = ctx->prof_ms[i];
+    if (i < 8 && launches_out) launches_out[i] = ctx->prof_launches[i];
     if (reset) { ctx->prof_ms[i] = 0; ctx->prof_launches[i] = 0; }
   }
   return 0;

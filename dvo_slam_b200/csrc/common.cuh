@@ -174,8 +174,8 @@ struct dvo_b200_ctx {
   void* h_results = nullptr; size_t h_results_bytes = 0;  // pinned
   // profiling
   bool profile = false;
-  double prof_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  int64_t prof_launches[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  double prof_ms[16] = {0};           // classes 0..7 (dvo_b200_profile_read); 8 + i: level kernel of the i-th level of a match
+  int64_t prof_launches[16] = {0};
   std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> prof_pending;
   std::vector<cudaEvent_t> event_pool;
   std::mutex mu;

@@ -294,7 +294,7 @@ int pyramid_build_batch(dvo_b200_ctx* ctx, int n, const float* d_I, const float*
     q.nstrips = (q.h + kTileH - 1) / kTileH;
     q.plane_off = plane_f2; plane_f2 += 4 * (size_t)q.pitch * q.h;
     q.mask_off = mask_words; mask_words += q.words;
-    q.tmpl_off = tmpl_floats; tmpl_floats += q.w + q.h;
+    q.tmpl_off = tmpl_floats; tmpl_floats += (size_t)((q.w + q.h + 3) & ~3);   // every level's tx[] starts 16-byte aligned (bulk copies)
     q.range_off = range_f2; range_f2 += (size_t)q.nbands * q.nstrips;
   }
   plane_f2 = align_up(plane_f2, 32);          // keep every image 256-byte aligned

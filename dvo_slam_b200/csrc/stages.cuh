@@ -103,6 +103,11 @@ __device__ __forceinline__ f2 lds_f2(unsigned addr) {
   asm volatile("ld.shared.b64 %0, [%1+%2];" : "=l"(v) : "r"(addr), "n"(kOff));
   return v;
 }
+__device__ __forceinline__ float lds_f32(unsigned addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ f2 lds_f2_at(unsigned addr) {
   f2 v;
   asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(addr));
@@ -117,17 +122,20 @@ template <typename T>
 __device__ __forceinline__ const T* pin(const T* p) { asm volatile("" : "+l"(p)); return p; }
 
 // ---- shared-memory stage buffers -----------------------------------------------------------------------
-struct TileDesc {          // written by the producer before it arms the full barrier of the stage
+struct __align__(16) TileDesc {   // written by the producer before it arms the full barrier of the stage
   int skip;                // 1: no pixel of the tile can be valid (no reference depth, or the window misses the image)
-  int bx0, row_lo;         // image column of window column 0; (virtual, -1 .. h) image row of window row 0
+  int origin;              // (row_lo * kWinCols + bx0) * 8: byte offset of image pixel (0, 0) relative to win[0][0], negated by the
+                           // consumer; row_lo is the (virtual, -1 .. h) image row of window row 0, bx0 the column of window column 0
   int ulo, ucount;         // a tap (u0, v0) is served by the window iff (unsigned)(u0 - ulo) < ucount
   int vlo, vcount;         //                                       and (unsigned)(v0 - vlo) < vcount
+  int exact;               // 1: the window holds the whole bounding box of the tile's taps -- no in-bounds tap can miss it
   int pad_;
 };
 struct __align__(128) StageBuf {
-  float2 ref0[kTileH][kTileW];       // reference P0 rows of the tile
-  float2 ref1[kTileH][kTileW];       // reference P1 rows (stage B)
-  float2 win[kWinRows][kWinCols];    // window of the current image (P0 in stage A, P3 in stage B)
+  float2 ref0[kTileH][kTileW];       // reference P3 rows of the tile: (I, Zsel)
+  float2 ref1[kTileH][kTileW];       // reference P1 rows (stage B): (Ix, Iy)
+  float2 win[kWinRows][kWinCols];    // window of the current image (P0 in stage A, P2 in stage B)
+  float tx[kTileW];                  // point-cloud template of the band's columns
 };
 struct TilePipe {
   StageBuf buf[kStages];
@@ -135,11 +143,21 @@ struct TilePipe {
   TileDesc desc[kStages];
 };
 
-// developer timing (DVO_B200_TIMING=1): cycles one warp of the CTA spends waiting on the pipeline
+// developer timing (build with -DDVO_PIPE_TIMING, run with DVO_B200_TIMING=1): cycles one warp of the CTA spends
+// waiting on the pipeline.  Compiled out of the product build.
+#ifdef DVO_PIPE_TIMING
 struct PipeTiming {
   unsigned long long wait_full_a = 0, wait_full_b = 0, wait_empty = 0, produce = 0, rounds_a = 0, rounds_b = 0;
+  unsigned long long tiles = 0, tiles_inexact = 0, tiles_skipped = 0, slow_rounds = 0, rounds = 0;
   bool on = false;
 };
+#define DVO_CLOCK(tm) ((tm).on ? clock64() : 0)
+#define DVO_ADD(tm, field, v) do { if ((tm).on) (tm).field += (v); } while (0)
+#else
+struct PipeTiming {};
+#define DVO_CLOCK(tm) 0ll
+#define DVO_ADD(tm, field, v) do { } while (0)
+#endif
 
 // geometry of one pyramid level and this CTA's share of it
 struct LevelGeom {
@@ -188,7 +206,7 @@ __device__ __noinline__ void produce_tile(TilePipe& tp, const PairLevel& pl, con
   const int lane = threadIdx.x & 31;
   const float2* cur = kStageB ? pl.c3 : pl.c0;
   const int bufi = t % kStages;
-  const long long tp0 = tm.on ? clock64() : 0;
+  const long long tp0 = DVO_CLOCK(tm);
   StageBuf& sb = tp.buf[bufi];
   const int y0 = s * kTileH, rows = min(kTileH, g.h - y0);
   const int x0 = b * kTileW, bw = min(kTileW, g.w - x0);
@@ -196,8 +214,8 @@ __device__ __noinline__ void produce_tile(TilePipe& tp, const PairLevel& pl, con
   // ---- window of the current image: corner rays x {zmin, zmax} (lane & 7 selects the corner) ----
   const float2 zr = __ldg(pl.rrange + (size_t)s * g.nbands + b);
   TileDesc d;
-  d.skip = 0; d.bx0 = 0; d.row_lo = 0; d.ulo = 0; d.ucount = 0; d.vlo = 0; d.vcount = 0; d.pad_ = 0;
-  int ncols = 0, nrows = 0;
+  d.skip = 0; d.origin = 0; d.ulo = 0; d.ucount = 0; d.vlo = 0; d.vcount = 0; d.exact = 0; d.pad_ = 0;
+  int ncols = 0, nrows = 0, win_bx0 = 0, win_row_lo = 0;
   if (!(zr.x <= zr.y)) {
     d.skip = 1;                       // no non-NaN reference depth: nothing is selected in this tile
   } else {
@@ -227,12 +245,15 @@ __device__ __noinline__ void produce_tile(TilePipe& tp, const PairLevel& pl, con
       int row_lo = max((int)floorf(vmin) - 2, -1), row_hi = min((int)floorf(vmax) + 3, g.h);
       int bx0 = col_lo & ~1;
       ncols = (col_hi + 2 - bx0) & ~1;              // even count covering [bx0, col_hi]
-      if (ncols > kWinCols) { bx0 += ((ncols - kWinCols) / 2) & ~1; ncols = kWinCols; }
+      bool whole = true;
+      if (ncols > kWinCols) { bx0 += ((ncols - kWinCols) / 2) & ~1; ncols = kWinCols; whole = false; }
       nrows = row_hi - row_lo + 1;
-      if (nrows > kWinRows) { row_lo += (nrows - kWinRows) / 2; nrows = kWinRows; }
+      if (nrows > kWinRows) { row_lo += (nrows - kWinRows) / 2; nrows = kWinRows; whole = false; }
       if (ncols < 4 || nrows < 4) { ncols = 0; nrows = 0; }
       else {
-        d.bx0 = bx0; d.row_lo = row_lo;
+        d.exact = whole ? 1 : 0;
+        win_bx0 = bx0; win_row_lo = row_lo;
+        d.origin = (row_lo * kWinCols + bx0) * 8;
         // columns are clamped per tap (max(u0-1, 0), min(u0+2, w-1)); rows -1 and h are staged as replicas
         d.ulo = bx0 == 0 ? 0 : bx0 + 1;
         const int uhi = (bx0 + ncols - 1 >= g.w - 1) ? g.w - 2 : bx0 + ncols - 3;
@@ -243,11 +264,13 @@ __device__ __noinline__ void produce_tile(TilePipe& tp, const PairLevel& pl, con
     }
   }
   const unsigned win_row_bytes = (unsigned)ncols * 8u;
-  const unsigned total = d.skip ? 0u : (unsigned)rows * ref_row_bytes * (kStageB ? 2u : 1u) + (unsigned)nrows * win_row_bytes;
+  const unsigned tx_bytes = (unsigned)((bw + 3) & ~3) * 4u;
+  const unsigned total = d.skip ? 0u : (unsigned)rows * ref_row_bytes * (kStageB ? 2u : 1u) + (unsigned)nrows * win_row_bytes + tx_bytes;
   // the descriptor is ready: now wait until the consumers have released the buffer's previous tile
-  const long long tp1 = tm.on ? clock64() : 0;
+  const long long tp1 = DVO_CLOCK(tm);
   mbar_wait(&tp.empty[bufi], ((t / kStages) & 1u) ^ 1u, error_flag);
-  if (tm.on) { const long long tp2 = clock64(); tm.produce += tp1 - tp0; tm.wait_empty += tp2 - tp1; }
+  DVO_ADD(tm, produce, tp1 - tp0); DVO_ADD(tm, wait_empty, DVO_CLOCK(tm) - tp1);
+  DVO_ADD(tm, tiles, 1); DVO_ADD(tm, tiles_inexact, (!d.skip && !d.exact) ? 1 : 0); DVO_ADD(tm, tiles_skipped, d.skip ? 1 : 0);
   if (lane == 0) {
     tp.desc[bufi] = d;
     if (total) mbar_arrive_expect_tx(&tp.full[bufi], total);
@@ -261,9 +284,10 @@ __device__ __noinline__ void produce_tile(TilePipe& tp, const PairLevel& pl, con
       if (kStageB) bulk_g2s(&sb.ref1[lane][0], pl.r1 + off, ref_row_bytes, &tp.full[bufi]);
     }
     if (lane < nrows) {
-      const int yy = min(max(d.row_lo + lane, 0), g.h - 1);
-      bulk_g2s(&sb.win[lane][0], cur + (size_t)yy * g.pitch + d.bx0, win_row_bytes, &tp.full[bufi]);
+      const int yy = min(max(win_row_lo + lane, 0), g.h - 1);
+      bulk_g2s(&sb.win[lane][0], cur + (size_t)yy * g.pitch + win_bx0, win_row_bytes, &tp.full[bufi]);
     }
+    if (lane == 31) bulk_g2s(&sb.tx[0], pl.rtmpl + x0, tx_bytes, &tp.full[bufi]);
   }
 }
 
@@ -309,6 +333,7 @@ __device__ __forceinline__ f2 ld_f2(const float2* p) { const float2 v = *p; retu
 
 // the staged window as one warp sees it during one tile
 struct WinView {
+  bool exact;                // no in-bounds tap of this tile can miss the window: skip the per-pixel test
   unsigned base;             // shared address of win[0][0] minus (row_lo * kWinCols + bx0) * 8: index with image coordinates
   unsigned safe;             // shared address of win[1][1]: where rejected points read
   const float2* plane;       // the same plane in global memory, for taps the window does not hold
@@ -351,9 +376,13 @@ __device__ __forceinline__ float depth_sigma(float z) {
 // Stage A pixel: (e.i, e.z) and validity from the four taps of (I, Z').
 __device__ __forceinline__ bool residual_pixel(const PixelProjection& p, const WinView& wv, float Ir, float z, const StageConsts& c,
                                                float& ei, float& ez) {
-  const bool hit = (unsigned)(p.u0 - wv.ulo) < (unsigned)wv.ucount && (unsigned)(p.v0 - wv.vlo) < (unsigned)wv.vcount;
+  bool hit = true, any_miss = false;
+  if (!wv.exact) {   // warp-uniform
+    hit = (unsigned)(p.u0 - wv.ulo) < (unsigned)wv.ucount && (unsigned)(p.v0 - wv.vlo) < (unsigned)wv.vcount;
+    any_miss = __any_sync(kFullMask, p.inb && !hit);
+  }
   f2 c00, c10, c01, c11;
-  if (!__any_sync(kFullMask, p.inb && !hit)) {
+  if (!any_miss) {
     const unsigned a = p.inb ? wv.base + (unsigned)(p.v0 * kWinCols + p.u0) * 8u : wv.safe;
     c00 = lds_f2<0>(a); c10 = lds_f2<8>(a); c01 = lds_f2<kWinRowBytes>(a); c11 = lds_f2<kWinRowBytes + 8>(a);
   } else {
@@ -373,9 +402,13 @@ __device__ __forceinline__ bool residual_pixel(const PixelProjection& p, const W
 // rows above and below it.
 __device__ __forceinline__ bool record_pixel(const PixelProjection& p, const WinView& wv, float Ir, float z, f2 gref,
                                              const StageConsts& c, f2& E, f2& G, f2& H) {
-  const bool hit = (unsigned)(p.u0 - wv.ulo) < (unsigned)wv.ucount && (unsigned)(p.v0 - wv.vlo) < (unsigned)wv.vcount;
+  bool hit = true, any_miss = false;
+  if (!wv.exact) {   // warp-uniform
+    hit = (unsigned)(p.u0 - wv.ulo) < (unsigned)wv.ucount && (unsigned)(p.v0 - wv.vlo) < (unsigned)wv.vcount;
+    any_miss = __any_sync(kFullMask, p.inb && !hit);
+  }
   Taps12 t;
-  if (!__any_sync(kFullMask, p.inb && !hit)) {
+  if (!any_miss) {
     const unsigned a = p.inb ? wv.base + (unsigned)(p.v0 * kWinCols + p.u0) * 8u : wv.safe;
     t.c00 = lds_f2<0>(a); t.c10 = lds_f2<8>(a); t.c01 = lds_f2<kWinRowBytes>(a); t.c11 = lds_f2<kWinRowBytes + 8>(a);
     t.t0 = lds_f2<-kWinRowBytes>(a); t.t1 = lds_f2<-kWinRowBytes + 8>(a);
@@ -526,19 +559,30 @@ __device__ __forceinline__ void scale_state_init(ScaleState& s) {
 __device__ __forceinline__ void scale_round32(ScaleState& st, int lane, unsigned lt_mask, bool v, float w, float ei, float ez) {
   const unsigned m = __ballot_sync(kFullMask, v);
   if (m == 0u) return;
-  const float w_first = __shfl_sync(kFullMask, w, __ffs(m) - 1);   // first valid weight of the round
+  float w_first, wn, xi, xz;
+  bool next;
+  int sg;
+  if (m == kFullMask) {   // the common round: every point valid, the next valid point is the next lane
+    w_first = __shfl_sync(kFullMask, w, 0);
+    wn = __shfl_down_sync(kFullMask, w, 1);
+    next = lane != 31;
+    sg = (int)((unsigned)(st.cnt + lane) << 31);
+    xi = ei; xz = ez;
+  } else {
+    w_first = __shfl_sync(kFullMask, w, __ffs(m) - 1);              // first valid weight of the round
+    const unsigned above = (m >> lane) >> 1;
+    wn = __shfl_sync(kFullMask, w, above ? lane + __ffs(above) : lane);
+    next = above != 0u;
+    sg = (int)((unsigned)(st.cnt + __popc(m & lt_mask)) << 31);     // sign bit set for odd rank
+    // rejected points carry garbage (possibly NaN) residuals: zero them so that 0 * outer stays 0
+    xi = v ? ei : 0.f; xz = v ? ez : 0.f;
+  }
   if (st.cnt == 0) st.wfirst = w_first;
   {   // the pending leader of an earlier round pairs with the first valid point of this round
     const float s = st.pend ? st.pw + w_first : 0.f;
     const f2 ss = pk(s, __int_as_float(__float_as_int(s) ^ st.psign));
     st.acc0 = fma2(ss, bc(st.po0), st.acc0); st.acc1 = fma2(ss, bc(st.po1), st.acc1); st.acc2 = fma2(ss, bc(st.po2), st.acc2);
   }
-  const unsigned above = (m >> lane) >> 1;
-  const float wn = __shfl_sync(kFullMask, w, above ? lane + __ffs(above) : lane);
-  const bool next = above != 0u;
-  const int sg = ((st.cnt + __popc(m & lt_mask)) & 1) << 31;          // sign bit set for odd rank
-  // rejected points carry garbage (possibly NaN) residuals: zero them so that 0 * outer stays 0
-  const float xi = v ? ei : 0.f, xz = v ? ez : 0.f;
   const float a0 = xi * xi, a1 = xi * xz, a2 = xz * xz;
   const float s = (v && next) ? w + wn : 0.f;
   const f2 ss = pk(s, __int_as_float(__float_as_int(s) ^ sg));
@@ -577,9 +621,10 @@ __device__ __forceinline__ void scale_state_export(ScaleState& st, int lane, flo
 __device__ __forceinline__ WinView make_view(const StageBuf& sb, const TileDesc& d, const float2* plane, const LevelGeom& g) {
   WinView wv;
   const unsigned w0 = smem_u32(&sb.win[0][0]);
-  wv.base = pin(w0 - (unsigned)((d.row_lo * kWinCols + d.bx0) * 8));
+  wv.base = pin(w0 - (unsigned)d.origin);
   wv.safe = pin(w0 + (unsigned)((kWinCols + 1) * 8));
   wv.plane = plane;
+  wv.exact = d.exact != 0;
   wv.ulo = d.ulo; wv.ucount = d.ucount; wv.vlo = d.vlo; wv.vcount = d.vcount;
   wv.w = g.w; wv.h = g.h; wv.pitch = g.pitch;
   return wv;
@@ -611,9 +656,9 @@ __device__ __forceinline__ void stage_a_run(TilePipe& tp, const PairLevel& pl, c
     for (int b = 0; b < g.nbands; ++b, ++i) {
       const unsigned t = tbase + i;
       const int bufi = t % kStages;
-      const long long tw0 = tm.on ? clock64() : 0;
+      const long long tw0 = DVO_CLOCK(tm);
       mbar_wait(&tp.full[bufi], (t / kStages) & 1u, error_flag);
-      if (tm.on) tm.wait_full_a += clock64() - tw0;
+      DVO_ADD(tm, wait_full_a, DVO_CLOCK(tm) - tw0);
       const StageBuf& sb = tp.buf[bufi];
       const TileDesc d = tp.desc[bufi];
       if (row_ok && !d.skip) {
@@ -621,18 +666,28 @@ __device__ __forceinline__ void stage_a_run(TilePipe& tp, const PairLevel& pl, c
         const int x0 = b * kTileW, bw = min(kTileW, g.w - x0);
         const int nr = (bw + 31) >> 5;
         unsigned refa = pin(smem_u32(&sb.ref0[q][0]) + lane * 8);
-        const float* txp = pin(pl.rtmpl + x0 + lane);
+        unsigned txa = pin(smem_u32(&sb.tx[0]) + lane * 4);
         const int xlim = bw - lane;        // lane's column r*32+lane is inside the band iff r*32 < xlim
+        // two rounds per trip: their projection / tap / blend chains are independent and interleave
 #pragma unroll 1
-        for (int r = 0; r < nr; ++r, refa += 256, txp += 32) {
-          const f2 rz = lds_f2_at(refa);
-          const float tx = __ldg(txp);
-          float z = hi(rz);
-          if (bw < kTileW) z = (r * 32 < xlim) ? z : __int_as_float(0x7fc00000);   // past a partial band: stale shared memory
-          const PixelProjection p = project_pixel(tx, ty, z, c);
-          float ei, ez;
-          const bool v = residual_pixel(p, wv, lo(rz), z, c, ei, ez);
-          scale_round32(ss, lane, lt_mask, v, student_weight(c, ei, ez), ei, ez);
+        for (int r = 0; r < nr; r += 2, refa += 512, txa += 256) {
+          const bool second = r + 1 < nr;                       // warp-uniform
+          const f2 rz0 = lds_f2_at(refa);
+          const f2 rz1 = second ? lds_f2_at(refa + 256) : pk(0.f, __int_as_float(0x7fc00000));
+          const float tx0 = lds_f32(txa), tx1 = second ? lds_f32(txa + 128) : 0.f;
+          float z0 = hi(rz0), z1 = hi(rz1);
+          if (bw < kTileW) {   // past a partial band: stale shared memory
+            z0 = (r * 32 < xlim) ? z0 : __int_as_float(0x7fc00000);
+            z1 = (r * 32 + 32 < xlim) ? z1 : __int_as_float(0x7fc00000);
+          }
+          const PixelProjection p0 = project_pixel(tx0, ty, z0, c);
+          const PixelProjection p1 = project_pixel(tx1, ty, z1, c);
+          float ei0, ez0, ei1, ez1;
+          const bool v0 = residual_pixel(p0, wv, lo(rz0), z0, c, ei0, ez0);
+          const bool v1 = residual_pixel(p1, wv, lo(rz1), z1, c, ei1, ez1);
+          const float w0 = student_weight(c, ei0, ez0), w1 = student_weight(c, ei1, ez1);
+          scale_round32(ss, lane, lt_mask, v0, w0, ei0, ez0);
+          scale_round32(ss, lane, lt_mask, v1, w1, ei1, ez1);
         }
       }
       __syncwarp();
@@ -758,9 +813,9 @@ __device__ __forceinline__ void stage_b_run(TilePipe& tp, const PairLevel& pl, c
     for (int b = 0; b < g.nbands; ++b, ++i) {
       const unsigned t = tbase + i;
       const int bufi = t % kStages;
-      const long long tw0 = tm.on ? clock64() : 0;
+      const long long tw0 = DVO_CLOCK(tm);
       mbar_wait(&tp.full[bufi], (t / kStages) & 1u, error_flag);
-      if (tm.on) tm.wait_full_b += clock64() - tw0;
+      DVO_ADD(tm, wait_full_b, DVO_CLOCK(tm) - tw0);
       const StageBuf& sb = tp.buf[bufi];
       const TileDesc d = tp.desc[bufi];
       const int x0 = b * kTileW, bw = min(kTileW, g.w - x0);
@@ -768,18 +823,19 @@ __device__ __forceinline__ void stage_b_run(TilePipe& tp, const PairLevel& pl, c
         const WinView wv = make_view(sb, d, pl.c3, g);
         const int nr = (bw + 31) >> 5;
         unsigned refa = pin(smem_u32(&sb.ref0[q][0]) + lane * 8);
-        const float* txp = pin(pl.rtmpl + x0 + lane);
+        unsigned txa = pin(smem_u32(&sb.tx[0]) + lane * 4);
         const int xlim = bw - lane;
 #pragma unroll 1
-        for (int r = 0; r < nr; ++r, refa += 256, txp += 32) {
+        for (int r = 0; r < nr; ++r, refa += 256, txa += 128) {
           const f2 rz = lds_f2_at(refa);
           const f2 gr = lds_f2<sizeof(float2) * kTileW * kTileH>(refa);     // ref1 follows ref0 in the stage buffer
-          const float tx = __ldg(txp);
+          const float tx = lds_f32(txa);
           float z = hi(rz);
           if (bw < kTileW) z = (r * 32 < xlim) ? z : __int_as_float(0x7fc00000);
           const PixelProjection p = project_pixel(tx, ty, z, c);
           f2 E, G, H;
           const bool valid = record_pixel(p, wv, lo(rz), z, gr, c, E, G, H);
+          DVO_ADD(tm, rounds, 1); DVO_ADD(tm, slow_rounds, wv.exact ? 0 : 1);
           bool keep = valid;
           if (cta_has_tail) {   // warp-uniform
             const unsigned m = __ballot_sync(kFullMask, valid);
@@ -791,7 +847,8 @@ __device__ __forceinline__ void stage_b_run(TilePipe& tp, const PairLevel& pl, c
           const float ei = valid ? lo(E) : 0.f, ez = valid ? hi(E) : 0.f;
           const float wall = student_weight(c, ei, ez);
           const float wgt = valid ? wall : 0.f;
-          stage_b_pixel(acc, cb, wgt, keep, ei, ez, valid ? G : 0ull, valid ? H : 0ull, valid ? z : 1.0f, tx, ty);
+          // (tx too: past a partial band it comes from shared memory no copy has written)
+          stage_b_pixel(acc, cb, wgt, keep, ei, ez, valid ? G : 0ull, valid ? H : 0ull, valid ? z : 1.0f, valid ? tx : 0.f, ty);
         }
       } else if (kDump && row_ok) {
         for (int xl = lane; xl < bw; xl += 32) dump_record(dump, (size_t)y * g.w + x0 + xl, false, 0ull, 0ull, 0ull, 0.f);

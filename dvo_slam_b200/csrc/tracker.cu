@@ -348,6 +348,7 @@ struct PersistentArgs {
   dvo_b200_iteration_stats* ilog;
   int max_log;
   float* dump;            // test hook: seven record planes of the (single) pair, or nullptr
+  unsigned long long* dbg2;  // optional (timing build): {tiles, inexact tiles, skipped tiles, rounds, rounds of inexact tiles, max / min CTA lifetime}
   unsigned long long* dbg;   // optional: ns spent per CTA in {stage A, stage B, wait A, wait B, mid, end, queue, total}
   int npairs, g, nsquads, strips_per_cta;
   LevelLaunch lp;
@@ -429,7 +430,9 @@ k_level_persistent(PersistentArgs a) {
   unsigned long long t_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t0 = 0, t1 = 0;
   const bool timing = a.dbg != nullptr && threadIdx.x == 0;
   PipeTiming tm;
+#ifdef DVO_PIPE_TIMING
   tm.on = a.dbg != nullptr && lane == 0 && (warp == 0 || warp == kConsumerWarps);   // one consumer warp and the producer
+#endif
   const unsigned long long t_start = timing ? global_ns() : 0;
 #define DVO_TICK() do { if (timing) t0 = global_ns(); } while (0)
 #define DVO_TOCK(slot) do { if (timing) { t1 = global_ns(); t_acc[slot] += t1 - t0; t0 = t1; } } while (0)
@@ -459,9 +462,9 @@ k_level_persistent(PersistentArgs a) {
       {
         StageConsts c;
         load_stage_consts(st, pl, lp.w, lp.h, false, c);
-        const long long ts0 = tm.on ? clock64() : 0;
+        const long long ts0 = DVO_CLOCK(tm);
         stage_a_run(tp, pl, geo, c, row_exports, tile_count, a.error_flag, tm);
-        if (tm.on) tm.rounds_a += clock64() - ts0;
+        DVO_ADD(tm, rounds_a, DVO_CLOCK(tm) - ts0);
       }
       __syncthreads();
       if (warp == 0) {   // this CTA's rows, in order -> one summary; row_base: rank of each row's first point inside the CTA
@@ -498,10 +501,10 @@ k_level_persistent(PersistentArgs a) {
         const long long my_n = __float_as_int(__ldcg(cta_exports + (size_t)rank * kSegExportFloats));
         RecordDump dump;
         dump.planes = a.dump; dump.n = lp.n;
-        const long long ts0 = tm.on ? clock64() : 0;
+        const long long ts0 = DVO_CLOCK(tm);
         if (a.dump) stage_b_run<true>(tp, pl, geo, c, cb, row_base, my_base, n_keep, my_base + my_n > n_keep, dump, acc, tile_count, a.error_flag, tm);
         else stage_b_run<false>(tp, pl, geo, c, cb, row_base, my_base, n_keep, my_base + my_n > n_keep, dump, acc, tile_count, a.error_flag, tm);
-        if (tm.on) tm.rounds_b += clock64() - ts0;
+        DVO_ADD(tm, rounds_b, DVO_CLOCK(tm) - ts0);
         float v[kNormalValues];
         stage_b_values(acc, v);
 #pragma unroll
@@ -539,10 +542,15 @@ k_level_persistent(PersistentArgs a) {
     t_acc[7] = global_ns() - t_start;
     for (int i = 0; i < 8; ++i) atomicAdd(a.dbg + i, t_acc[i]);
   }
+#ifdef DVO_PIPE_TIMING
   if (tm.on) {   // cycles: consumer warp 0 {stage A, wait full A, stage B, wait full B}, producer {descriptor, wait empty}
     if (warp == 0) { atomicAdd(a.dbg + 8, tm.rounds_a); atomicAdd(a.dbg + 9, tm.wait_full_a); atomicAdd(a.dbg + 10, tm.rounds_b); atomicAdd(a.dbg + 11, tm.wait_full_b); }
     else { atomicAdd(a.dbg + 12, tm.produce); atomicAdd(a.dbg + 13, tm.wait_empty); atomicAdd(a.dbg + 14, tm.rounds_a); atomicAdd(a.dbg + 15, tm.rounds_b); }
+    if (warp == 0) { atomicAdd(a.dbg2 + 3, tm.rounds); atomicAdd(a.dbg2 + 4, tm.slow_rounds); }
+    else { atomicAdd(a.dbg2 + 0, tm.tiles); atomicAdd(a.dbg2 + 1, tm.tiles_inexact); atomicAdd(a.dbg2 + 2, tm.tiles_skipped); }
   }
+  if (timing) { atomicMax(a.dbg2 + 5, t_acc[7]); atomicMin(a.dbg2 + 6, t_acc[7]); }
+#endif
 #undef DVO_TICK
 #undef DVO_TOCK
 }
@@ -769,10 +777,12 @@ int launch_level(dvo_b200_ctx* ctx, const LevelLaunch& lp, const LevelPlan& plan
   pa.ilog = ws.d_iter_log; pa.max_log = max_log;
   pa.dump = dump;
   pa.dbg = ctx->d_dbg ? ctx->d_dbg + 16 * li : nullptr;
+  pa.dbg2 = ctx->d_dbg ? ctx->d_dbg + 128 + 8 * li : nullptr;
   pa.npairs = npairs; pa.g = plan.g; pa.nsquads = plan.nsquads; pa.strips_per_cta = plan.strips_per_cta;
   pa.lp = lp;
   {
     ProfScope prof(ctx, 0);
+    ProfScope prof_level(ctx, 8 + std::min(li, 7));
     void* args[] = {&pa};
     DVO_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)k_level_persistent, dim3(ctx->num_sms * ctx->ctas_per_sm),
                                               dim3(kCtaThreads), args, kLevelSmemBytes, st));

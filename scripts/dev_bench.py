@@ -25,10 +25,13 @@ for spc in spcs:
     else: os.environ.pop("DVO_B200_STRIPS_PER_CTA", None)
     for _ in range(2): res = eng.match_batch(refs, curs, cfg, raw=True)
     eng.profile_read(reset=True)
+    eng.profile_enable(True)
     t0 = time.perf_counter()
     for _ in range(steps): res = eng.match_batch(refs, curs, cfg, raw=True)
     eng.synchronize()
     ms = (time.perf_counter() - t0) * 1e3 / steps
     pix = sum((W >> res[i].levels[l].id) * (H >> res[i].levels[l].id) * res[i].levels[l].num_iterations for i in range(B) for l in range(res[i].num_levels))
+    its = np.array([[res[i].levels[l].num_iterations for l in range(res[i].num_levels)] for i in range(B)])
+    print("iterations per level (coarse->fine): mean", np.round(its.mean(0), 2), "max", its.max(0), "p99", np.percentile(its, 99, axis=0))
     print(f"spc={spc} batch={B}: {ms:.2f} ms/step  {B / ms * 1e3:.0f} align/s  algorithmic {40 * pix / ms / 1e6:.0f} GB/s  frac {40 * pix / ms / 1e6 / 6578.3:.3f}", flush=True)
     eng.profile_read(reset=True)     # DVO_B200_TIMING=1: per-level CTA-time breakdown on stderr
