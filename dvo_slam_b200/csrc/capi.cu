@@ -121,7 +121,7 @@ int dvo_b200_destroy(dvo_b200_ctx* ctx) {
   for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
   Workspace& ws = ctx->ws;
   cudaFree(ws.d_pair_level); cudaFree(ws.d_state); cudaFree(ws.d_row_exports); cudaFree(ws.d_row_base);
-  cudaFree(ws.d_cta_exports); cudaFree(ws.d_cta_base); cudaFree(ws.d_normal_partial); cudaFree(ws.d_dump);
+  cudaFree(ws.d_cta_exports); cudaFree(ws.d_cta_base); cudaFree(ws.d_normal_partial); cudaFree(ws.d_dump); cudaFree(ws.d_tinit);
   cudaFree(ws.d_iter_log); cudaFree(ws.d_squads);
   if (ws.h_active) cudaFreeHost(ws.h_active);
   pool_close(ctx);
@@ -371,6 +371,7 @@ int dvo_b200_profile_read(dvo_b200_ctx* ctx, double ms_out[8], int64_t launches_
       if (u[0]) fprintf(stderr, "[dvo_b200 timing]   tiles %llu (inexact %.2f%%, skipped %.2f%%), stage-B rounds of inexact tiles %.2f%%; CTA lifetime of the last launch-set: "
                                 "max %.3f ms, min %.3f ms\n", u[0], 100.0 * (double)u[1] / (double)u[0], 100.0 * (double)u[2] / (double)u[0],
                         100.0 * (double)u[4] / (double)(u[3] + 1), (double)u[5] * 1e-6, (double)u[6] * 1e-6);
+      if (u[7]) fprintf(stderr, "[dvo_b200 timing]   end step: critical part %.1f%% of the end time\n", 100.0 * (double)u[7] / (double)(v[5] + 1));
     }
     if (reset) {
       cudaMemset(ctx->d_dbg, 0, sizeof(h));

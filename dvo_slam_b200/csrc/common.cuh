@@ -147,11 +147,12 @@ struct Workspace {              // per-ctx scratch of the level kernel
   int* d_cta_base = nullptr;         // per squad, per CTA: exclusive prefix of valid counts
   float* d_normal_partial = nullptr; // per squad, per CTA: log-likelihood sum, 21 upper-triangular A, 6 b
   float* d_dump = nullptr;           // test hook: seven residual-record planes of one level
+  double* d_tinit = nullptr;         // per pair initial estimate (4x4)
   dvo_b200_iteration_stats* d_iter_log = nullptr;
   int* h_active = nullptr;           // pinned: per level, the kernel's error flag
   char* d_squads = nullptr;          // persistent kernel: SquadState[nsquads] + {queue head, error flag}
   size_t cap_pairs = 0, cap_row_exports = 0, cap_row_base = 0, cap_cta_exports = 0, cap_cta_base = 0, cap_partial = 0,
-         cap_squads = 0, cap_iter_log = 0, cap_dump = 0;
+         cap_squads = 0, cap_iter_log = 0, cap_dump = 0, cap_tinit = 0;
 };
 
 }  // namespace dvo_b200

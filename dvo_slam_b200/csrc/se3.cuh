@@ -167,45 +167,74 @@ DVO_HD void se3_log(const SE3d& s, double out[6]) {
   out[3] = wx; out[4] = wy; out[5] = wz;
 }
 
-// x = A.ldlt().solve(b) for a symmetric 6x6 (diagonal pivoting, Eigen's tolerance rule on D)
+// x = A.ldlt().solve(b) for a symmetric 6x6 (diagonal pivoting, Eigen's tolerance rule on D).
+//
+// Eigen's unblocked LDL^T is left-looking: when step k searches the remaining diagonal for its pivot, the entries it
+// compares have not been updated yet, so the whole pivot sequence is a selection sort of the ORIGINAL diagonal by
+// decreasing magnitude (first maximum wins) and can be found up front.  Factorising the symmetrically permuted matrix
+// without pivoting then performs exactly the operations of the in-place pivoted version, with compile-time indices:
+// on the device everything stays in registers (the in-place version indexed a local-memory array through the
+// permutation, ~700 local loads and stores on the critical path of every Gauss-Newton iteration).
 DVO_HD void ldlt_solve6(const double Ain[36], const double bin[6], double x[6]) {
-  const int n = 6;
-  double A[36];
-  for (int i = 0; i < 36; ++i) A[i] = Ain[i];
-  int perm[6];
+  constexpr int n = 6;
+  int idx[6] = {0, 1, 2, 3, 4, 5};
+#pragma unroll
   for (int k = 0; k < n; ++k) {
     int piv = k;
-    double best = fabs(A[k * n + k]);
+    double best = fabs(Ain[idx[k] * n + idx[k]]);
+#pragma unroll
     for (int i = k + 1; i < n; ++i) {
-      double v = fabs(A[i * n + i]);
+      double v = fabs(Ain[idx[i] * n + idx[i]]);
       if (v > best) { best = v; piv = i; }
     }
-    perm[k] = piv;
-    if (piv != k) {
-      for (int j = 0; j < n; ++j) { double t = A[k * n + j]; A[k * n + j] = A[piv * n + j]; A[piv * n + j] = t; }
-      for (int i = 0; i < n; ++i) { double t = A[i * n + k]; A[i * n + k] = A[i * n + piv]; A[i * n + piv] = t; }
-    }
-    for (int j = 0; j < k; ++j) A[k * n + k] -= A[k * n + j] * A[k * n + j] * A[j * n + j];
-    double d = A[k * n + k];
+    // swap idx[k] <-> idx[piv] with static indexing
+    int ik = idx[k], ip = ik;
+#pragma unroll
+    for (int i = k + 1; i < n; ++i) if (piv == i) ip = idx[i];
+#pragma unroll
+    for (int i = k + 1; i < n; ++i) if (piv == i) idx[i] = ik;
+    idx[k] = ip;
+  }
+  double A[6][6], y[6];
+#pragma unroll
+  for (int i = 0; i < n; ++i) {
+    y[i] = bin[idx[i]];
+#pragma unroll
+    for (int j = 0; j <= i; ++j) A[i][j] = Ain[idx[i] * n + idx[j]];     // lower triangle of P A P^T
+  }
+#pragma unroll
+  for (int k = 0; k < n; ++k) {
+#pragma unroll
+    for (int j = 0; j < k; ++j) A[k][k] -= A[k][j] * A[k][j] * A[j][j];
+    const double d = A[k][k];
+#pragma unroll
     for (int i = k + 1; i < n; ++i) {
-      double s = A[i * n + k];
-      for (int j = 0; j < k; ++j) s -= A[i * n + j] * A[k * n + j] * A[j * n + j];
-      A[i * n + k] = (d != 0.0) ? s / d : 0.0;
+      double s = A[i][k];
+#pragma unroll
+      for (int j = 0; j < k; ++j) s -= A[i][j] * A[k][j] * A[j][j];
+      A[i][k] = (d != 0.0) ? s / d : 0.0;
     }
   }
-  double y[6];
-  for (int i = 0; i < n; ++i) y[i] = bin[i];
-  for (int k = 0; k < n; ++k) { double t = y[k]; y[k] = y[perm[k]]; y[perm[k]] = t; }
+#pragma unroll
   for (int i = 0; i < n; ++i)
-    for (int j = 0; j < i; ++j) y[i] -= A[i * n + j] * y[j];
+#pragma unroll
+    for (int j = 0; j < i; ++j) y[i] -= A[i][j] * y[j];
   double dmax = 0;
-  for (int i = 0; i < n; ++i) dmax = fmax(dmax, fabs(A[i * n + i]));
-  double tol = fmax(dmax * DBL_EPSILON, 1.0 / DBL_MAX);
-  for (int i = 0; i < n; ++i) y[i] = fabs(A[i * n + i]) > tol ? y[i] / A[i * n + i] : 0.0;
+#pragma unroll
+  for (int i = 0; i < n; ++i) dmax = fmax(dmax, fabs(A[i][i]));
+  const double tol = fmax(dmax * DBL_EPSILON, 1.0 / DBL_MAX);
+#pragma unroll
+  for (int i = 0; i < n; ++i) y[i] = fabs(A[i][i]) > tol ? y[i] / A[i][i] : 0.0;
+#pragma unroll
   for (int i = n - 1; i >= 0; --i)
-    for (int j = i + 1; j < n; ++j) y[i] -= A[j * n + i] * y[j];
-  for (int k = n - 1; k >= 0; --k) { double t = y[k]; y[k] = y[perm[k]]; y[perm[k]] = t; }
-  for (int i = 0; i < n; ++i) x[i] = y[i];
+#pragma unroll
+    for (int j = i + 1; j < n; ++j) y[i] -= A[j][i] * y[j];
+#pragma unroll
+  for (int i = 0; i < n; ++i) {
+    // x[idx[i]] = y[i] with static indexing of x
+#pragma unroll
+    for (int t = 0; t < n; ++t) if (idx[i] == t) x[t] = y[i];
+  }
 }
 
 }  // namespace dvo_b200

@@ -78,19 +78,12 @@ __device__ void log_iteration(dvo_b200_iteration_stats* ilog, int max_log, int p
   for (int i = 0; i < 36; ++i) e.information[i] = with_increment ? st.A_done[i] : nan;
 }
 
-// pls_src: this level's pair descriptors, either in device memory already (pls_src == pls) or in pinned host
-// memory that the kernel reads over PCIe (the tracker path: keeps the per-level upload off the H2D copy engine,
-// where it would queue behind a bulk image upload of another context).  T_init likewise.
-__global__ void k_level_begin(PairState* states, const PairLevel* pls_src, PairLevel* pls, const double* T_init, int npairs,
-                              LevelLaunch lp) {
-  int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= npairs) return;
-  PairState& st = states[p];
-  const PairLevel pl = pls_src[p];
-  if (pls_src != pls) pls[p] = pl;
+// Start of a pyramid level for one pair (dense_tracking.cpp:137-150, 205-210, 238): run by one thread of the squad that
+// owns the pair, before the level's first iteration.
+__device__ void level_begin(PairState& st, const PairLevel& pl, const double* T_init, int pair, const LevelLaunch& lp) {
   if (lp.first_level) {
     // dense_tracking.cpp:137-150: first increment is the given guess
-    st.inc = (lp.use_initial_estimate && T_init) ? se3_from_matrix(T_init + (size_t)p * 16) : se3_identity();
+    st.inc = (lp.use_initial_estimate && T_init) ? se3_from_matrix(T_init + (size_t)pair * 16) : se3_identity();
     st.initial = st.inc; st.initial_old = st.inc;
     st.estimate = se3_identity(); st.estimate_old = se3_identity();
     st.num_levels = 0; st.num_iterations_total = 0; st.iter_log_count = 0;
@@ -113,6 +106,14 @@ __global__ void k_level_begin(PairState* states, const PairLevel* pls_src, PairL
   st.num_levels = lp.level_index + 1;
   se3_log(st.inc, st.x);  // dense_tracking.cpp:238
   prepare_iteration(st, pl);
+}
+
+// The pair descriptors of all levels and the initial estimates are written by the host into pinned memory; this kernel
+// reads them over PCIe (unified addressing) into device memory, which keeps the upload off the H2D copy engine, where it
+// would queue behind a bulk image upload of another context.
+__global__ void k_stage_words(const uint4* __restrict__ src, uint4* __restrict__ dst, size_t n16) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n16) dst[i] = src[i];
 }
 
 // one warp per pair: combine the CTA summaries of the squad in order -> covariance -> P_k (dense_tracking.cpp:276-295).
@@ -181,8 +182,10 @@ struct PairEndSmem {
 template <typename Release>
 __device__ __noinline__ void pair_end_cta(PairState& st, const PairLevel& pl, int pair, const float* partial, int ntiles,
                                              int* active, const LevelLaunch& lp, dvo_b200_iteration_stats* ilog, int max_log,
-                                             PairEndSmem& sm, Release release) {
+                                             PairEndSmem& sm, Release release, unsigned long long* tcrit = nullptr) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned long long tc0 = 0;
+  if (tcrit && threadIdx.x == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tc0));
   {   // fp64 sum of the partials: warp q takes tiles q, q+4, ... with independent loads in flight
     double v = 0.0;
     if (lane < kNormalValues && warp < kEndWarps) {
@@ -265,6 +268,7 @@ __device__ __noinline__ void pair_end_cta(PairState& st, const PairLevel& pl, in
   } else {
     st.level_active = 0;
   }
+  if (tcrit) { unsigned long long tc1; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tc1)); atomicAdd(tcrit, tc1 - tc0); }
   release();
 
   // ---- deferred ----
@@ -347,11 +351,15 @@ struct PersistentArgs {
   int* error_flag;
   dvo_b200_iteration_stats* ilog;
   int max_log;
+  const double* T_init;   // per pair 4x4 (device memory) or nullptr
+  int nlev;               // pyramid levels this launch walks every pair through (coarse to fine)
+  int skip_begin;         // test hook: the pair state was placed by k_set_state
   float* dump;            // test hook: seven record planes of the (single) pair, or nullptr
   unsigned long long* dbg2;  // optional (timing build): {tiles, inexact tiles, skipped tiles, rounds, rounds of inexact tiles, max / min CTA lifetime}
   unsigned long long* dbg;   // optional: ns spent per CTA in {stage A, stage B, wait A, wait B, mid, end, queue, total}
-  int npairs, g, nsquads, strips_per_cta;
-  LevelLaunch lp;
+  int npairs, g, nsquads;
+  int strips_per_cta[kMaxLevels];
+  LevelLaunch lp[kMaxLevels];
 };
 
 __device__ __forceinline__ unsigned long long global_ns() {
@@ -406,19 +414,15 @@ k_level_persistent(PersistentArgs a) {
   const int squad = blockIdx.x / a.g, rank = blockIdx.x - squad * a.g;
   if (squad >= a.nsquads) return;   // leftover CTAs
   SquadState* sq = a.squads + squad;
-  const LevelLaunch& lp = a.lp;
-  float* row_exports = a.row_exports + (size_t)squad * lp.h * kSegExportFloats;
-  int* row_base = a.row_base + (size_t)squad * lp.h;
+  int hmax = 0;
+  for (int li = 0; li < a.nlev; ++li) hmax = max(hmax, a.lp[li].h);
+  float* row_exports = a.row_exports + (size_t)squad * hmax * kSegExportFloats;
+  int* row_base = a.row_base + (size_t)squad * hmax;
   float* cta_exports = a.cta_exports + (size_t)squad * a.g * kSegExportFloats;
   int* cta_base = a.cta_base + (size_t)squad * a.g;
   float* partial = a.partial + (size_t)squad * a.g * kNormalValues;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  LevelGeom geo;
-  geo.w = lp.w; geo.h = lp.h; geo.n = lp.n; geo.pitch = lp.pitch; geo.nbands = lp.nbands; geo.nstrips = lp.nstrips;
-  geo.strip0 = min(rank * a.strips_per_cta, lp.nstrips);
-  geo.strip1 = min(geo.strip0 + a.strips_per_cta, lp.nstrips);
-  const int row0 = min(geo.strip0 * kTileH, lp.h), row1 = min(geo.strip1 * kTileH, lp.h);
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kStages; ++i) { mbar_init(&tp.full[i], 1); mbar_init(&tp.empty[i], kConsumerWarps); }
@@ -455,7 +459,29 @@ k_level_persistent(PersistentArgs a) {
     const int pair = __ldcg(&sq->pair);
     if (pair < 0 || *reinterpret_cast<volatile int*>(a.error_flag)) break;
     PairState& st = a.states[pair];
-    const PairLevel pl = a.pls[pair];
+
+    // ---- the squad walks its pair through the levels of this launch, coarse to fine ----
+    for (int li = 0; li < a.nlev; ++li) {
+    const LevelLaunch& lp = a.lp[li];
+    const PairLevel pl = a.pls[(size_t)li * a.npairs + pair];
+    LevelGeom geo;
+    geo.w = lp.w; geo.h = lp.h; geo.n = lp.n; geo.pitch = lp.pitch; geo.nbands = lp.nbands; geo.nstrips = lp.nstrips;
+    geo.strip0 = min(rank * a.strips_per_cta[li], lp.nstrips);
+    geo.strip1 = min(geo.strip0 + a.strips_per_cta[li], lp.nstrips);
+    const int row0 = min(geo.strip0 * kTileH, lp.h), row1 = min(geo.strip1 * kTileH, lp.h);
+    if (!a.skip_begin) {   // DenseTracker::match, start of a level: the last CTA to arrive initialises the pair's level state
+      if (squad_arrive(sq, episode, a.g, lt.s_flag)) {
+        if (threadIdx.x == 0) {
+          level_begin(st, pl, a.T_init, pair, lp);
+          squad_release(sq, episode);
+        }
+      } else {
+        squad_wait(sq, episode, a.error_flag);
+      }
+      __syncthreads();
+      ++episode;
+      DVO_TOCK(6);
+    }
 
     for (;;) {
       // ---- stage A ----
@@ -526,7 +552,7 @@ k_level_persistent(PersistentArgs a) {
       DVO_TOCK(1);
       if (squad_arrive(sq, episode, a.g, lt.s_flag)) {
         DVO_TOCK(3);
-        pair_end_cta(st, pl, pair, partial, a.g, nullptr, lp, a.ilog, a.max_log, lt.end, [&] { squad_release(sq, episode); });
+        pair_end_cta(st, pl, pair, partial, a.g, nullptr, lp, a.ilog, a.max_log, lt.end, [&] { squad_release(sq, episode); }, a.dbg2 ? a.dbg2 + 7 : nullptr);
         __syncthreads();
         DVO_TOCK(5);
       } else {
@@ -537,6 +563,8 @@ k_level_persistent(PersistentArgs a) {
       ++episode;
       if (!__ldcg(&st.level_active) || *reinterpret_cast<volatile int*>(a.error_flag)) break;
     }
+    if (*reinterpret_cast<volatile int*>(a.error_flag)) break;
+    }   // levels
   }
   if (timing) {
     t_acc[7] = global_ns() - t_start;
@@ -669,25 +697,26 @@ int ensure_geometry(dvo_b200_ctx* ctx) {
   return 0;
 }
 
-// How one pyramid level is spread over the persistent grid.
-struct LevelPlan {
+// How a group of consecutive pyramid levels is spread over the persistent grid: one launch walks every pair through the
+// group's levels (coarse to fine) inside the kernel.
+struct GroupPlan {
+  int first_li, nlev;   // levels [first_li, first_li + nlev) of the match (index 0 = coarsest)
   int g;                // CTAs per squad
   int nsquads;          // squads in the grid
-  int strips_per_cta;
+  int strips_per_cta[kMaxLevels];
 };
 
-LevelPlan plan_level(int nstrips, int nbands, int num_sms, int ctas_per_sm, int npairs) {
-  // A squad of g CTAs gives each CTA spc = ceil(nstrips / g) strips.  Small squads keep many pairs in flight and
-  // amortise the two barriers and the serial P_k / solve sections of an iteration over more tiles per CTA; but the
-  // batch is processed in waves of nsquads pairs, and a last wave that is mostly empty wastes more than that.
-  // Pairs are handed out from a queue, so a level takes about (pairs per squad + tail) x time per pair, where the
-  // tail (pairs that need two or three times the mean number of iterations) is worth a bit more than one pair and
-  // the time per pair goes with (tiles per CTA + per-iteration overhead in tile units).
+// Squad size for one level on its own.  A squad of g CTAs gives each CTA spc = ceil(nstrips / g) strips.  Small squads keep
+// many pairs in flight and amortise the two barriers and the serial P_k / solve sections of an iteration over more tiles
+// per CTA; but the batch is processed in waves of nsquads pairs, and a last wave that is mostly empty wastes more than
+// that.  Pairs are handed out from a queue, so a level takes about (pairs per squad + tail) x time per pair, where the
+// tail (pairs that need two or three times the mean number of iterations) is worth a bit more than one pair and the time
+// per pair goes with (tiles per CTA + per-iteration overhead in tile units).
+int level_squad_size(int nstrips, int nbands, int grid, int npairs) {
   const char* env = getenv("DVO_B200_STRIPS_PER_CTA");     // developer override (experiments)
   const int forced_spc = env ? atoi(env) : 0;
-  const int grid = num_sms * ctas_per_sm;
   const double overhead_tiles = 3.0;
-  LevelPlan best{1, 1, nstrips};
+  int best_g = 1;
   double best_cost = -1.0;
   for (int spc = 1; spc <= nstrips; ++spc) {
     const int g = (nstrips + spc - 1) / spc;
@@ -697,9 +726,48 @@ LevelPlan plan_level(int nstrips, int nbands, int num_sms, int ctas_per_sm, int 
     const double per_squad = (double)npairs / nsquads;
     double cost = (std::max(per_squad, 1.0) + (npairs > nsquads ? 1.2 : 0.0)) * ((double)spc * nbands + overhead_tiles);
     if (forced_spc > 0) cost = std::abs(spc - forced_spc);
-    if (best_cost < 0 || cost < best_cost - 1e-9) { best_cost = cost; best = LevelPlan{g, nsquads, spc}; }
+    if (best_cost < 0 || cost < best_cost - 1e-9) { best_cost = cost; best_g = g; }
   }
-  return best;
+  return best_g;
+}
+
+// Levels small enough for one CTA per pair (no squad barriers at all) form one group: a CTA takes a pair from the queue and
+// runs it through all of them, so a pair that needs many iterations on one coarse level delays nobody.  The remaining
+// (fine) levels form a second group with the squad size of the finest level; a squad likewise walks its pair through both.
+// With few pairs every level gets its own launch and the squad size that minimises its latency.
+int plan_groups(const dvo_b200_pyramid* ref, int first, int last, int grid, int npairs, GroupPlan* out) {
+  const int nlev = first - last + 1;
+  int g_level[kMaxLevels];
+  for (int li = 0; li < nlev; ++li) {
+    const LevelInfo& L = ref->L[first - li];
+    g_level[li] = level_squad_size(L.nstrips, L.nbands, grid, npairs);
+  }
+  int ngroups = 0;
+  const bool walk = npairs >= grid / 4 && !getenv("DVO_B200_NO_WALK");
+  for (int li = 0; li < nlev;) {
+    GroupPlan& G = out[ngroups++];
+    G.first_li = li; G.nlev = 1; G.g = g_level[li];
+    if (walk) {
+      const LevelInfo& L0 = ref->L[first - li];
+      const bool coarse = L0.nstrips * L0.nbands <= 40;
+      if (coarse) G.g = 1;
+      while (li + G.nlev < nlev) {
+        const LevelInfo& Ln = ref->L[first - (li + G.nlev)];
+        const bool coarse_n = Ln.nstrips * Ln.nbands <= 40;
+        if (coarse_n != coarse) break;
+        if (!coarse) G.g = g_level[li + G.nlev];      // the finest level of the group decides
+        G.nlev++;
+      }
+    }
+    for (int k = 0; k < G.nlev; ++k) {
+      const LevelInfo& L = ref->L[first - (li + k)];
+      const int g_eff = std::min(G.g, L.nstrips);
+      G.strips_per_cta[k] = (L.nstrips + g_eff - 1) / g_eff;
+    }
+    G.nsquads = std::min(grid / G.g, std::max(npairs, 1));
+    li += G.nlev;
+  }
+  return ngroups;
 }
 
 int check_batch(dvo_b200_ctx* ctx, const dvo_b200_config* cfg, int n, dvo_b200_pyramid* const* refs,
@@ -751,38 +819,42 @@ LevelLaunch make_level_launch(const LevelInfo& L, const dvo_b200_config* cfg, in
   return lp;
 }
 
-void add_need(ScratchNeed& need, const LevelInfo& L, const LevelPlan& pl) {
-  need.row_export_floats = std::max(need.row_export_floats, (size_t)pl.nsquads * L.h * kSegExportFloats);
-  need.row_base_ints = std::max(need.row_base_ints, (size_t)pl.nsquads * L.h);
+void add_need(ScratchNeed& need, int hmax, const GroupPlan& pl) {
+  need.row_export_floats = std::max(need.row_export_floats, (size_t)pl.nsquads * hmax * kSegExportFloats);
+  need.row_base_ints = std::max(need.row_base_ints, (size_t)pl.nsquads * hmax);
   need.cta_export_floats = std::max(need.cta_export_floats, (size_t)pl.nsquads * pl.g * kSegExportFloats);
   need.cta_base_ints = std::max(need.cta_base_ints, (size_t)pl.nsquads * pl.g);
   need.partial_floats = std::max(need.partial_floats, (size_t)pl.nsquads * pl.g * kNormalValues);
   need.squads = std::max(need.squads, (size_t)pl.nsquads + 1);
 }
 
-// enqueue the persistent kernel of one level (squad states zeroed first); `tail` receives {queue head, error flag}
-int launch_level(dvo_b200_ctx* ctx, const LevelLaunch& lp, const LevelPlan& plan, int npairs, int max_log, float* dump, int li,
-                 int** tail_out) {
+// enqueue the persistent kernel of one group of levels (squad states zeroed first); `tail` receives {queue head, error flag}
+int launch_group(dvo_b200_ctx* ctx, const LevelLaunch* lps, const GroupPlan& plan, const PairLevel* d_pls, const double* d_Tinit,
+                 int npairs, int max_log, float* dump, int skip_begin, int group_index, int** tail_out) {
   Workspace& ws = ctx->ws;
   cudaStream_t st = ctx->stream;
   // squad states, queue head and error flag (last SquadState slot) start at zero
   DVO_CUDA(ctx, cudaMemsetAsync(ws.d_squads, 0, sizeof(SquadState) * (plan.nsquads + 1), st));
   PersistentArgs pa;
-  pa.states = ws.d_state; pa.pls = ws.d_pair_level;
+  pa.states = ws.d_state; pa.pls = d_pls;
   pa.row_exports = ws.d_row_exports; pa.row_base = ws.d_row_base; pa.cta_exports = ws.d_cta_exports; pa.cta_base = ws.d_cta_base;
   pa.partial = ws.d_normal_partial;
   pa.squads = reinterpret_cast<SquadState*>(ws.d_squads);
   int* tail = reinterpret_cast<int*>(pa.squads + plan.nsquads);
   pa.next_pair = tail; pa.error_flag = tail + 1;
   pa.ilog = ws.d_iter_log; pa.max_log = max_log;
+  pa.T_init = d_Tinit; pa.nlev = plan.nlev; pa.skip_begin = skip_begin;
   pa.dump = dump;
-  pa.dbg = ctx->d_dbg ? ctx->d_dbg + 16 * li : nullptr;
-  pa.dbg2 = ctx->d_dbg ? ctx->d_dbg + 128 + 8 * li : nullptr;
-  pa.npairs = npairs; pa.g = plan.g; pa.nsquads = plan.nsquads; pa.strips_per_cta = plan.strips_per_cta;
-  pa.lp = lp;
+  pa.dbg = ctx->d_dbg ? ctx->d_dbg + 16 * std::min(group_index, 7) : nullptr;
+  pa.dbg2 = ctx->d_dbg ? ctx->d_dbg + 128 + 8 * std::min(group_index, 7) : nullptr;
+  pa.npairs = npairs; pa.g = plan.g; pa.nsquads = plan.nsquads;
+  for (int k = 0; k < kMaxLevels; ++k) {
+    pa.strips_per_cta[k] = k < plan.nlev ? plan.strips_per_cta[k] : 0;
+    if (k < plan.nlev) pa.lp[k] = lps[k];
+  }
   {
     ProfScope prof(ctx, 0);
-    ProfScope prof_level(ctx, 8 + std::min(li, 7));
+    ProfScope prof_level(ctx, 8 + std::min(group_index, 7));
     void* args[] = {&pa};
     DVO_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)k_level_persistent, dim3(ctx->num_sms * ctx->ctas_per_sm),
                                               dim3(kCtaThreads), args, kLevelSmemBytes, st));
@@ -804,50 +876,61 @@ int tracker_match_batch(dvo_b200_ctx* ctx, const dvo_b200_config* cfg, int n, dv
   const int last = cfg->last_level, first = cfg->first_level;
   const int max_log = iter_stats ? max_iter_stats : 0;
   if ((rc = ensure_geometry(ctx))) return rc;
+  const int nlev = first - last + 1;
+  const int grid = ctx->num_sms * ctx->ctas_per_sm;
+  GroupPlan groups[kMaxLevels];
+  const int ngroups = plan_groups(refs[0], first, last, grid, n, groups);
   ScratchNeed need;
-  for (int level = first; level >= last; --level) {
-    const LevelInfo& L = refs[0]->L[level];
-    add_need(need, L, plan_level(L.nstrips, L.nbands, ctx->num_sms, ctx->ctas_per_sm, n));
+  for (int gi = 0; gi < ngroups; ++gi) {
+    int hmax = 0;
+    for (int k = 0; k < groups[gi].nlev; ++k) hmax = std::max(hmax, refs[0]->L[first - (groups[gi].first_li + k)].h);
+    add_need(need, hmax, groups[gi]);
   }
-  rc = ensure_workspace(ctx, n, need, max_log);
+  rc = ensure_workspace(ctx, n * nlev, need, max_log);     // d_pair_level holds the descriptors of every level
   if (rc) return rc;
 
   // selection masks for non-default thresholds (PointSelection caches per pyramid, point_selection.cpp:100-113)
   for (int i = 0; i < n; ++i)
     if ((rc = pyramid_reselect(ctx, refs[i], cfg->intensity_derivative_threshold, cfg->depth_derivative_threshold))) return rc;
 
-  // Pair descriptors of every level and the initial estimates go into the pinned stage once; k_level_begin
-  // reads them from there (host-mapped, unified addressing), so the level loop below never touches the H2D copy
-  // engine or the host between launches.
-  const int nlev = first - last + 1;
-  const size_t desc_bytes = sizeof(PairLevel) * (size_t)n * nlev;
+  // Pair descriptors of every level and the initial estimates go into the pinned stage once; one small kernel copies
+  // them to device memory (reads over PCIe: no H2D copy-engine work, no host round trip between the launches below).
+  const size_t desc_bytes = (sizeof(PairLevel) * (size_t)n * nlev + 15) / 16 * 16;
   const bool have_init = cfg->use_initial_estimate && T_init;
   const size_t init_bytes = have_init ? sizeof(double) * 16 * (size_t)n : 0;
   if ((rc = ensure_stage(ctx, 0, desc_bytes + init_bytes))) return rc;
+  if ((rc = grow(ctx, ws.d_tinit, ws.cap_tinit, (size_t)16 * n))) return rc;
   DVO_CUDA(ctx, cudaStreamSynchronize(st));   // previous use of the pinned stage has drained
   PairLevel* h_desc = (PairLevel*)ctx->h_stage;
   for (int level = first, li = 0; level >= last; --level, ++li) fill_pair_levels(h_desc + (size_t)li * n, n, refs, curs, level);
-  double* d_Tinit = nullptr;
-  if (have_init) {
-    d_Tinit = (double*)((char*)ctx->h_stage + desc_bytes);
-    std::memcpy(d_Tinit, T_init, init_bytes);
-  }
+  if (have_init) std::memcpy((char*)ctx->h_stage + desc_bytes, T_init, init_bytes);
   ctx->h2d_bytes += desc_bytes + init_bytes;
+  {
+    ProfScope prof(ctx, 2);
+    const size_t n16 = desc_bytes / 16;
+    k_stage_words<<<(unsigned)((n16 + 255) / 256), 256, 0, st>>>((const uint4*)h_desc, (uint4*)ws.d_pair_level, n16);
+    ctx->launches++;
+    if (have_init) {
+      const size_t m16 = init_bytes / 16;
+      k_stage_words<<<(unsigned)((m16 + 255) / 256), 256, 0, st>>>((const uint4*)((char*)ctx->h_stage + desc_bytes), (uint4*)ws.d_tinit, m16);
+      ctx->launches++;
+    }
+  }
 
   for (int i = 0; i < 8; ++i) ws.h_active[i] = 0;
   if (max_log > 0) DVO_CUDA(ctx, cudaMemsetAsync(ws.d_iter_log, 0, sizeof(dvo_b200_iteration_stats) * (size_t)n * max_log, st));
-  for (int level = first, li = 0; level >= last; --level, ++li) {
-    const LevelInfo& L = refs[0]->L[level];
-    const LevelLaunch lp = make_level_launch(L, cfg, li, level);
-    const LevelPlan plan = plan_level(L.nstrips, L.nbands, ctx->num_sms, ctx->ctas_per_sm, n);
-    {
-      ProfScope prof(ctx, 2);
-      k_level_begin<<<(n + 63) / 64, 64, 0, st>>>(ws.d_state, h_desc + (size_t)li * n, ws.d_pair_level, d_Tinit, n, lp);
-      ctx->launches++;
+  for (int gi = 0; gi < ngroups; ++gi) {
+    const GroupPlan& G = groups[gi];
+    LevelLaunch lps[kMaxLevels];
+    for (int k = 0; k < G.nlev; ++k) {
+      const int li = G.first_li + k, level = first - li;
+      lps[k] = make_level_launch(refs[0]->L[level], cfg, li, level);
     }
     int* tail = nullptr;
-    if ((rc = launch_level(ctx, lp, plan, n, max_log, nullptr, li, &tail))) return rc;
-    DVO_CUDA(ctx, cudaMemcpyAsync(&ws.h_active[level_flag_slot(li)], tail + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+    if ((rc = launch_group(ctx, lps, G, ws.d_pair_level + (size_t)G.first_li * n, have_init ? ws.d_tinit : nullptr, n, max_log, nullptr,
+                           0, gi, &tail)))
+      return rc;
+    DVO_CUDA(ctx, cudaMemcpyAsync(&ws.h_active[level_flag_slot(gi)], tail + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
   }
   // results
   dvo_b200_result* d_res = (dvo_b200_result*)d_results_user;
@@ -862,7 +945,7 @@ int tracker_match_batch(dvo_b200_ctx* ctx, const dvo_b200_config* cfg, int n, dv
     ctx->launches++;
   }
   DVO_CUDA(ctx, cudaGetLastError());
-  ctx->pending_level_flags = first - last + 1;   // checked at the next synchronisation point (device-results variant)
+  ctx->pending_level_flags = ngroups;   // checked at the next synchronisation point (device-results variant)
   if (h_results) {
     size_t bytes = sizeof(dvo_b200_result) * n;
     if (bytes > ctx->h_results_bytes) {
@@ -918,10 +1001,13 @@ int tracker_linearize(dvo_b200_ctx* ctx, const dvo_b200_config* cfg, dvo_b200_py
   Workspace& ws = ctx->ws;
   const LevelInfo& L = ref->L[level];
   if ((rc = ensure_geometry(ctx))) return rc;
-  const LevelPlan plan = plan_level(L.nstrips, L.nbands, ctx->num_sms, ctx->ctas_per_sm, 1);
+  GroupPlan plan;
   {
+    GroupPlan tmp[kMaxLevels];
+    plan_groups(ref, level, level, ctx->num_sms * ctx->ctas_per_sm, 1, tmp);
+    plan = tmp[0];
     ScratchNeed need;
-    add_need(need, L, plan);
+    add_need(need, L.h, plan);
     if (planes7) need.dump_floats = 7 * (size_t)L.n;
     if ((rc = ensure_workspace(ctx, 1, need, 0))) return rc;
   }
@@ -945,7 +1031,7 @@ int tracker_linearize(dvo_b200_ctx* ctx, const dvo_b200_config* cfg, dvo_b200_py
   ctx->launches += 1;
   int* tail = nullptr;
   ws.h_active[0] = 0;
-  if ((rc = launch_level(ctx, lp, plan, 1, 0, planes7 ? ws.d_dump : nullptr, 0, &tail))) return rc;
+  if ((rc = launch_group(ctx, &lp, plan, ws.d_pair_level, nullptr, 1, 0, planes7 ? ws.d_dump : nullptr, 1, 0, &tail))) return rc;
   DVO_CUDA(ctx, cudaMemcpyAsync(&ws.h_active[0], tail + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
   DVO_CUDA(ctx, cudaGetLastError());
   PairState* hs = nullptr;

@@ -117,7 +117,27 @@ class Matrix {
     for (int i = 0; i < R * C; ++i) o.data()[i] = (U)m_[i];
     return o;
   }
-  T determinant() const { static_assert(R == 2 && C == 2, "2x2 only"); return m_[0] * m_[3] - m_[2] * m_[1]; }
+  T sum() const { T a = m_[0]; for (int i = 1; i < R * C; ++i) a += m_[i]; return a; }
+  T squaredNorm() const { T a = m_[0] * m_[0]; for (int i = 1; i < R * C; ++i) a += m_[i] * m_[i]; return a; }
+  T determinant() const {
+    static_assert(R == C, "square only");
+    if (R == 2) return m_[0] * m_[3] - m_[2] * m_[1];
+    T a[R * C];   // partial-pivot LU (only the 2x2 closed form is used by the reference's translation units)
+    for (int i = 0; i < R * C; ++i) a[i] = m_[i];
+    T det = T(1);
+    for (int k = 0; k < R; ++k) {
+      int piv = k;
+      for (int i = k + 1; i < R; ++i) if (std::fabs(a[k * R + i]) > std::fabs(a[k * R + piv])) piv = i;
+      if (a[k * R + piv] == T(0)) return T(0);
+      if (piv != k) { for (int j = 0; j < C; ++j) { T t = a[j * R + k]; a[j * R + k] = a[j * R + piv]; a[j * R + piv] = t; } det = -det; }
+      det *= a[k * R + k];
+      for (int i = k + 1; i < R; ++i) {
+        const T f = a[k * R + i] / a[k * R + k];
+        for (int j = k; j < C; ++j) a[j * R + i] -= f * a[j * R + k];
+      }
+    }
+    return det;
+  }
   Matrix inverse() const {   // Eigen's 2x2 inverse: adjugate times 1/det
     static_assert(R == 2 && C == 2, "2x2 only");
     const T invdet = T(1) / determinant();
@@ -185,8 +205,17 @@ class Transform {
   void setIdentity() { m_.setIdentity(); }
   T& operator()(int i, int j) { return m_(i, j); }
   const T& operator()(int i, int j) const { return m_(i, j); }
+  static Transform Identity() { Transform t; t.setIdentity(); return t; }
   Matrix<T, Dim, Dim> rotation() const { return m_.template block<Dim, Dim>(0, 0); }
+  Matrix<T, Dim, Dim> linear() const { return rotation(); }
   Matrix<T, Dim, 1> translation() const { return m_.template block<Dim, 1>(0, Dim); }
+  Transform operator*(const Transform& o) const { Transform r; r.m_ = m_ * o.m_; return r; }
+  Transform inverse() const {   // rigid-body inverse (Affine mode with an orthonormal linear part)
+    Transform r; r.setIdentity();
+    for (int i = 0; i < Dim; ++i) for (int j = 0; j < Dim; ++j) r.m_(i, j) = m_(j, i);
+    for (int i = 0; i < Dim; ++i) { T s = T(0); for (int k = 0; k < Dim; ++k) s += m_(k, i) * m_(k, Dim); r.m_(i, Dim) = -s; }
+    return r;
+  }
   template <typename U> Transform<U, Dim, Mode> cast() const { Transform<U, Dim, Mode> t; t.matrix() = m_.template cast<U>(); return t; }
  private:
   MatrixType m_;

@@ -60,8 +60,12 @@ def test_batch_512_against_reference_numerics(engine, oracle):
     def flow(levels):
         return ([l["termination"] for l in levels], [l["num_iterations"] for l in levels])
 
-    dts, drs, info_err, ll_err = [], [], [], []
-    agree = {"gpu": {"term": 0, "it1": 0, "both": 0}, "mirror": {"term": 0, "it1": 0, "both": 0}}
+    def rel_info(a, b):
+        return float(np.linalg.norm(a - b) / np.linalg.norm(b))
+
+    dts, drs = [], []
+    err = {k: {"info": [], "ll": [], "info_same_flow": [], "ll_same_flow": [], "dt": []} for k in ("gpu", "mirror")}
+    agree = {"gpu": {"term": 0, "it1": 0, "both": 0, "exact": 0}, "mirror": {"term": 0, "it1": 0, "both": 0, "exact": 0}}
     for i in range(B):
         fa, mi = cpu_res[i]
         r = res[i]
@@ -70,31 +74,48 @@ def test_batch_512_against_reference_numerics(engine, oracle):
         assert [l["valid_pixels"] for l in r.levels] == [l["valid_pixels"] for l in fa["levels"]]
         assert not r.is_nan()
         dts.append(dt); drs.append(dr)
-        info_err.append(np.linalg.norm(r.information - fa["information"]) / np.linalg.norm(fa["information"]))
-        ll_err.append(abs(r.log_likelihood - fa["log_likelihood"]) / abs(fa["log_likelihood"]))
         ft, fi = flow(fa["levels"])
-        for name, (t, it) in (("gpu", flow(r.levels)), ("mirror", flow(mi["levels"]))):
+        cand = (("gpu", flow(r.levels), r.information, r.log_likelihood, r.transformation),
+                ("mirror", flow(mi["levels"]), mi["information"], mi["log_likelihood"], mi["T"]))
+        for name, (t, it), info, ll, T in cand:
             same_t = t == ft
             within1 = all(abs(a - b) <= 1 for a, b in zip(it, fi))
+            exact = same_t and it == fi
             agree[name]["term"] += same_t; agree[name]["it1"] += within1; agree[name]["both"] += same_t and within1
+            agree[name]["exact"] += exact
+            e_info, e_ll = rel_info(info, fa["information"]), abs(ll - fa["log_likelihood"]) / abs(fa["log_likelihood"])
+            err[name]["info"].append(e_info); err[name]["ll"].append(e_ll); err[name]["dt"].append(pose_delta(fa["T"], T)[0])
+            if exact:
+                err[name]["info_same_flow"].append(e_info); err[name]["ll_same_flow"].append(e_ll)
     rate = {k: {m: v / B for m, v in d.items()} for k, d in agree.items()}
+
+    def dist(v):
+        return {"median": _pct(v, 50), "p95": _pct(v, 95), "max": float(max(v))} if len(v) else None
+
     summary = {
         "pairs": B,
         "pose_dt_m": {"median": _pct(dts, 50), "p95": _pct(dts, 95), "p99": _pct(dts, 99), "max": max(dts)},
         "pose_dr_rad": {"median": _pct(drs, 50), "p95": _pct(drs, 95), "p99": _pct(drs, 99), "max": max(drs)},
-        "information_rel_frobenius": {"median": _pct(info_err, 50), "p95": _pct(info_err, 95), "max": max(info_err)},
-        "log_likelihood_rel": {"median": _pct(ll_err, 50), "p95": _pct(ll_err, 95), "max": max(ll_err)},
         "control_flow_vs_faithful": rate,
+        "vs_faithful": {k: {m: dist(v) for m, v in d.items()} for k, d in err.items()},
     }
     print("\nbatch-512 parity vs FAITHFUL:", json.dumps(summary))
     os.makedirs("gpurun_out", exist_ok=True)
     with open(os.path.join("gpurun_out", "batch512_parity.json"), "w") as f:
         json.dump(summary, f, indent=1)
-    # the CUDA path is as close to the reference's numerics as an independent IEEE restatement of the same algorithm
+    # the CUDA path is as close to the reference's numerics as an independent IEEE restatement of the same algorithm:
+    # control flow ...
     for m in ("term", "it1", "both"):
         assert rate["gpu"][m] >= rate["mirror"][m] - 0.05, (m, rate)
     assert rate["gpu"]["term"] >= 0.55 and rate["gpu"]["it1"] >= 0.35, rate
-    # where the control flow coincides the numbers coincide: medians far inside the tolerance
+    # ... and Result.Information / Result.LogLikelihood / pose (they depend on which iteration was the last one)
+    g, m = summary["vs_faithful"]["gpu"], summary["vs_faithful"]["mirror"]
+    for key in ("info", "ll", "dt"):
+        assert g[key]["median"] <= 1.25 * m[key]["median"] + 1e-6, (key, g[key], m[key])
+        assert g[key]["p95"] <= 1.25 * m[key]["p95"] + 1e-6, (key, g[key], m[key])
+    # pairs whose control flow is identical to FAITHFUL's: what is left is rounding
+    if g["info_same_flow"] is not None:
+        assert g["info_same_flow"]["median"] < 2e-3 and g["ll_same_flow"]["median"] < 1e-4, g
+    # typical agreement is far inside the tolerance
     assert summary["pose_dt_m"]["median"] < 5e-4 and summary["pose_dr_rad"]["median"] < 1e-4
     assert summary["pose_dt_m"]["p99"] < POSE_TOL_T and summary["pose_dr_rad"]["p99"] < POSE_TOL_R
-    assert summary["log_likelihood_rel"]["p95"] < 2e-2
