@@ -13,10 +13,14 @@ over one batch of synthetic frame pairs.  Workload at every N: 512 independent 6
            results on the host (D2H), every step
   roofline: the persistent per-level kernel k_level_persistent (both stages of every Gauss-Newton iteration), algorithmic
            40 B per pixel-iteration / their device time measured with CUDA events
-  cpu_baseline: the oracle's FAITHFUL restatement of the reference CPU path, match-only, on the
-           box's host cores (bounded sample)
-  --impl reference: the reference's CPU algorithm (oracle FAITHFUL port; the reference itself needs
-           Eigen/OpenCV/Sophus and cannot be built here) from host images: pyramid build + match.
+  cpu_baseline: the reference's CPU path, match-only, on the box's host cores (bounded sample).  kind
+           "reference" = every per-point pass (warp/residual, weights, scale, LL, normal equations) executed by
+           the reference's own SSE object code (oracle/_ref/libdvo_ref_O3.so: dense_tracking_impl.cpp,
+           core/math_sse.cpp, core/intrinsic_matrix.cpp compiled unmodified at the reference's -O3 -msse3; the
+           match() control flow around them is oracle/ref_driver.cpp).  kind "port" (fallback when oracle/_ref
+           is absent) = the oracle's scalar FAITHFUL restatement.
+  --impl reference: the same CPU implementation from host images (pyramid build + match), all host threads.
+  --config 5: BASELINE.json configs[4] (1280x960, 6 levels, mu = 0.05, 32 pairs per GPU = 256 over 8 GPUs).
 """
 from __future__ import annotations
 
@@ -37,9 +41,44 @@ import numpy as np  # noqa: E402
 
 W, H, LEVELS = 640, 480, 5
 FIRST_LEVEL, LAST_LEVEL, MAX_IT, PRECISION = 4, 0, 50, 1e-4   # benchmark.yaml:3-4 values, 5 levels
+MU = 0.0
 ALGO_BYTES_PER_PIXEL_ITERATION = 40.0
 LEVEL_PIXELS = [(W >> l) * (H >> l) for l in range(LEVELS)]
 METRIC = "frame-pair alignments/sec @640x480x5-level"
+DEFAULT_BATCH = 512
+
+
+def select_workload(config: int):
+    """configs[2]/[3] (default) or configs[4] of BASELINE.json; sets the module-level workload constants."""
+    global W, H, LEVELS, FIRST_LEVEL, MU, LEVEL_PIXELS, METRIC, DEFAULT_BATCH
+    if config == 5:
+        W, H, LEVELS, FIRST_LEVEL, MU, DEFAULT_BATCH = 1280, 960, 6, 5, 0.05, 32
+        METRIC = "frame-pair alignments/sec @1280x960x6-level"
+    elif config not in (0, 2, 3, 4):
+        raise SystemExit(f"unknown --config {config} (2/3 = 640x480x5 batch 512 per GPU [default], 5 = 1280x960x6 mu=0.05 batch 32 per GPU)")
+    LEVEL_PIXELS = [(W >> l) * (H >> l) for l in range(LEVELS)]
+
+
+def scene_config():
+    """640x480: fr1 intrinsics; 1280x960 = the same camera upsampled 2x (configs[4]: "upsampled TUM fr1")."""
+    from dvo_slam_b200 import synth
+    if W == 640:
+        return synth.SceneConfig()
+    f = W / 640.0
+    fx, fy, ox, oy = synth.FR1_INTRINSICS
+    return synth.SceneConfig(width=W, height=H, intrinsics=(fx * f, fy * f, ox * f + (f - 1) / 2, oy * f + (f - 1) / 2))
+
+
+def source_stamp() -> str:
+    """sha256 over the CUDA sources the level kernel is built from: ties a profile to a build."""
+    import glob
+    import hashlib
+    h = hashlib.sha256()
+    for p in sorted(glob.glob(os.path.join(ROOT, "dvo_slam_b200", "csrc", "*"))):
+        if p.endswith((".cu", ".cuh", ".h")):
+            h.update(os.path.basename(p).encode())
+            h.update(open(p, "rb").read())
+    return h.hexdigest()[:16]
 
 
 def parse_args():
@@ -48,7 +87,8 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=512, help="frame pairs per GPU")
+    ap.add_argument("--batch", type=int, default=0, help="frame pairs per GPU (0 = the workload's default: 512, or 32 for --config 5)")
+    ap.add_argument("--config", type=int, default=2, help="BASELINE.json configs index + 1 style: 2/3 = 640x480x5 (default), 5 = 1280x960x6 mu=0.05")
     ap.add_argument("--cpu-sample", type=int, default=0, help="pairs in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -112,16 +152,43 @@ def usable_cores() -> int:
 # ---------------------------------------------------------------------------------------------
 # CPU arm (oracle = test infrastructure; only this leg of bench.py may execute it)
 # ---------------------------------------------------------------------------------------------
+def cpu_kind():
+    """("reference", variant) when the reference's compiled translation units are present, else ("port", None)."""
+    from oracle import oracle_py as orc
+    for variant in ("_O3", ""):
+        if orc.ref_available(variant):
+            return "reference", variant
+    return "port", None
+
+
+def cpu_kind_text(kind, variant):
+    if kind == "reference":
+        return ("reference SSE object code (oracle/_ref/libdvo_ref%s.so = dense_tracking_impl.cpp + core/math_sse.cpp + "
+                "core/intrinsic_matrix.cpp compiled unmodified, %s) for every per-point pass; match() control flow, LDLT and "
+                "SE(3) from oracle/ref_driver.cpp; pyramids from the oracle port" % (variant, "-O3 -msse3" if variant == "_O3" else "-O2 -msse3"))
+    return "oracle scalar FAITHFUL port (oracle/_ref absent)"
+
+
 def cpu_alignments(pairs, include_pyramid: bool, threads: int):
-    """Runs the oracle FAITHFUL match on `pairs` with `threads` host threads; returns (seconds, n)."""
+    """Runs DenseTracker::match on `pairs` with `threads` host threads through the reference's object code
+    (oracle/_ref) when present, else the oracle FAITHFUL port; returns (seconds, n)."""
     from oracle import oracle_py as orc
     orc.lib()
     K = pairs[0]["intrinsics"]
-    cfg = orc.config(first_level=FIRST_LEVEL, last_level=LAST_LEVEL, max_iterations_per_level=MAX_IT, precision=PRECISION)
+    cfg = orc.config(first_level=FIRST_LEVEL, last_level=LAST_LEVEL, max_iterations_per_level=MAX_IT, precision=PRECISION, mu=MU)
     mode = orc.mode("faithful")
+    kind, variant = cpu_kind()
+
+    def pyramids(p):
+        r = orc.Pyramid(p["I_ref"], p["Z_ref"], K, LEVELS)
+        c = orc.Pyramid(p["I_cur"], p["Z_cur"], K, LEVELS)
+        if kind == "reference":
+            return orc.RefPyramid(r, variant), orc.RefPyramid(c, variant)
+        return r, c
+
     prebuilt = None
     if not include_pyramid:
-        prebuilt = [(orc.Pyramid(p["I_ref"], p["Z_ref"], K, LEVELS), orc.Pyramid(p["I_cur"], p["Z_cur"], K, LEVELS)) for p in pairs]
+        prebuilt = [pyramids(p) for p in pairs]
     idx = list(range(len(pairs)))
     lock = threading.Lock()
 
@@ -131,12 +198,11 @@ def cpu_alignments(pairs, include_pyramid: bool, threads: int):
                 if not idx:
                     return
                 i = idx.pop()
-            if include_pyramid:
-                r = orc.Pyramid(pairs[i]["I_ref"], pairs[i]["Z_ref"], K, LEVELS)
-                c = orc.Pyramid(pairs[i]["I_cur"], pairs[i]["Z_cur"], K, LEVELS)
+            r, c = pyramids(pairs[i]) if include_pyramid else prebuilt[i]
+            if kind == "reference":
+                orc.ref_match(r, c, cfg)
             else:
-                r, c = prebuilt[i]
-            orc.match(r, c, cfg, mode, max_iters=8)
+                orc.match(r, c, cfg, mode, max_iters=8)
 
     t0 = time.perf_counter()
     ths = [threading.Thread(target=worker) for _ in range(threads)]
@@ -151,13 +217,13 @@ def host_pairs(seeds, device="cpu"):
     from dvo_slam_b200 import synth
     out = []
     for s in seeds:
-        p = synth.make_pair(s, device=device)
+        p = synth.make_pair(s, scene_config(), device=device)
         out.append({k: (v.cpu().numpy() if hasattr(v, "cpu") else v) for k, v in p.items()})
     return out
 
 
 def run_reference(args, rank, world):
-    """Reference arm: the reference's CPU algorithm on the host cores (oracle FAITHFUL port)."""
+    """Reference arm: the reference's CPU implementation of the path on the host cores (see cpu_kind_text)."""
     if rank != 0:
         return
     cores = usable_cores()
@@ -178,15 +244,19 @@ def run_reference(args, rank, world):
         t_total += t
         n_total += n
     value = n_total / t_total
-    sample = f"{per_step} pairs/step x {args.steps} steps, oracle FAITHFUL, pyramid build + match from host images, {cores} threads"
+    kind, variant = cpu_kind()
+    sample = f"{per_step} pairs/step x {args.steps} steps, pyramid build + match from host images, {cores} threads; {cpu_kind_text(kind, variant)}"
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "alignments/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{per_step}-pair sample of the batch={args.batch}/GPU 640x480 5-level workload",
-                       "first_level": FIRST_LEVEL, "last_level": LAST_LEVEL, "max_iterations_per_level": MAX_IT, "precision": PRECISION},
-            "cpu_baseline": {"value": value, "unit": "alignments/s", "cores": cores, "kind": "port", "sample": sample},
+            "config": {"workload": f"{per_step}-pair sample of the batch={args.batch or DEFAULT_BATCH}/GPU {W}x{H} {LEVELS}-level workload",
+                       "first_level": FIRST_LEVEL, "last_level": LAST_LEVEL, "max_iterations_per_level": MAX_IT, "precision": PRECISION,
+                       "mu": MU},
+            "cpu_baseline": {"value": value, "unit": "alignments/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": "alignments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "note": "reference sources need Eigen3/OpenCV2/Sophus (absent here): timed arm is the oracle's FAITHFUL port"}
+            "note": "the reference's build system needs Eigen3/OpenCV2/Sophus/ROS (absent here); its hot-path translation units "
+                    "compile unmodified against header-only container shims (oracle/ref_shim) and are what this arm executes"
+                    if kind == "reference" else "oracle/_ref absent: timed arm is the oracle's scalar FAITHFUL port"}
     print(json.dumps(line))
 
 
@@ -197,25 +267,25 @@ def run_ours(args, rank, local_rank, world):
     import torch
     import torch.distributed as dist
     from dvo_slam_b200 import synth
-    from dvo_slam_b200.distributed import all_gather_results, results_to_tensor
+    from dvo_slam_b200.distributed import tensor_to_results
     from dvo_slam_b200.engine import Config, Engine, CResult
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl ours needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    B = args.batch
+    B = args.batch or DEFAULT_BATCH
     total = B * world
     eng = Engine(device=local_rank)
     stream = torch.cuda.ExternalStream(eng.stream, device=dev)
-    cfg = Config(first_level=FIRST_LEVEL, last_level=LAST_LEVEL, max_iterations_per_level=MAX_IT, precision=PRECISION)
-    K = synth.FR1_INTRINSICS
+    cfg = Config(first_level=FIRST_LEVEL, last_level=LAST_LEVEL, max_iterations_per_level=MAX_IT, precision=PRECISION, mu=MU)
+    scfg = scene_config()
+    K = scfg.intrinsics
 
     # ---- synthetic batch: distinct seeded pairs, rendered on the GPU, kept in pinned host memory ----
     npx = W * H
     hI = torch.empty((2 * B, H, W), dtype=torch.float32).pin_memory()
     hZ = torch.empty((2 * B, H, W), dtype=torch.float32).pin_memory()
-    scfg = synth.SceneConfig()
     for i in range(B):
         p = synth.make_pair(rank * B + i, scfg, device=dev)
         hI[i].copy_(p["I_ref"]); hZ[i].copy_(p["Z_ref"])
@@ -262,8 +332,24 @@ def run_ours(args, rank, local_rank, world):
 
     last = {}
 
+    # N > 1: the one exchange of the path -- an all-gather of the fixed-size result records -- is part of every step:
+    # results are written to device memory (dvo_b200_match_batch_device), gathered over NCCL on the engine's
+    # stream, and the gathered table is read back to the host (what dvo_slam's single-process callers consume).
+    if world > 1:
+        d_local = torch.zeros((B, C.sizeof(CResult)), dtype=torch.uint8, device=dev)
+        d_all = torch.zeros((total, C.sizeof(CResult)), dtype=torch.uint8, device=dev)
+        h_all = torch.zeros((total, C.sizeof(CResult)), dtype=torch.uint8).pin_memory()
+
     def step_resident():
-        last["res"] = eng.match_batch(refs, curs, cfg, raw=True)
+        if world == 1:
+            last["res"] = eng.match_batch(refs, curs, cfg, raw=True)
+            return
+        eng.match_batch_device(refs, curs, cfg, d_local.data_ptr())
+        with torch.cuda.stream(stream):
+            dist.all_gather_into_tensor(d_all, d_local)
+            h_all.copy_(d_all, non_blocking=True)
+        eng.synchronize()
+        last["gathered"] = h_all
 
     # e2e: every step goes host images (8-bit grey, 16-bit raw depth, pinned) -> dvo_b200_pyramid_create_raw_batch
     # -> dvo_b200_match_batch -> host results through the public C ABI.  A double-buffered front end on two host
@@ -315,7 +401,11 @@ def run_ours(args, rank, local_rank, world):
     value = total / (ms_per_step * 1e-3)
 
     # pixel-iterations actually executed in one step on this rank (from the results' statistics)
-    res = last["res"]
+    if world > 1:
+        assert last["gathered"].shape[0] == total
+        res = tensor_to_results(last["gathered"][rank * B:(rank + 1) * B])
+    else:
+        res = last["res"]
     pix_iters = 0
     it_hist = [0] * LEVELS
     for i in range(B):
@@ -334,14 +424,22 @@ def run_ours(args, rank, local_rank, world):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = algo_bytes / (stage_ms * 1e-3) / 1e9 if stage_ms > 0 else 0.0
-    # DRAM traffic of the dominant launch from the committed `ncu --set full` capture (profiles/), if present
+    # DRAM traffic of the dominant launch from the committed `ncu --set full` capture of THIS build (profiles/,
+    # regenerated by scripts/gpu_ncu.sh + scripts/make_traffic_json.py, which stamps the hash of the CUDA sources);
+    # a capture of another build is reported as stale and not used
     traffic, traffic_note = None, None
-    try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
-            tj = json.load(f)
-        traffic, traffic_note = tj["dram_bytes_per_step"] / tj["launches_per_step"], tj["note"]
-    except Exception:
-        pass
+    if W == 640 and B == 512:
+        try:
+            with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
+                tj = json.load(f)
+            if tj.get("source_stamp") == source_stamp():
+                traffic, traffic_note = tj["dram_bytes_per_step"] / tj["launches_per_step"], tj["note"]
+            else:
+                traffic_note = "stale: profiles/r02_traffic.json was captured from sources %s, this build is %s" % (tj.get("source_stamp"), source_stamp())
+        except Exception as e:
+            traffic_note = f"no capture: {e}"
+    else:
+        traffic_note = "capture exists for the default workload only"
 
     # ---- e2e: host buffers in, host results out, every step ----
     run_e2e(max(2, min(args.warmup, 4)))
@@ -366,10 +464,6 @@ def run_ours(args, rank, local_rank, world):
     if not worst < 2e-3:
         raise SystemExit(f"e2e leg disagrees with the resident leg: max |dT| = {worst}")
 
-    # ---- result gather (one all-gather of fixed-size records, outside the iteration loop) ----
-    gathered = all_gather_results(results_to_tensor(res, dev), total)
-    assert gathered.shape[0] == total
-
     # ---- single-pair latency (configs[1]) ----
     lat_ms = None
     if rank == 0:
@@ -380,7 +474,7 @@ def run_ours(args, rank, local_rank, world):
             eng.match_batch(refs[:1], curs[:1], cfg, raw=True)
         lat_ms = (time.perf_counter() - t0) / 10 * 1e3
 
-    # ---- CPU baseline: oracle FAITHFUL, match only, bounded sample (rank 0, N=1 only) ----
+    # ---- CPU baseline: the reference's CPU path, match only, bounded sample (rank 0, N=1 only) ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = usable_cores()
@@ -389,18 +483,20 @@ def run_ours(args, rank, local_rank, world):
                "intrinsics": K} for i in range(min(nsample, B))]
         t1, n1 = cpu_alignments(hp[: max(2, min(8, len(hp)))], False, 1)
         tc, nc = cpu_alignments(hp, False, cores)
-        cpu = {"value": nc / tc, "unit": "alignments/s", "cores": cores, "kind": "port",
-               "sample": f"first {len(hp)} pairs of the batch, oracle FAITHFUL match() on prebuilt pyramids, {cores} threads",
+        kind, variant = cpu_kind()
+        cpu = {"value": nc / tc, "unit": "alignments/s", "cores": cores, "kind": kind,
+               "sample": f"first {len(hp)} pairs of the batch, match() on prebuilt pyramids, {cores} threads; {cpu_kind_text(kind, variant)}",
                "value_1core": n1 / t1}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "alignments/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
-                "config": {"workload": f"batch={B} independent 640x480 frame pairs per GPU, 5-level pyramid (FirstLevel=4, LastLevel=0)",
-                           "global_batch": total, "max_iterations_per_level": MAX_IT, "precision": PRECISION, "mu": 0.0,
-                           "parallelism": f"pairs sharded over {world} GPU(s), no data-path collective, one result all-gather",
-                           "l2": "inputs larger than L2: %.1f GB of pyramids per GPU" % (2 * B * sum(LEVEL_PIXELS) * 24 / 1e9),
+                "config": {"workload": f"batch={B} independent {W}x{H} frame pairs per GPU, {LEVELS}-level pyramid (FirstLevel={FIRST_LEVEL}, LastLevel=0)",
+                           "global_batch": total, "max_iterations_per_level": MAX_IT, "precision": PRECISION, "mu": MU,
+                           "parallelism": f"pairs sharded over {world} GPU(s), no collective inside the alignments; one NCCL all-gather of the "
+                                          f"result records per step" + (", inside the timed region" if world > 1 else " (N=1: none)"),
+                           "l2": "inputs larger than L2: %.1f GB of pyramids per GPU" % (2 * B * sum(LEVEL_PIXELS) * 32 / 1e9),
                            "iterations_per_level_mean": [it_hist[l] / B for l in range(LEVELS)]},
                 "e2e": {"value": e2e_value, "unit": "alignments/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d_per_step,
                         "d2h_bytes_per_step": d2h_per_step, "h2d_bytes_counted": h2d_meas, "d2h_bytes_counted": d2h_meas,
@@ -408,7 +504,9 @@ def run_ours(args, rank, local_rank, world):
                         "timer": "host clock between device synchronisations, max over ranks"},
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
-                             "traffic": traffic, "traffic_note": traffic_note, "kernel": "k_level_persistent (one launch per pyramid level: warp+residual+weight+scale, LL+J^T W J, on-device solve)",
+                             "traffic": traffic, "traffic_note": traffic_note, "kernel": "k_level_persistent (persistent cooperative kernel; one launch per level group: coarse levels walked in one launch, "
+                                       "fine levels in another; bulk-copy staged tiles, warp+residual+weight+scale, LL+J^T W J, on-device solve)",
+                             "source_stamp": source_stamp(),
                              "algorithmic_bytes_per_step": algo_bytes, "kernel_ms_per_step": stage_ms,
                              "algorithmic_bytes_per_launch": algo_bytes / stage_launches if stage_launches else None,
                              "kernel_ms_per_launch": stage_ms / stage_launches if stage_launches else None,
@@ -422,6 +520,7 @@ def run_ours(args, rank, local_rank, world):
 
 def main():
     args = parse_args()
+    select_workload(args.config)
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -258,16 +258,17 @@ int dvo_b200_pyramid_level_info(const dvo_b200_pyramid* p, int32_t level, int32_
 }
 
 int dvo_b200_pyramid_download(dvo_b200_ctx* ctx, const dvo_b200_pyramid* p, int32_t level, float* planes6) {
-  if (!ctx || !p || !planes6 || level < 0 || level >= p->levels)
+  if (!p || !planes6 || level < 0 || level >= p->levels)
     return set_error(ctx, DVO_B200_ERR_INVALID_ARGUMENT, "pyramid_download: invalid argument");
-  cudaSetDevice(ctx->device);
+  cudaSetDevice(ctx ? ctx->device : (p->slab && p->slab->pool ? p->slab->pool->device : 0));
   const LevelInfo& L = p->L[level];
   size_t N = L.n;
   const size_t plane = (size_t)L.pitch * L.h;      // float2 elements per plane, rows padded to the pitch
   std::vector<float> tmp(6 * plane);
-  DVO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (ctx) DVO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (p->slab && p->slab->ready) DVO_CUDA(ctx, cudaEventSynchronize(p->slab->ready));   // the pyramid's own build has finished
   DVO_CUDA(ctx, cudaMemcpy(tmp.data(), p->planes + L.plane_off, sizeof(float) * 6 * plane, cudaMemcpyDeviceToHost));
-  ctx->d2h_bytes += sizeof(float) * 6 * plane;
+  if (ctx) ctx->d2h_bytes += sizeof(float) * 6 * plane;
   // device planes: P0 = (I, Z'), P1 = (Ix, Iy), P2 = (I, Z).  The depth gradients are not stored (the tracker forms
   // them from P2 on the fly): restate calculateDerivativeX/Y<float> on the true depth (rgbd_image.cpp:419-472).
   auto Zt = [&](int y, int x) { return tmp[4 * plane + 2 * ((size_t)y * L.pitch + x) + 1]; };

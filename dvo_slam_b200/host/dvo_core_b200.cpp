@@ -71,14 +71,15 @@ dvo_b200_pyramid* RgbdImagePyramid::device(dvo_b200_ctx* ctx, size_t levels) {
 
 RgbdImage& RgbdImagePyramid::level(size_t idx) {
   if (idx < levels_.size() && (idx == 0 || levels_[idx]->hasIntensity())) return *levels_[idx];
-  if (!device_ || !device_ctx_ || device_levels_ <= idx)
+  if (!device_ || device_levels_ <= idx)
     throw std::runtime_error("RgbdImagePyramid::level: level not built (call build/compute and match first)");
   while (levels_.size() <= idx) levels_.push_back(camera_.level(levels_.size()).create());
   int w = 0, h = 0;
   float K[4];
   dvo_b200_pyramid_level_info(device_, int(idx), &w, &h, K);
   std::vector<float> planes(size_t(6) * w * h);
-  if (dvo_b200_pyramid_download(device_ctx_, device_, int(idx), planes.data()) != 0)
+  // no context: the pyramid may be read after the tracker (and context) that uploaded it is gone
+  if (dvo_b200_pyramid_download(nullptr, device_, int(idx), planes.data()) != 0)
     throw std::runtime_error("dvo_b200_pyramid_download failed");
   RgbdImage& img = *levels_[idx];
   cv::Mat* dst[6] = {&img.intensity, &img.depth, &img.intensity_dx, &img.intensity_dy, &img.depth_dx, &img.depth_dy};

@@ -217,6 +217,7 @@ int main(int argc, char** argv) {
 
   // first pose: closest ground-truth entry at or after the first RGB stamp (findClosestEntry, tools.h:68-82)
   dvo::core::AffineTransformd trajectory;
+  trajectory.setIdentity();          // benchmark.cpp:399: identity unless ground truth provides the first pose
   size_t gt_first = 0;
   if (!gt.empty()) {
     while (gt_first + 1 < gt.size() && gt[gt_first].stamp < pairs.front().rgb_stamp) ++gt_first;

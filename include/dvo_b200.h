@@ -145,7 +145,9 @@ int dvo_b200_pyramid_num_levels(const dvo_b200_pyramid* p);
 int dvo_b200_pyramid_level_info(const dvo_b200_pyramid* p, int32_t level, int32_t* width, int32_t* height, float K[4]);
 /* Debug/test read-back of one level: 6 planes (I, Z, Ix, Iy, Zx, Zy) of h*w floats into host memory.
  * Z is the tracker's masked depth: NaN wherever the reference would reject the pixel as a bilinear
- * tap or as a reference point (any of I,Z,Ix,Iy,Zx,Zy NaN).  Synchronises. */
+ * tap or as a reference point (any of I,Z,Ix,Iy,Zx,Zy NaN).  Synchronises.  ctx may be NULL: pyramids are shared objects
+ * that can outlive the context that built them (boost::shared_ptr<RgbdImagePyramid>); the read then waits for the
+ * pyramid's own build to finish and uses no context at all. */
 int dvo_b200_pyramid_download(dvo_b200_ctx* ctx, const dvo_b200_pyramid* p, int32_t level, float* planes6);
 /* PointSelection::select result (point_selection.cpp:89-152) for the given thresholds: number of
  * selected points S and (optional) h*w byte mask.  Synchronises. */

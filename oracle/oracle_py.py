@@ -261,8 +261,52 @@ def ref_lib(variant: str = ""):
         L.ref_linearize.restype = C.c_int64
         L.ref_linearize.argtypes = [fp, fp, C.c_int, C.c_int, fp, dp, C.c_float, C.c_float, C.c_int, fp, C.POINTER(C.c_int64), fp,
                                     C.POINTER(C.c_int32), fp, fp, fp, fp, fp, fp]
+        L.ref_pyramid_create.restype = C.c_void_p
+        L.ref_pyramid_create.argtypes = [C.c_int, C.POINTER(fp), C.POINTER(C.c_int), C.POINTER(C.c_int), fp]
+        L.ref_pyramid_destroy.argtypes = [C.c_void_p]
+        L.ref_match.restype = C.c_int
+        L.ref_match.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, dp, C.c_float,
+                                C.c_float, dp, dp, dp, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int64)]
         _ref[variant] = L
     return _ref[variant]
+
+
+class RefPyramid:
+    """The reference's image model for one frame (acceleration images + cached point lists), filled from the planes of an
+    oracle Pyramid (the pyramid / derivative code of the reference needs OpenCV proper and is not compiled)."""
+
+    def __init__(self, pyr: "Pyramid", variant: str = ""):
+        self.variant = variant
+        n = pyr.levels
+        self._planes = [np.ascontiguousarray(pyr.planes(l)) for l in range(n)]
+        info = [pyr.level_info(l) for l in range(n)]
+        w = (C.c_int * n)(*[i[0] for i in info]); h = (C.c_int * n)(*[i[1] for i in info])
+        K = np.ascontiguousarray(np.array([i[2] for i in info], dtype=np.float32).reshape(-1))
+        ptrs = (C.POINTER(C.c_float) * n)(*[_fptr(p) for p in self._planes])
+        self.h = ref_lib(variant).ref_pyramid_create(n, ptrs, w, h, _fptr(K))
+        self.levels = n
+
+    def __del__(self):
+        h, self.h = getattr(self, "h", None), None
+        if h and self.variant in _ref:
+            try:
+                _ref[self.variant].ref_pyramid_destroy(h)
+            except Exception:
+                pass
+
+
+def ref_match(ref: RefPyramid, cur: RefPyramid, cfg: Config, T_init=None):
+    """DenseTracker::match() with every per-point pass run by the reference's own object code (oracle/ref_driver.cpp)."""
+    T0 = np.ascontiguousarray(np.asarray(T_init if T_init is not None else np.eye(4), dtype=np.float64).reshape(16))
+    nl = cfg.first_level - cfg.last_level + 1
+    T = np.zeros(16); info = np.zeros(36); ll = C.c_double()
+    term = (C.c_int32 * nl)(); its = (C.c_int32 * nl)(); vp = (C.c_int64 * nl)()
+    rc = ref_lib(ref.variant).ref_match(ref.h, cur.h, cfg.first_level, cfg.last_level, cfg.max_iterations_per_level, cfg.precision, cfg.mu,
+                                        cfg.use_initial_estimate, _dptr(T0), cfg.intensity_derivative_threshold,
+                                        cfg.depth_derivative_threshold, _dptr(T), _dptr(info), C.byref(ll), term, its, vp)
+    assert rc == 0
+    levels = [{"id": cfg.first_level - i, "termination": term[i], "num_iterations": its[i], "valid_pixels": vp[i]} for i in range(nl)]
+    return {"T": T.reshape(4, 4), "information": info.reshape(6, 6), "log_likelihood": ll.value, "levels": levels}
 
 
 def ref_linearize(ref_planes6, cur_planes6, K, T, use_weights=False, prev_precision=None, ti=0.0, td=0.0, variant=""):

@@ -154,4 +154,229 @@ int64_t ref_linearize(const float* ref_planes6, const float* cur_planes6, int w,
   return (int64_t)n;
 }
 
+
+// ---- whole alignments through the reference's object code ----------------------------------------------------------------
+// ref_match() is DenseTracker::match() (dense_tracking.cpp:131-376) with every per-point pass executed by the reference's
+// own compiled functions and data structures (no conversions inside the loop): the control flow, the Revertable poses and the
+// statistics are restated here (dense_tracking.cpp itself needs Sophus); SE(3) exp/log and the 6x6 LDL^T come from the
+// oracle (orc_se3_exp / orc_se3_log / orc_ldlt_solve6, which restate Sophus / Eigen).  Used as the CPU baseline of bench.py
+// (kind "reference") and by tests/test_reference_pin.py (control flow and pose equal to the oracle's FAITHFUL mode).
+void orc_se3_exp(const double xi[6], double T[16]);
+void orc_se3_log(const double T[16], double xi[6]);
+void orc_ldlt_solve6(const double A[36], const double b[6], double x[6]);
+
+}  // extern "C"
+
+namespace {
+
+struct RefLevel {
+  int w = 0, h = 0;
+  IntrinsicMatrix K;
+  RgbdCamera* camera = nullptr;
+  RgbdImage* image = nullptr;                         // carries the acceleration image (rgbd_image.cpp:534-543)
+  std::vector<float> depth;                           // for the point cloud of the reference role
+  PointWithIntensityAndDepth::VectorType points;      // PointSelection's cached list (point_selection.cpp:100-113)
+  float ti = -1.f, td = -1.f;
+  bool have_points = false;
+};
+struct RefPyramid {
+  std::vector<RefLevel> levels;
+  ~RefPyramid() { for (RefLevel& l : levels) { delete l.image; delete l.camera; } }
+};
+
+void select_points(RefLevel& L, float ti, float td) {
+  if (L.have_points && L.ti == ti && L.td == td) return;
+  ValidPointAndGradientThresholdPredicate predicate;
+  predicate.intensity_threshold = ti; predicate.depth_threshold = td;
+  L.points.clear();
+  const float* accel = L.image->acceleration.ptr<float>(0);
+  size_t idx = 0;
+  for (size_t y = 0; y < (size_t)L.h; ++y)
+    for (size_t x = 0; x < (size_t)L.w; ++x, ++idx) {
+      const float tx = (x - L.K.ox()) / L.K.fx(), ty = (y - L.K.oy()) / L.K.fy();   // rgbd_image.cpp:197-198
+      const float depth = L.depth[idx];
+      PointWithIntensityAndDepth p;
+      p.point.data[0] = tx * depth; p.point.data[1] = ty * depth; p.point.data[2] = 1.0f * depth; p.point.data[3] = 1.0f;   // :258-259
+      std::memcpy(p.intensity_and_depth.data, accel + 8 * idx, sizeof(float) * 8);
+      if (predicate.isPointOk(x, y, p.point.z, p.intensity_and_depth.idx, p.intensity_and_depth.idy, p.intensity_and_depth.zdx, p.intensity_and_depth.zdy))
+        L.points.push_back(p);
+    }
+  L.ti = ti; L.td = td; L.have_points = true;
+}
+
+// rigid 4x4 (row-major double) helpers
+void mat_mul(const double A[16], const double B[16], double C[16]) {
+  for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) { double s = 0; for (int k = 0; k < 4; ++k) s += A[i * 4 + k] * B[k * 4 + j]; C[i * 4 + j] = s; }
+}
+void mat_inv(const double A[16], double B[16]) {
+  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) B[i * 4 + j] = A[j * 4 + i];
+  for (int i = 0; i < 3; ++i) { double s = 0; for (int k = 0; k < 3; ++k) s += A[k * 4 + i] * A[k * 4 + 3]; B[i * 4 + 3] = -s; }
+  B[12] = B[13] = B[14] = 0; B[15] = 1;
+}
+void mat_identity(double A[16]) { for (int i = 0; i < 16; ++i) A[i] = (i % 5 == 0) ? 1.0 : 0.0; }
+
+}  // namespace
+
+extern "C" {
+
+void* ref_pyramid_create(int nlevels, const float* const* planes6, const int* w, const int* h, const float* K4) {
+  RefPyramid* P = new RefPyramid;
+  P->levels.resize(nlevels);
+  for (int l = 0; l < nlevels; ++l) {
+    RefLevel& L = P->levels[l];
+    L.w = w[l]; L.h = h[l];
+    L.K = IntrinsicMatrix::create(K4[4 * l], K4[4 * l + 1], K4[4 * l + 2], K4[4 * l + 3]);
+    L.camera = new RgbdCamera(L.w, L.h, L.K);
+    L.image = new RgbdImage(*L.camera);
+    L.image->width = L.w; L.image->height = L.h;
+    const size_t N = (size_t)L.w * L.h;
+    L.image->acceleration = cv::Mat_<RgbdImage::Vec8f>(L.h, L.w);
+    float* a = L.image->acceleration.ptr<float>(0);
+    for (size_t i = 0; i < N; ++i) {
+      for (int c = 0; c < 6; ++c) a[8 * i + c] = planes6[l][c * N + i];
+      a[8 * i + 6] = 0.f; a[8 * i + 7] = 0.f;
+    }
+    L.depth.assign(planes6[l] + N, planes6[l] + 2 * N);
+  }
+  return P;
+}
+void ref_pyramid_destroy(void* p) { delete static_cast<RefPyramid*>(p); }
+
+// termination codes as dvo::DenseTracker::TerminationCriteria (dense_tracking.h:71-81):
+// 0 IterationsExceeded, 1 IncrementTooSmall, 2 LogLikelihoodDecreased, 3 TooFewConstraints
+int ref_match(void* ref_p, void* cur_p, int first_level, int last_level, int max_iterations, double precision_cfg, double mu,
+              int use_initial_estimate, const double* T_init, float ti, float td, double T_out[16], double info_out[36],
+              double* ll_out, int32_t* termination, int32_t* num_iterations, int64_t* valid_pixels) {
+  RefPyramid& ref = *static_cast<RefPyramid*>(ref_p);
+  RefPyramid& cur = *static_cast<RefPyramid*>(cur_p);
+  // DenseTracker members (dense_tracking.cpp:160-165)
+  static thread_local PointWithIntensityAndDepth::VectorType points_error;
+  static thread_local dvo::DenseTracker::ResidualVectorType residuals;
+  static thread_local dvo::DenseTracker::WeightVectorType weights;
+
+  double inc[16], initial[16], initial_old[16], estimate[16], estimate_old[16];
+  if (use_initial_estimate && T_init) std::memcpy(inc, T_init, sizeof(inc)); else mat_identity(inc);       // :137-147
+  std::memcpy(initial, inc, sizeof(inc)); std::memcpy(initial_old, inc, sizeof(inc));
+  mat_identity(estimate); mat_identity(estimate_old);
+  bool accept = true;
+  const double kNaN = std::numeric_limits<double>::quiet_NaN();
+  double A_last[36], A_prev[36], nll_last = kNaN, nll_prev = kNaN, prior_last = 0, prior_prev = 0;
+  int have = 0;       // completed iterations recorded on the last level (0, 1, 2+)
+  int li = 0, last_termination = -1, last_level_iterations = 0;
+  for (int level = first_level; level >= last_level; --level, ++li) {
+    RefLevel& R = ref.levels[level];
+    RefLevel& C = cur.levels[level];
+    Eigen::Vector2f mean; mean.setZero();
+    Eigen::Matrix2f precision; precision.setZero();                                  // :205-206
+    int iteration = 0;
+    double error = std::numeric_limits<double>::max(), last_error = error;
+    select_points(R, ti, td);                                                        // :225
+    valid_pixels[li] = (int64_t)R.points.size();
+    if (points_error.size() < R.points.size() + 2) { points_error.resize(R.points.size() + 2); residuals.resize(R.points.size() + 2); weights.resize(R.points.size() + 2); }
+    Vector8f wcur, wref;                                                             // :215-220
+    float wcur_id = 0.5f, wref_id = 0.5f, wcur_zd = 1.0f, wref_zd = 0.0f;
+    const IntrinsicMatrix& K = C.K;
+    wcur <<  1.0f / 255.0f,  1.0f, wcur_id * K.fx() / 255.0f, wcur_id * K.fy() / 255.0f, wcur_zd * K.fx(), wcur_zd * K.fy(), 0.0f, 0.0f;
+    wref << -1.0f / 255.0f, -1.0f, wref_id * K.fx() / 255.0f, wref_id * K.fy() / 255.0f, wref_zd * K.fx(), wref_zd * K.fy(), 0.0f, 0.0f;
+    double x[6];
+    orc_se3_log(inc, x);                                                             // :238
+    int term = -1, recorded = 0;
+    have = 0;
+    do {
+      orc_se3_exp(x, inc);                                                           // :259
+      double inv[16], tmp[16];
+      mat_inv(inc, inv);
+      std::memcpy(initial_old, initial, sizeof(initial)); mat_mul(inv, initial, tmp); std::memcpy(initial, tmp, sizeof(tmp));      // :260
+      std::memcpy(estimate_old, estimate, sizeof(estimate)); mat_mul(inc, estimate, tmp); std::memcpy(estimate, tmp, sizeof(tmp));   // :261
+      Eigen::Affine3f transformf;
+      for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) transformf(i, j) = (float)estimate[i * 4 + j];                        // :263
+      ComputeResidualsResult rr;
+      rr.first_point_error = points_error.begin();
+      rr.first_residual = residuals.begin();
+      computeResidualsSse(R.points.begin(), R.points.end(), *C.image, K, transformf, wref, wcur, rr);                               // :271
+      const size_t n = rr.last_residual - rr.first_residual;
+      ++recorded;
+      if (n < 6) {                                                                   // :276-284
+        std::memcpy(initial, initial_old, sizeof(initial)); std::memcpy(estimate, estimate_old, sizeof(estimate));
+        term = 3;
+        break;
+      }
+      if (iteration == 0) std::fill(weights.begin(), weights.begin() + n, 1.0f);    // :286-293
+      else computeWeightsSse(rr.first_residual, rr.last_residual, weights.begin(), mean, precision);
+      precision = computeScaleSse(rr.first_residual, rr.last_residual, weights.begin(), mean).inverse();                           // :295
+      const float ll = computeCompleteDataLogLikelihood(rr.first_residual, rr.last_residual, weights.begin(), mean, precision);     // :297
+      double li6[6];
+      orc_se3_log(initial, li6);
+      double sq = 0;
+      for (int i = 0; i < 6; ++i) sq += li6[i] * li6[i];
+      const double prior = mu * sq;                                                  // :302
+      last_error = error;                                                            // :306-307
+      error = -(double)ll;
+      accept = error < last_error;                                                   // :312
+      if (!accept) {
+        std::memcpy(initial, initial_old, sizeof(initial)); std::memcpy(estimate, estimate_old, sizeof(estimate));
+        term = 2;
+        break;
+      }
+      // :327-343
+      OptimizedSelfAdjointMatrix6x6f A_opt;
+      A_opt.setZero();
+      Vector6 b; b.setZero();
+      dvo::DenseTracker::WeightVectorType::iterator w_it = weights.begin();
+      for (PointIterator e_it = rr.first_point_error; e_it != rr.last_point_error; ++e_it, ++w_it) {
+        const float* p = e_it->point.data;
+        Matrix2x6 Jw, J;
+        NumType z = 1.0f / p[2];
+        NumType z_sqr = 1.0f / (p[2] * p[2]);
+        Jw(0, 0) = z; Jw(0, 1) = 0.0f; Jw(0, 2) = -p[0] * z_sqr; Jw(0, 3) = Jw(0, 2) * p[1]; Jw(0, 4) = 1.0f - Jw(0, 2) * p[0]; Jw(0, 5) = -p[1] * z;
+        Jw(1, 0) = 0.0f; Jw(1, 1) = z; Jw(1, 2) = -p[1] * z_sqr; Jw(1, 3) = -1.0f + Jw(1, 2) * p[1]; Jw(1, 4) = -Jw(0, 3); Jw(1, 5) = p[0] * z;
+        const float Jz[6] = {0.0f, 0.0f, 1.0f, p[1], -p[0], 0.0f};
+        const float* e = e_it->intensity_and_depth.data;
+        for (int c = 0; c < 6; ++c) {
+          J(0, c) = e[2] * Jw(0, c) + e[3] * Jw(1, c);
+          J(1, c) = (e[4] * Jw(0, c) + e[5] * Jw(1, c)) - Jz[c];
+        }
+        Eigen::Vector2f r(e[0], e[1]);
+        Eigen::Matrix2f W = (*w_it) * precision;
+        A_opt.rankUpdate(J, W);
+        b -= J.transpose() * W * r;
+      }
+      Matrix6x6 Af;
+      A_opt.toEigen(Af);
+      double A[36], bd[6];
+      for (int i = 0; i < 6; ++i) { for (int j = 0; j < 6; ++j) A[i * 6 + j] = (double)Af(i, j); bd[i] = (double)b(i); }
+      for (int i = 0; i < 6; ++i) { A[i * 6 + i] += mu; bd[i] += mu * li6[i]; }      // :345-346
+      orc_ldlt_solve6(A, bd, x);                                                     // :347
+      std::memcpy(A_prev, A_last, sizeof(A_prev)); nll_prev = nll_last; prior_prev = prior_last;
+      std::memcpy(A_last, A, sizeof(A_last)); nll_last = -(double)ll; prior_last = prior;
+      ++have;
+      iteration++;                                                                   // :353
+      double m = 0;
+      for (int i = 0; i < 6; ++i) m = std::fabs(x[i]) > m ? std::fabs(x[i]) : m;
+      if (!(accept && m > precision_cfg && !(iteration >= max_iterations))) break;   // :357
+    } while (true);
+    {
+      double m = 0;
+      for (int i = 0; i < 6; ++i) m = std::fabs(x[i]) > m ? std::fabs(x[i]) : m;
+      if (m <= precision_cfg) term = 1;                                              // :359
+      if (iteration >= max_iterations) term = 0;                                     // :362
+    }
+    termination[li] = term;
+    num_iterations[li] = recorded;
+    last_termination = term; last_level_iterations = recorded;
+  }
+  // :368-373: last iteration of the last level, or the one before after LogLikelihoodDecreased
+  (void)last_level_iterations;
+  double inv[16];
+  mat_inv(estimate, inv);
+  std::memcpy(T_out, inv, sizeof(inv));
+  const double* Apick = nullptr; double nll = kNaN, prior = 0;
+  if (last_termination == 2) { if (have >= 1) { Apick = A_last; nll = nll_last; prior = prior_last; } }   // the rejected iteration recorded no system
+  else if (last_termination != 3 && have >= 1) { Apick = A_last; nll = nll_last; prior = prior_last; }
+  for (int i = 0; i < 36; ++i) info_out[i] = Apick ? Apick[i] * 0.008 * 0.008 : kNaN;
+  *ll_out = Apick ? nll + prior : kNaN;
+  (void)A_prev; (void)nll_prev; (void)prior_prev;
+  return 0;
+}
+
 }  // extern "C"

@@ -101,3 +101,37 @@ def test_reference_built_at_its_own_O3_stays_within_the_stated_spread(oracle):
         assert np.allclose(r["precision"], o["precision"], rtol=5e-4)
         assert np.abs(r["A"] - o["A"]).max() <= 5e-4 * np.abs(o["A"]).max()
         assert np.abs(r["b"] - o["b"]).max() <= 5e-4 * np.abs(o["b"]).max()
+
+
+def test_whole_alignment_through_reference_object_code_equals_faithful_oracle(oracle):
+    """DenseTracker::match() end to end: oracle/ref_driver.cpp runs the coarse-to-fine loop (dense_tracking.cpp:131-376) with
+    every per-point pass executed by the reference's own object code; the oracle's FAITHFUL match must take the same control
+    flow on every level and return the same Result (the poses agree to the rounding of the 4x4 bookkeeping, Information and
+    LogLikelihood exactly)."""
+    _need_ref(oracle)
+    from dvo_slam_b200 import synth
+    fa = oracle.mode("faithful")
+    cases = []
+    for seed in GOLDEN_SEEDS:
+        g = load_golden(seed)
+        im = golden_images(g, oracle)
+        cases.append((im["I_ref"], im["Z_ref"], im["I_cur"], im["Z_cur"], g["K"], GOLDEN_LEVELS,
+                      dict(first_level=2, last_level=0, max_iterations_per_level=50, precision=1e-4), None))
+    for seed, extra in ((3, {}), (5, dict(mu=0.05, use_initial_estimate=1))):     # 640x480, 5 levels (BASELINE configs[0])
+        p = synth.make_pair(seed)
+        a = {k: p[k].numpy() for k in ("I_ref", "Z_ref", "I_cur", "Z_cur")}
+        cfg = dict(first_level=4, last_level=0, max_iterations_per_level=50, precision=1e-4)
+        cfg.update(extra)
+        T0 = synth.se3_exp(p["xi"] * 0.8) if extra else None
+        cases.append((a["I_ref"], a["Z_ref"], a["I_cur"], a["Z_cur"], p["intrinsics"], 5, cfg, T0))
+    for Ir, Zr, Ic, Zc, K, levels, cfg, T0 in cases:
+        oref, ocur = oracle.Pyramid(Ir, Zr, K, levels), oracle.Pyramid(Ic, Zc, K, levels)
+        ocfg = oracle.config(**cfg)
+        o = oracle.match(oref, ocur, ocfg, fa, T_init=T0)
+        r = oracle.ref_match(oracle.RefPyramid(oref), oracle.RefPyramid(ocur), ocfg, T_init=T0)
+        assert [l["termination"] for l in r["levels"]] == [l["termination"] for l in o["levels"]]
+        assert [l["num_iterations"] for l in r["levels"]] == [l["num_iterations"] for l in o["levels"]]
+        assert [l["valid_pixels"] for l in r["levels"]] == [l["valid_pixels"] for l in o["levels"]]
+        assert np.abs(r["T"] - o["T"]).max() < 1e-12
+        assert np.array_equal(r["information"], o["information"])
+        assert r["log_likelihood"] == o["log_likelihood"]
