@@ -5,6 +5,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <vector>
 
 namespace dvo_b200 {
 
@@ -333,6 +334,22 @@ int dvo_b200_residual_image(dvo_b200_ctx* ctx, const dvo_b200_config* cfg, dvo_b
   if (!ctx || !cfg || !planes7) return set_error(ctx, DVO_B200_ERR_INVALID_ARGUMENT, "residual_image: null argument");
   cudaSetDevice(ctx->device);
   return tracker_linearize(ctx, cfg, reference, current, level, T, 0, nullptr, count, nullptr, nullptr, nullptr, nullptr, planes7);
+}
+
+int dvo_b200_intensity_error_image(dvo_b200_ctx* ctx, const dvo_b200_config* cfg, dvo_b200_pyramid* reference,
+                                   dvo_b200_pyramid* current, int32_t level, const double* T, float* image, int64_t* count) {
+  if (!ctx || !cfg || !image || !reference || !current) return set_error(ctx, DVO_B200_ERR_INVALID_ARGUMENT, "intensity_error_image: null argument");
+  if (level < 0 || level >= reference->levels) return set_error(ctx, DVO_B200_ERR_INVALID_ARGUMENT, "intensity_error_image: level out of range");
+  const size_t n = size_t(reference->L[level].w) * reference->L[level].h;
+  std::vector<float> planes(7 * n);
+  int64_t valid = 0;
+  int rc = dvo_b200_residual_image(ctx, cfg, reference, current, level, T, planes.data(), &valid);
+  if (rc != 0) return rc;
+  // the residual stage leaves NaN at pixels that are unselected, dropped (odd last point) or invalid after the warp:
+  // exactly the pixels the reference's raster walk leaves at the zero initialisation (dense_tracking.cpp:415-439)
+  for (size_t i = 0; i < n; ++i) image[i] = planes[i] == planes[i] ? fabsf(planes[i]) : 0.0f;
+  if (count) *count = valid;
+  return 0;
 }
 
 int dvo_b200_linearize(dvo_b200_ctx* ctx, const dvo_b200_config* cfg, dvo_b200_pyramid* reference, dvo_b200_pyramid* current,

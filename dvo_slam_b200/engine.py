@@ -25,7 +25,7 @@ ABI_SYMBOLS = [
     "dvo_b200_pyramid_create_raw_batch", "dvo_b200_pyramid_create_bgr_batch",
     "dvo_b200_pyramid_retain", "dvo_b200_pyramid_release", "dvo_b200_pyramid_num_levels", "dvo_b200_pyramid_level_info",
     "dvo_b200_pyramid_download", "dvo_b200_pyramid_select", "dvo_b200_match", "dvo_b200_match_batch",
-    "dvo_b200_match_batch_device", "dvo_b200_residual_image", "dvo_b200_linearize", "dvo_b200_profile_enable",
+    "dvo_b200_match_batch_device", "dvo_b200_residual_image", "dvo_b200_intensity_error_image", "dvo_b200_linearize", "dvo_b200_profile_enable",
     "dvo_b200_profile_read",
 ]
 
@@ -129,6 +129,7 @@ def load_library():
                                        C.POINTER(IterationStats), i32]
     L.dvo_b200_match_batch_device.argtypes = [vp, C.POINTER(Config), i32, C.POINTER(vp), C.POINTER(vp), dp, vp]
     L.dvo_b200_residual_image.argtypes = [vp, C.POINTER(Config), vp, vp, i32, dp, fp, C.POINTER(i64)]
+    L.dvo_b200_intensity_error_image.argtypes = [vp, C.POINTER(Config), vp, vp, i32, dp, fp, C.POINTER(i64)]
     L.dvo_b200_linearize.argtypes = [vp, C.POINTER(Config), vp, vp, i32, dp, i32, fp, C.POINTER(i64), fp, fp, dp, dp]
     L.dvo_b200_profile_enable.argtypes = [vp, i32]
     L.dvo_b200_profile_read.argtypes = [vp, dp, C.POINTER(i64), i32]
@@ -337,6 +338,18 @@ class Engine:
                                                      T.ctypes.data_as(C.POINTER(C.c_double)),
                                                      out.ctypes.data_as(C.POINTER(C.c_float)), C.byref(cnt)))
         return cnt.value, out
+
+    def intensity_error_image(self, ref: Pyramid, cur: Pyramid, level: int, T, cfg: Config | None = None):
+        """DenseTracker::computeIntensityErrorImage (dense_tracking.cpp:378-444) -> (n_written, image[h, w])."""
+        cfg = cfg or Config()
+        w, h, _ = ref.level_info(level)
+        out = np.empty((h, w), dtype=np.float32)
+        T = np.ascontiguousarray(np.asarray(T, dtype=np.float64).reshape(16))
+        cnt = C.c_int64()
+        self._check(self.lib.dvo_b200_intensity_error_image(self.ctx, C.byref(cfg), ref.handle, cur.handle, level,
+                                                            T.ctypes.data_as(C.POINTER(C.c_double)),
+                                                            out.ctypes.data_as(C.POINTER(C.c_float)), C.byref(cnt)))
+        return int(cnt.value), out
 
     def linearize(self, ref: Pyramid, cur: Pyramid, level: int, T, use_weights=False, prev_precision=None, cfg: Config | None = None):
         cfg = cfg or Config()

@@ -1,6 +1,8 @@
 // dvo_core_b200.cpp -- implementation of the adapter classes in include/dvo/ (the reference's
 // libdvo_core.so surface for the hot path) on top of the C ABI of libdvo_b200.so.
+#include <algorithm>
 #include <cassert>
+#include <cstring>
 #include <cstdlib>
 #include <stdexcept>
 
@@ -67,6 +69,50 @@ dvo_b200_pyramid* RgbdImagePyramid::device(dvo_b200_ctx* ctx, size_t levels) {
   device_ctx_ = ctx;
   device_levels_ = levels;
   return device_;
+}
+
+void RgbdImagePyramid::deviceBatch(dvo_b200_ctx* ctx, const std::vector<RgbdImagePyramid*>& pyramids, size_t levels,
+                                   std::vector<dvo_b200_pyramid*>& out) {
+  out.assign(pyramids.size(), static_cast<dvo_b200_pyramid*>(0));
+  // distinct pyramids without a sufficient device mirror, of the geometry of the first such pyramid
+  std::vector<RgbdImagePyramid*> todo;
+  int w = 0, h = 0;
+  for (size_t i = 0; i < pyramids.size(); ++i) {
+    RgbdImagePyramid* p = pyramids[i];
+    std::lock_guard<std::mutex> lock(p->mutex_);
+    if (p->device_ && p->device_levels_ >= std::max(levels, p->requested_levels_)) continue;
+    if (std::find(todo.begin(), todo.end(), p) != todo.end()) continue;
+    const RgbdImage& l0 = *p->levels_[0];
+    if (l0.intensity.type() != CV_32FC1 || l0.depth.type() != CV_32FC1) continue;
+    if (todo.empty()) { w = l0.intensity.cols; h = l0.intensity.rows; }
+    else if (l0.intensity.cols != w || l0.intensity.rows != h || &p->camera_ != &todo[0]->camera_) continue;
+    todo.push_back(p);
+  }
+  if (todo.size() >= 2) {
+    const size_t npx = size_t(w) * h, n = todo.size();
+    size_t lv = levels;
+    for (size_t i = 0; i < n; ++i) lv = std::max(lv, todo[i]->requested_levels_);
+    std::vector<float> I(n * npx), Z(n * npx);
+    for (size_t i = 0; i < n; ++i) {
+      for (int y = 0; y < h; ++y) {   // row by row: a cv::Mat need not be continuous
+        std::memcpy(&I[i * npx + size_t(y) * w], todo[i]->levels_[0]->intensity.ptr<float>(y), sizeof(float) * w);
+        std::memcpy(&Z[i * npx + size_t(y) * w], todo[i]->levels_[0]->depth.ptr<float>(y), sizeof(float) * w);
+      }
+    }
+    const IntrinsicMatrix& k = todo[0]->camera_.level(0).intrinsics();
+    std::vector<dvo_b200_pyramid*> handles(n);
+    int rc = dvo_b200_pyramid_create_batch(ctx, int(n), I.data(), Z.data(), w, h, k.fx(), k.fy(), k.ox(), k.oy(), int(lv), handles.data());
+    if (rc != 0) throw std::runtime_error(std::string("dvo_b200_pyramid_create_batch: ") + dvo_b200_last_error(ctx));
+    dvo_b200_synchronize(ctx);   // one synchronisation for the whole upload: the staging vectors go out of scope
+    for (size_t i = 0; i < n; ++i) {
+      std::lock_guard<std::mutex> lock(todo[i]->mutex_);
+      if (todo[i]->device_) dvo_b200_pyramid_release(todo[i]->device_);
+      todo[i]->device_ = handles[i];
+      todo[i]->device_ctx_ = ctx;
+      todo[i]->device_levels_ = lv;
+    }
+  }
+  for (size_t i = 0; i < pyramids.size(); ++i) out[i] = pyramids[i]->device(ctx, levels);   // the rest one by one
 }
 
 RgbdImage& RgbdImagePyramid::level(size_t idx) {
@@ -237,11 +283,15 @@ bool DenseTracker::matchBatch(const std::vector<core::RgbdImagePyramid*>& refere
   c.intensity_derivative_threshold = cfg.IntensityDerivativeThreshold; c.depth_derivative_threshold = cfg.DepthDerivativeThreshold;
   std::vector<dvo_b200_pyramid*> r(n), q(n);
   std::vector<double> T(16 * n);
+  {
+    std::vector<core::RgbdImagePyramid*> all(references);
+    all.insert(all.end(), currents.begin(), currents.end());
+    for (size_t i = 0; i < all.size(); ++i) all[i]->compute(cfg.getNumLevels());   // dense_tracking.cpp:133
+    std::vector<dvo_b200_pyramid*> dev;
+    core::RgbdImagePyramid::deviceBatch(ctx, all, cfg.getNumLevels(), dev);        // one upload, one synchronisation
+    for (size_t i = 0; i < n; ++i) { r[i] = dev[i]; q[i] = dev[n + i]; }
+  }
   for (size_t i = 0; i < n; ++i) {
-    references[i]->compute(cfg.getNumLevels());
-    currents[i]->compute(cfg.getNumLevels());   // dense_tracking.cpp:133
-    r[i] = references[i]->device(ctx, cfg.getNumLevels());
-    q[i] = currents[i]->device(ctx, cfg.getNumLevels());
     if (cfg.UseInitialEstimate) assert(!results[i].isNaN() && "Provided initialization is NaN!");
     for (int a = 0; a < 4; ++a) for (int b = 0; b < 4; ++b) T[16 * i + a * 4 + b] = results[i].Transformation.matrix()(a, b);
   }
@@ -265,18 +315,14 @@ cv::Mat DenseTracker::computeIntensityErrorImage(core::RgbdImagePyramid& referen
   int w = 0, h = 0;
   float K[4];
   dvo_b200_pyramid_level_info(r, int(level), &w, &h, K);
-  std::vector<float> planes(size_t(7) * w * h);
   double T[16];
   for (int a = 0; a < 4; ++a) for (int b = 0; b < 4; ++b) T[a * 4 + b] = transformation.matrix()(a, b);
   dvo_b200_config c;
   dvo_b200_config_default(&c);
   c.intensity_derivative_threshold = cfg.IntensityDerivativeThreshold; c.depth_derivative_threshold = cfg.DepthDerivativeThreshold;
-  int64_t count = 0;
-  if (dvo_b200_residual_image(ctx, &c, r, q, int(level), T, planes.data(), &count) != 0)
-    throw std::runtime_error(std::string("dvo_b200_residual_image: ") + dvo_b200_last_error(ctx));
   cv::Mat result = cv::Mat::zeros(h, w, CV_32FC1);
-  float* out = result.ptr<float>();
-  for (size_t i = 0; i < size_t(w) * h; ++i) out[i] = planes[i] == planes[i] ? std::fabs(planes[i]) : 0.0f;   // dense_tracking.cpp:424-433
+  if (dvo_b200_intensity_error_image(ctx, &c, r, q, int(level), T, result.ptr<float>(), nullptr) != 0)
+    throw std::runtime_error(std::string("dvo_b200_intensity_error_image: ") + dvo_b200_last_error(ctx));
   return result;
 }
 

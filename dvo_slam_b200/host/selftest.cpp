@@ -7,6 +7,8 @@
 #include <cstdlib>
 #include <fstream>
 #include <iostream>
+#include <chrono>
+#include <string>
 #include <vector>
 
 #include "dvo/dense_tracking.h"
@@ -37,7 +39,7 @@ static cv::Mat load_plane(std::ifstream& f, int w, int h) {
 }
 
 int main(int argc, char** argv) {
-  if (argc < 8) { std::fprintf(stderr, "usage: selftest pair.bin w h fx fy ox oy [first last]\n"); return 2; }
+  if (argc < 8) { std::fprintf(stderr, "usage: selftest pair.bin w h fx fy ox oy [first last [error_image.bin [batch]]]\n"); return 2; }
   const int w = std::atoi(argv[2]), h = std::atoi(argv[3]);
   dvo::core::IntrinsicMatrix K = dvo::core::IntrinsicMatrix::create(float(std::atof(argv[4])), float(std::atof(argv[5])), float(std::atof(argv[6])), float(std::atof(argv[7])));
   std::ifstream f(argv[1], std::ios::binary);
@@ -76,6 +78,10 @@ int main(int argc, char** argv) {
   cv::Mat err = tracker.computeIntensityErrorImage(*reference, *current, result.Transformation.inverse(), size_t(cfg.LastLevel));
   double esum = 0;
   for (size_t i = 0; i < err.total(); ++i) esum += err.ptr<float>()[i];
+  if (argc > 10) {   // the image itself, for the bit-exact comparison with the oracle's raster walk (tests/test_host_adapter.py)
+    std::ofstream ef(argv[10], std::ios::binary);
+    for (int y = 0; y < err.rows; ++y) ef.write(reinterpret_cast<const char*>(err.ptr<float>(y)), sizeof(float) * size_t(err.cols));
+  }
   // N1: the two fan-outs of dvo_slam as one batched call each; the answers must be those of the sequential calls
   dvo::DenseTracker::Result r_keyframe, r_odometry;
   dvo_slam::matchKeyframeAndOdometry(tracker, *reference, *reference, *current, r_keyframe, r_odometry);
@@ -91,11 +97,63 @@ int main(int argc, char** argv) {
   dvo_slam::LogLikelihoodTrackingResultEvaluation loglik(result);
   dvo_slam::NormalizedLogLikelihoodTrackingResultEvaluation nloglik(result);
   entropy.add(r_keyframe);
+  // ... and on DISTINCT results: a coarser alignment (stops one level earlier) and the reverse alignment
+  dvo::DenseTracker::Config coarse_cfg = cfg;
+  coarse_cfg.LastLevel = cfg.LastLevel + 1;
+  dvo::DenseTracker coarse(coarse_cfg);
+  coarse.collectIterationStatistics(true);
+  dvo::DenseTracker::Result r_coarse, r_reverse;
+  coarse.match(*reference, *current, r_coarse);
+  tracker.match(*current, *reference, r_reverse);
+  const dvo::DenseTracker::Result* rs[3] = {&result, &r_coarse, &r_reverse};
+  std::string eval = "[";
+  for (int i = 0; i < 3; ++i) {
+    char buf[2048];
+    int off = std::snprintf(buf, sizeof(buf), "%s{\"ll\": %.17g, \"n_last\": %zu, \"info\": [", i ? ", " : "", rs[i]->LogLikelihood,
+                            rs[i]->Statistics.Levels.back().Iterations.back().ValidConstraints);
+    for (int a = 0; a < 6; ++a) for (int b = 0; b < 6; ++b) off += std::snprintf(buf + off, sizeof(buf) - size_t(off), "%s%.17g", (a + b) ? ", " : "", rs[i]->Information(a, b));
+    std::snprintf(buf + off, sizeof(buf) - size_t(off), "]}");
+    eval += buf;
+  }
+  eval += "]";
+  // keyframe_tracker.cpp usage pattern: constructed from the first result, add() the following ones, ratios of a later one
+  dvo_slam::EntropyRatioTrackingResultEvaluation e2(result);
+  dvo_slam::LogLikelihoodTrackingResultEvaluation l2(result);
+  dvo_slam::NormalizedLogLikelihoodTrackingResultEvaluation n2(result);
+  e2.add(r_coarse); l2.add(r_coarse); n2.add(r_coarse);
+  // the C++ batch path timed: `batch` proposals over 2*batch DISTINCT pyramids (uploads batched inside matchBatch), then
+  // the same proposals again with the device mirrors in place
+  double batch_first_ms = 0, batch_again_ms = 0;
+  int nbatch = argc > 11 ? std::atoi(argv[11]) : 0;
+  if (nbatch > 0) {
+    std::vector<Frame> frames(size_t(2 * nbatch));
+    std::vector<Proposal> props(size_t(nbatch), p0);
+    std::vector<Proposal*> pp;
+    for (int i = 0; i < nbatch; ++i) {
+      frames[size_t(2 * i)].pyramid = camera.create(Ir, Zr);
+      frames[size_t(2 * i + 1)].pyramid = camera.create(Ic, Zc);
+      props[size_t(i)].Reference = &frames[size_t(2 * i)];
+      props[size_t(i)].Current = &frames[size_t(2 * i + 1)];
+      pp.push_back(&props[size_t(i)]);
+    }
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    dvo_slam::matchProposals(tracker, pp);
+    std::chrono::steady_clock::time_point t1 = std::chrono::steady_clock::now();
+    dvo_slam::matchProposals(tracker, pp);
+    std::chrono::steady_clock::time_point t2 = std::chrono::steady_clock::now();
+    batch_first_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+    batch_again_ms = std::chrono::duration<double, std::milli>(t2 - t1).count();
+    for (int i = 0; i < nbatch; ++i) if (!same_pose(props[size_t(i)].TrackingResult, result)) nbatch = -1;
+  }
   std::printf("], \"second_t\": [%.17g, %.17g, %.17g], \"err_sum\": %.9g, \"level1_w\": %d, \"batch_equal\": %d, \"proposals_equal\": %d, "
-              "\"entropy_ratio_first\": %.17g, \"entropy_ratio_avg\": %.17g, \"ll_ratio\": %.17g, \"nll_ratio\": %.17g, \"logdet\": %.17g}\n",
+              "\"entropy_ratio_first\": %.17g, \"entropy_ratio_avg\": %.17g, \"ll_ratio\": %.17g, \"nll_ratio\": %.17g, \"logdet\": %.17g, "
+              "\"eval_results\": %s, \"eval\": {\"entropy_first\": %.17g, \"entropy_avg\": %.17g, \"ll_first\": %.17g, \"ll_avg\": %.17g, "
+              "\"nll_first\": %.17g, \"nll_avg\": %.17g}, \"batch\": %d, \"batch_first_ms\": %.3f, \"batch_again_ms\": %.3f}\n",
               guess.matrix()(0, 3), guess.matrix()(1, 3), guess.matrix()(2, 3), esum, reference->level(1).intensity.cols,
               int(batch_equal), int(proposals_equal), entropy.ratioWithFirst(r_odometry), entropy.ratioWithAverage(r_odometry),
-              loglik.ratioWithFirst(result), nloglik.ratioWithAverage(result), std::log(result.Information.determinant()));
+              loglik.ratioWithFirst(result), nloglik.ratioWithAverage(result), std::log(result.Information.determinant()),
+              eval.c_str(), e2.ratioWithFirst(r_reverse), e2.ratioWithAverage(r_reverse), l2.ratioWithFirst(r_reverse), l2.ratioWithAverage(r_reverse),
+              n2.ratioWithFirst(r_reverse), n2.ratioWithAverage(r_reverse), nbatch, batch_first_ms, batch_again_ms);
   std::cerr << result.Statistics;
   return 0;
 }

@@ -76,6 +76,11 @@ class RgbdImagePyramid {   // rgbd_image.h:242-262
   // --- extension used by the adapter's DenseTracker: the device mirror with at least `levels` levels,
   // created on first use through `ctx` (uploads level 0 and builds the pyramid on the GPU). ---
   dvo_b200_pyramid* device(dvo_b200_ctx* ctx, size_t levels);
+  // the same for many pyramids at once: every pyramid that still needs its device mirror is uploaded in ONE
+  // dvo_b200_pyramid_create_batch call followed by ONE synchronisation (pyramids that appear several times in the
+  // list -- a keyframe in several proposals -- are uploaded once); out[i] = device mirror of pyramids[i]
+  static void deviceBatch(dvo_b200_ctx* ctx, const std::vector<RgbdImagePyramid*>& pyramids, size_t levels,
+                          std::vector<dvo_b200_pyramid*>& out);
  private:
   RgbdCameraPyramid& camera_;
   std::vector<RgbdImagePtr> levels_;

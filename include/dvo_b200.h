@@ -181,6 +181,13 @@ int dvo_b200_match_batch_device(dvo_b200_ctx* ctx, const dvo_b200_config* cfg, i
 int dvo_b200_residual_image(dvo_b200_ctx* ctx, const dvo_b200_config* cfg, dvo_b200_pyramid* reference,
                             dvo_b200_pyramid* current, int32_t level, const double* T, float* planes7,
                             int64_t* count);
+/* DenseTracker::computeIntensityErrorImage (dense_tracking.cpp:378-444): image = h*w floats on the host,
+ * |intensity residual| at every selected reference pixel whose warped residual is valid, 0 elsewhere (the odd
+ * last selected point included: the reference's SSE residual loop never visits it).  T as above; the selection
+ * thresholds come from cfg.  *count (optional) = residuals written. */
+int dvo_b200_intensity_error_image(dvo_b200_ctx* ctx, const dvo_b200_config* cfg, dvo_b200_pyramid* reference,
+                                   dvo_b200_pyramid* current, int32_t level, const double* T, float* image,
+                                   int64_t* count);
 /* One linearisation at a fixed transform (test hook mirroring dense_tracking.cpp:271-343):
  * use_weights=0 -> w=1 (first iteration on a level), else Student-t weights from prev_precision. */
 int dvo_b200_linearize(dvo_b200_ctx* ctx, const dvo_b200_config* cfg, dvo_b200_pyramid* reference,

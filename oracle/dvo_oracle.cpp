@@ -717,6 +717,43 @@ int64_t orc_residual_image(const orc_pyramid* ref, const orc_pyramid* cur, int l
   return int64_t(e.size());
 }
 
+// DenseTracker::computeIntensityErrorImage (dense_tracking.cpp:378-444): residuals with valid flags
+// (computeResidualsAndValidFlagsSse), then a raster walk over the selection's debug index (1 at every
+// selected pixel, point_selection.cpp:139-140) that consumes one valid flag per selected pixel and one
+// residual per set flag.  The flag vector is zero-initialised (line 391) and the SSE loop never visits
+// the odd last point (dense_tracking_impl.cpp:169), so that pixel reads flag 0 and stays 0 in the image.
+int64_t orc_intensity_error_image(const orc_pyramid* ref, const orc_pyramid* cur, int level, const double T[16],
+                                  float ti, float td, const orc_mode* mode, float* image) {
+  const Level& R = ref->levels[level];
+  const Level& C = cur->levels[level];
+  std::vector<RefPoint> pts;
+  select_points(R, ti, td, pts);
+  LevelConsts c;
+  make_level_consts(C, T, c);
+  std::vector<ErrPoint> e;
+  compute_residuals(pts, C, c, *mode, e);
+  const size_t N = size_t(R.w) * R.h;
+  std::vector<uint8_t> debug_idx(N, 0), valid(pts.size(), 0);
+  for (const RefPoint& p : pts) debug_idx[size_t(p.pix)] = 1;
+  {  // last_valid_flag stream: one flag per visited point, 1 iff the point produced a residual (lines 292-293, 388-389)
+    size_t j = 0;
+    for (size_t k = 0; k < pts.size() && j < e.size(); ++k)
+      if (e[j].pix == pts[k].pix) { valid[k] = 1; ++j; }
+  }
+  for (size_t i = 0; i < N; ++i) image[i] = 0.0f;                    // cv::Mat::zeros (line 415)
+  size_t flag_it = 0, res_it = 0;
+  for (size_t i = 0; i < N; ++i) {                                   // lines 426-439
+    if (debug_idx[i] == 1) {
+      if (valid[flag_it] == 1) {
+        image[i] = std::fabs(e[res_it].e[0]);
+        ++res_it;
+      }
+      ++flag_it;
+    }
+  }
+  return int64_t(res_it);
+}
+
 int64_t orc_linearize(const orc_pyramid* ref, const orc_pyramid* cur, int level, const double T[16], float ti,
                       float td, int use_weights, const float prev_precision[4], const orc_mode* mode,
                       float precision_out[4], float* ll_out, double A_out[36], double b_out[6]) {

@@ -82,6 +82,8 @@ def lib():
         L.orc_select.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float, C.POINTER(Mode), C.POINTER(C.c_uint8)]
         L.orc_residual_image.restype = C.c_int64
         L.orc_residual_image.argtypes = [C.c_void_p, C.c_void_p, C.c_int, dp, C.c_float, C.c_float, C.POINTER(Mode), fp]
+        L.orc_intensity_error_image.restype = C.c_int64
+        L.orc_intensity_error_image.argtypes = [C.c_void_p, C.c_void_p, C.c_int, dp, C.c_float, C.c_float, C.POINTER(Mode), fp]
         L.orc_linearize.restype = C.c_int64
         L.orc_linearize.argtypes = [C.c_void_p, C.c_void_p, C.c_int, dp, C.c_float, C.c_float, C.c_int, fp,
                                     C.POINTER(Mode), fp, fp, dp, dp]
@@ -167,6 +169,15 @@ def residual_image(ref: Pyramid, cur: Pyramid, level, T, m: Mode, ti=0.0, td=0.0
     out = np.empty((7, h, w), dtype=np.float32)
     T = np.ascontiguousarray(np.asarray(T, dtype=np.float64).reshape(16))
     n = lib().orc_residual_image(ref.h, cur.h, level, _dptr(T), ti, td, C.byref(m), _fptr(out))
+    return int(n), out
+
+
+def intensity_error_image(ref: Pyramid, cur: Pyramid, level, T, m: Mode, ti=0.0, td=0.0):
+    """DenseTracker::computeIntensityErrorImage (dense_tracking.cpp:378-444) -> (n_written, image[h, w])."""
+    w, h, _ = ref.level_info(level)
+    out = np.empty((h, w), dtype=np.float32)
+    T = np.ascontiguousarray(np.asarray(T, dtype=np.float64).reshape(16))
+    n = lib().orc_intensity_error_image(ref.h, cur.h, level, _dptr(T), ti, td, C.byref(m), _fptr(out))
     return int(n), out
 
 
@@ -264,6 +275,8 @@ def ref_lib(variant: str = ""):
         L.ref_pyramid_create.restype = C.c_void_p
         L.ref_pyramid_create.argtypes = [C.c_int, C.POINTER(fp), C.POINTER(C.c_int), C.POINTER(C.c_int), fp]
         L.ref_pyramid_destroy.argtypes = [C.c_void_p]
+        L.ref_intensity_error_image.restype = C.c_int64
+        L.ref_intensity_error_image.argtypes = [C.c_void_p, C.c_void_p, C.c_int, dp, C.c_float, C.c_float, fp]
         L.ref_match.restype = C.c_int
         L.ref_match.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, dp, C.c_float,
                                 C.c_float, dp, dp, dp, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int64)]
@@ -285,6 +298,7 @@ class RefPyramid:
         ptrs = (C.POINTER(C.c_float) * n)(*[_fptr(p) for p in self._planes])
         self.h = ref_lib(variant).ref_pyramid_create(n, ptrs, w, h, _fptr(K))
         self.levels = n
+        self.size = [(i[0], i[1]) for i in info]
 
     def __del__(self):
         h, self.h = getattr(self, "h", None), None
@@ -307,6 +321,16 @@ def ref_match(ref: RefPyramid, cur: RefPyramid, cfg: Config, T_init=None):
     assert rc == 0
     levels = [{"id": cfg.first_level - i, "termination": term[i], "num_iterations": its[i], "valid_pixels": vp[i]} for i in range(nl)]
     return {"T": T.reshape(4, 4), "information": info.reshape(6, 6), "log_likelihood": ll.value, "levels": levels}
+
+
+def ref_intensity_error_image(ref: RefPyramid, cur: RefPyramid, level, T, ti=0.0, td=0.0):
+    """computeIntensityErrorImage with residuals and valid flags from the reference's computeResidualsAndValidFlagsSse."""
+    L = ref_lib(ref.variant)
+    w, h = ref.size[level]
+    out = np.empty((h, w), dtype=np.float32)
+    T = np.ascontiguousarray(np.asarray(T, dtype=np.float64).reshape(16))
+    n = L.ref_intensity_error_image(ref.h, cur.h, level, _dptr(T), ti, td, _fptr(out))
+    return int(n), out
 
 
 def ref_linearize(ref_planes6, cur_planes6, K, T, use_weights=False, prev_precision=None, ti=0.0, td=0.0, variant=""):

@@ -242,6 +242,61 @@ void* ref_pyramid_create(int nlevels, const float* const* planes6, const int* w,
 }
 void ref_pyramid_destroy(void* p) { delete static_cast<RefPyramid*>(p); }
 
+// DenseTracker::computeIntensityErrorImage (dense_tracking.cpp:378-444) with the residuals AND the valid flags produced by
+// the reference's own computeResidualsAndValidFlagsSse (the Debug instantiation of the SSE loop); the raster walk over the
+// selection's debug index is restated from lines 415-439.  image: h*w floats.  Returns the residuals consumed.
+int64_t ref_intensity_error_image(void* ref_p, void* cur_p, int level, const double* T, float ti, float td, float* image) {
+  RefPyramid& ref = *static_cast<RefPyramid*>(ref_p);
+  RefPyramid& cur = *static_cast<RefPyramid*>(cur_p);
+  RefLevel& R = ref.levels[level];
+  RefLevel& C = cur.levels[level];
+  select_points(R, ti, td);
+  const size_t N = (size_t)R.w * R.h;
+  // debug index: 1 at every selected pixel (point_selection.cpp:139-140); same predicate walk as select_points()
+  std::vector<uint8_t> debug_idx(N, 0);
+  {
+    ValidPointAndGradientThresholdPredicate predicate;
+    predicate.intensity_threshold = ti; predicate.depth_threshold = td;
+    const float* accel = R.image->acceleration.ptr<float>(0);
+    size_t idx = 0;
+    for (size_t y = 0; y < (size_t)R.h; ++y)
+      for (size_t x = 0; x < (size_t)R.w; ++x, ++idx) {
+        const float* a = accel + 8 * idx;
+        if (predicate.isPointOk(x, y, R.depth[idx], a[2], a[3], a[4], a[5])) debug_idx[idx] = 1;
+      }
+  }
+  const IntrinsicMatrix& K = C.K;
+  Vector8f wcur, wref;                                 // dense_tracking.cpp:401-406
+  float wcur_id = 0.5f, wref_id = 0.5f, wcur_zd = 1.0f, wref_zd = 0.0f;
+  wcur <<  1.0f / 255.0f,  1.0f, wcur_id * K.fx() / 255.0f, wcur_id * K.fy() / 255.0f, wcur_zd * K.fx(), wcur_zd * K.fy(), 0.0f, 0.0f;
+  wref << -1.0f / 255.0f, -1.0f, wref_id * K.fx() / 255.0f, wref_id * K.fy() / 255.0f, wref_zd * K.fx(), wref_zd * K.fy(), 0.0f, 0.0f;
+  Eigen::Affine3f transformf;
+  for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) transformf(i, j) = (float)T[i * 4 + j];   // transformation.cast<float>() (:413)
+  PointWithIntensityAndDepth::VectorType points_error(R.points.size() + 2);
+  dvo::DenseTracker::ResidualVectorType residuals(R.points.size() + 2);
+  std::vector<uint8_t> valid_residuals;
+  valid_residuals.resize(R.points.size() + 2);          // zero-initialised, as line 391
+  ComputeResidualsResult rr;
+  rr.first_point_error = points_error.begin();
+  rr.first_residual = residuals.begin();
+  rr.first_valid_flag = valid_residuals.begin();
+  computeResidualsAndValidFlagsSse(R.points.begin(), R.points.end(), *C.image, K, transformf, wref, wcur, rr);
+  for (size_t i = 0; i < N; ++i) image[i] = 0.0f;
+  const uint8_t* valid_pixel_it = debug_idx.data();
+  ValidFlagIterator valid_residual_it = rr.first_valid_flag;
+  ResidualIterator residual_it = rr.first_residual;
+  for (size_t i = 0; i < N; ++i, ++valid_pixel_it) {   // lines 426-439
+    if (*valid_pixel_it == 1) {
+      if (*valid_residual_it == 1) {
+        image[i] = std::abs(residual_it->coeff(0));
+        ++residual_it;
+      }
+      ++valid_residual_it;
+    }
+  }
+  return (int64_t)(residual_it - rr.first_residual);
+}
+
 // termination codes as dvo::DenseTracker::TerminationCriteria (dense_tracking.h:71-81):
 // 0 IterationsExceeded, 1 IncrementTooSmall, 2 LogLikelihoodDecreased, 3 TooFewConstraints
 int ref_match(void* ref_p, void* cur_p, int first_level, int last_level, int max_iterations, double precision_cfg, double mu,

@@ -85,6 +85,8 @@ class Matrix {
   const T& operator()(int i, int j) const { return m_[j * R + i]; }
   T& operator()(int i) { return m_[i]; }
   const T& operator()(int i) const { return m_[i]; }
+  const T& coeff(int i) const { return m_[i]; }
+  const T& coeff(int i, int j) const { return m_[j * R + i]; }
   T& operator[](int i) { return m_[i]; }
   const T& operator[](int i) const { return m_[i]; }
   T* data() { return m_; }

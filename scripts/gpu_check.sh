@@ -9,3 +9,7 @@ if [ "$1" = "bench" ]; then
   timeout 600 python bench.py > gpurun_out/bench_dev.json 2> gpurun_out/bench_dev.err
   echo "bench exit $?"; cat gpurun_out/bench_dev.json; tail -5 gpurun_out/bench_dev.err
 fi
+if [ "$2" = "c5" ]; then
+  timeout 600 python bench.py --config 5 --steps 3 --no-cpu-baseline > gpurun_out/bench_c5.json 2> gpurun_out/bench_c5.err
+  echo "bench c5 exit $?"; cat gpurun_out/bench_c5.json; tail -5 gpurun_out/bench_c5.err
+fi

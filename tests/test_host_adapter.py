@@ -65,7 +65,8 @@ def test_adapter_matches_like_the_reference_callers(selftest_bin, tmp_path, orac
     from dvo_slam_b200 import synth
     pair = synth.make_pair(21)
     K = pair["intrinsics"]
-    r = subprocess.run([selftest_bin, _write_pair(tmp_path, pair), "640", "480"] + [repr(float(v)) for v in K] + ["3", "1"],
+    err_path = str(tmp_path / "err.bin")
+    r = subprocess.run([selftest_bin, _write_pair(tmp_path, pair), "640", "480"] + [repr(float(v)) for v in K] + ["3", "1", err_path, "16"],
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr
     out = json.loads(r.stdout.strip().splitlines()[-1])
@@ -85,6 +86,31 @@ def test_adapter_matches_like_the_reference_callers(selftest_bin, tmp_path, orac
     assert out["batch_equal"] == 1 and out["proposals_equal"] == 1
     # N4: keyframe-selection scores (tracking_result_evaluation.cpp:26-62) on identical results are exactly 1
     assert out["entropy_ratio_first"] == 1.0 and out["entropy_ratio_avg"] == 1.0 and out["ll_ratio"] == 1.0 and out["nll_ratio"] == 1.0
+    # ... and on distinct results (fine / coarser / reverse alignment), against the formulas of tracking_result_evaluation.cpp
+    # evaluated by hand from the printed Result fields: value = log det(Information) | -LogLikelihood | -LogLikelihood / n_last;
+    # constructed from result[0], add(result[1]), ratios of result[2]:  first = v2 / v0,  average = v2 / (v0 + v1) * 2
+    ev = out["eval_results"]
+    assert len({e["ll"] for e in ev}) == 3                       # really distinct
+    vals = {"entropy": [float(np.log(np.linalg.det(np.array(e["info"]).reshape(6, 6)))) for e in ev],
+            "ll": [-e["ll"] for e in ev], "nll": [-e["ll"] / e["n_last"] for e in ev]}
+    for name, v in vals.items():
+        assert out["eval"][name + "_first"] == pytest.approx(v[2] / v[0], rel=1e-9)
+        assert out["eval"][name + "_avg"] == pytest.approx(v[2] / (v[0] + v[1]) * 2.0, rel=1e-9)
+    assert abs(out["eval"]["entropy_avg"] - 1.0) > 1e-6 and abs(out["eval"]["ll_first"] - 1.0) > 1e-6
+    # N4: DenseTracker::computeIntensityErrorImage (dense_tracking.cpp:378-444) at the returned pose: bit-exact against the
+    # oracle's raster walk under the kernel's arithmetic (MIRROR), and within rounding of the reference's numerics (FAITHFUL)
+    err = np.fromfile(err_path, dtype=np.float32).reshape(240, 320)
+    Tinv = np.linalg.inv(T)            # the selftest passes result.Transformation.inverse() (benchmark / visualiser usage)
+    n_m, img_m = oracle.intensity_error_image(oref, ocur, 1, Tinv, oracle.mode("mirror"))
+    n_f, img_f = oracle.intensity_error_image(oref, ocur, 1, Tinv, oracle.mode("faithful"))
+    assert n_m > 50000 and np.array_equal(err, img_m)
+    both = (err > 0) & (img_f > 0)
+    assert both.sum() >= 0.999 * max((err > 0).sum(), (img_f > 0).sum())
+    assert np.abs(err - img_f)[both].max() < 2e-4                # intensity residual in [0,1] units; RTZ / rcp_ps differences
+    assert abs(float(err.sum()) - out["err_sum"]) <= 1e-3 * out["err_sum"]
+    # the C++ batch path (16 proposals over 32 distinct pyramids): same answers; first call = one batched upload + build
+    assert out["batch"] == 16 and out["batch_first_ms"] > 0 and out["batch_again_ms"] > 0
+    print("adapter matchProposals x16: first call %.2f ms (upload + pyramids + match), again %.2f ms (match only)" % (out["batch_first_ms"], out["batch_again_ms"]))
     info = np.array(fa["information"])
     # Information follows the (chaotic, pair-bug-sensitive) scale estimate of the last iteration: entries agree to ~1e-2 of
     # the largest one with FAITHFUL, i.e. log det to a few percent (measured 89.35 vs 90.49)

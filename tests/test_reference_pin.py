@@ -135,3 +135,53 @@ def test_whole_alignment_through_reference_object_code_equals_faithful_oracle(or
         assert np.abs(r["T"] - o["T"]).max() < 1e-12
         assert np.array_equal(r["information"], o["information"])
         assert r["log_likelihood"] == o["log_likelihood"]
+
+
+def test_intensity_error_image_walk_equals_reference_valid_flag_stream(oracle):
+    """DenseTracker::computeIntensityErrorImage (dense_tracking.cpp:378-444): the oracle's raster walk against the same
+    walk fed by the reference's OWN computeResidualsAndValidFlagsSse (flags and residuals from the Debug instantiation of
+    the SSE loop) -- bit for bit, including the odd last selected point, which the SSE loop never visits and which
+    therefore stays 0 although its warp is valid."""
+    _need_ref(oracle)
+    fa = oracle.mode("faithful")
+    for seed in GOLDEN_SEEDS:
+        g = load_golden(seed)
+        im = golden_images(g, oracle)
+        oref = oracle.Pyramid(im["I_ref"], im["Z_ref"], g["K"], GOLDEN_LEVELS)
+        ocur = oracle.Pyramid(im["I_cur"], im["Z_cur"], g["K"], GOLDEN_LEVELS)
+        rref, rcur = oracle.RefPyramid(oref), oracle.RefPyramid(ocur)
+        for lvl in range(GOLDEN_LEVELS):
+            for ti, td in ((0.0, 0.0), (2.0, 0.02)):
+                n_o, img_o = oracle.intensity_error_image(oref, ocur, lvl, g["kat_T"], fa, ti, td)
+                n_r, img_r = oracle.ref_intensity_error_image(rref, rcur, lvl, g["kat_T"], ti, td)
+                assert n_o == n_r and n_o > 0
+                assert np.array_equal(img_o, img_r)
+                # semantics, stated independently: |e.i| where the residual stage has a valid residual, 0 elsewhere
+                n_img, planes = oracle.residual_image(oref, ocur, lvl, g["kat_T"], fa, ti, td)
+                want = np.where(np.isnan(planes[0]), 0.0, np.abs(planes[0])).astype(np.float32)
+                assert n_img == n_o and np.array_equal(img_o, want)
+    # The odd-point drop made visible: reference = a frame with its bottom/right margin made invalid, current = the same
+    # frame unmasked, identity transform -> every selected point maps onto itself and is valid, so the only selected pixel
+    # the image may leave at 0 is the odd last one (which EXACT numerics, without the drop, would fill).
+    g = load_golden(GOLDEN_SEEDS[0])
+    im = golden_images(g, oracle)
+    saw_odd = False
+    for margin in range(4, 40):
+        Z = im["Z_ref"].copy()
+        Z[-margin:, :] = np.nan
+        Z[:, -margin:] = np.nan
+        oref = oracle.Pyramid(im["I_ref"], Z, g["K"], 1)
+        ocur = oracle.Pyramid(im["I_ref"], im["Z_ref"], g["K"], 1)
+        S, mask = oracle.select(oref, 0, 0.0, 0.0, None)
+        last = np.flatnonzero(mask.reshape(-1))[-1]
+        _, planes_exact = oracle.residual_image(oref, ocur, 0, np.eye(4), oracle.mode("exact"))
+        if S % 2 == 0 or np.isnan(planes_exact[0].reshape(-1)[last]):   # need: odd count, last point valid by itself
+            continue
+        rref, rcur = oracle.RefPyramid(oref), oracle.RefPyramid(ocur)
+        n_o, img_o = oracle.intensity_error_image(oref, ocur, 0, np.eye(4), fa)
+        n_r, img_r = oracle.ref_intensity_error_image(rref, rcur, 0, np.eye(4))
+        assert np.array_equal(img_o, img_r) and n_o == n_r <= S - 1
+        assert img_o.reshape(-1)[last] == 0.0                      # the point itself is fine and still 0 in the reference's image
+        saw_odd = True
+        break
+    assert saw_odd, "no margin gave an odd selection count with a valid last point"
