@@ -230,6 +230,8 @@ int dvo_b200_pyramid_create_raw(dvo_b200_ctx* ctx, const uint8_t* grey, const ui
   return dvo_b200_pyramid_create_raw_batch(ctx, 1, grey, raw_depth, depth_scale, width, height, fx, fy, ox, oy, levels, out);
 }
 
+int dvo_b200_pyramid_device(const dvo_b200_pyramid* p) { return p ? p->device : -1; }
+
 int dvo_b200_pyramid_retain(dvo_b200_pyramid* p) {
   if (!p) return DVO_B200_ERR_INVALID_ARGUMENT;
   p->refcount.fetch_add(1, std::memory_order_relaxed);

@@ -75,7 +75,8 @@ struct Slab {                  // one cudaMalloc shared by a batch of pyramids
 
 // opaque handle types of the C ABI
 struct dvo_b200_pyramid {
-  dvo_b200_ctx* ctx = nullptr;
+  dvo_b200_ctx* ctx = nullptr;   // the context that built it (may be gone by the time the pyramid is read: never dereferenced for that)
+  int device = 0;                // CUDA ordinal the planes live on
   std::atomic<int> refcount{1};   // retain/release may come from any host thread (boost::shared_ptr semantics)
   int levels = 0;
   dvo_b200::LevelInfo L[dvo_b200::kMaxLevels];

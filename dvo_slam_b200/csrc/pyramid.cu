@@ -350,7 +350,7 @@ int pyramid_build_batch(dvo_b200_ctx* ctx, int n, const float* d_I, const float*
   DVO_CUDA(ctx, cudaEventRecord(slab->ready, st));
   for (int i = 0; i < n; ++i) {
     dvo_b200_pyramid* p = new dvo_b200_pyramid;
-    p->ctx = ctx; p->refcount.store(1); p->levels = levels;
+    p->ctx = ctx; p->device = ctx->device; p->refcount.store(1); p->levels = levels;
     std::memcpy(p->L, L, sizeof(LevelInfo) * levels);
     p->slab = slab; slab->refs++;
     p->planes = planes + (size_t)i * plane_f2;

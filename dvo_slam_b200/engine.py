@@ -26,7 +26,9 @@ ABI_SYMBOLS = [
     "dvo_b200_pyramid_retain", "dvo_b200_pyramid_release", "dvo_b200_pyramid_num_levels", "dvo_b200_pyramid_level_info",
     "dvo_b200_pyramid_download", "dvo_b200_pyramid_select", "dvo_b200_match", "dvo_b200_match_batch",
     "dvo_b200_match_batch_device", "dvo_b200_residual_image", "dvo_b200_intensity_error_image", "dvo_b200_linearize", "dvo_b200_profile_enable",
-    "dvo_b200_profile_read",
+    "dvo_b200_profile_read", "dvo_b200_pyramid_device", "dvo_b200_sharded_create", "dvo_b200_sharded_destroy",
+    "dvo_b200_sharded_num_shards", "dvo_b200_sharded_ctx", "dvo_b200_sharded_last_error", "dvo_b200_shard_range",
+    "dvo_b200_sharded_pyramid_create_batch", "dvo_b200_sharded_pyramid_create_raw_batch", "dvo_b200_match_batch_sharded",
 ]
 
 
@@ -118,6 +120,20 @@ def load_library():
     L.dvo_b200_pyramid_create_raw.argtypes = [vp, vp, vp, C.c_float, i32, i32, C.c_float, C.c_float, C.c_float, C.c_float, i32, C.POINTER(vp)]
     L.dvo_b200_pyramid_create_raw_batch.argtypes = [vp, i32, vp, vp, C.c_float, i32, i32, C.c_float, C.c_float, C.c_float, C.c_float, i32, C.POINTER(vp)]
     L.dvo_b200_pyramid_create_bgr_batch.argtypes = [vp, i32, vp, vp, C.c_float, i32, i32, C.c_float, C.c_float, C.c_float, C.c_float, i32, C.POINTER(vp)]
+    L.dvo_b200_pyramid_device.argtypes = [vp]
+    L.dvo_b200_sharded_create.argtypes = [i32, C.POINTER(i32), C.POINTER(vp)]
+    L.dvo_b200_sharded_destroy.argtypes = [vp]
+    L.dvo_b200_sharded_num_shards.argtypes = [vp]
+    L.dvo_b200_sharded_ctx.restype = vp
+    L.dvo_b200_sharded_ctx.argtypes = [vp, i32]
+    L.dvo_b200_sharded_last_error.restype = C.c_char_p
+    L.dvo_b200_sharded_last_error.argtypes = [vp]
+    L.dvo_b200_shard_range.argtypes = [i64, i32, i32, C.POINTER(i64), C.POINTER(i64)]
+    L.dvo_b200_sharded_pyramid_create_batch.argtypes = [vp, i32, vp, vp, i32, i32, C.c_float, C.c_float, C.c_float, C.c_float, i32, C.POINTER(vp)]
+    L.dvo_b200_sharded_pyramid_create_raw_batch.argtypes = [vp, i32, vp, vp, C.c_float, i32, i32, C.c_float, C.c_float, C.c_float, C.c_float, i32,
+                                                        C.POINTER(vp)]
+    L.dvo_b200_match_batch_sharded.argtypes = [vp, C.POINTER(Config), i32, C.POINTER(vp), C.POINTER(vp), dp, C.POINTER(CResult),
+                                               C.POINTER(IterationStats), i32]
     L.dvo_b200_pyramid_retain.argtypes = [vp]
     L.dvo_b200_pyramid_release.argtypes = [vp]
     L.dvo_b200_pyramid_num_levels.argtypes = [vp]
@@ -377,3 +393,66 @@ class Engine:
         self._check(self.lib.dvo_b200_profile_read(self.ctx, ms, ln, int(reset)))
         names = ["residual", "normal", "pair_step", "pyramid", "select"]
         return {names[i]: {"ms": ms[i], "launches": ln[i]} for i in range(len(names))}
+
+
+class ShardedEngine:
+    """dvo_b200_sharded: one process, one context + host thread per device, contiguous shards of pair indices
+    (the C-ABI form of the multi-GPU path; the multi-process form is dvo_slam_b200/distributed.py)."""
+
+    def __init__(self, devices):
+        self.lib = load_library()
+        devs = (C.c_int32 * len(devices))(*devices)
+        h = C.c_void_p()
+        rc = self.lib.dvo_b200_sharded_create(len(devices), devs, C.byref(h))
+        if rc != 0:
+            raise RuntimeError(f"dvo_b200_sharded_create({list(devices)}) failed with status {rc}: no usable CUDA device "
+                               "(the engine has no CPU fallback)")
+        self.h = h
+        self.devices = list(devices)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.dvo_b200_sharded_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise RuntimeError(f"dvo_b200 sharded status {rc}: {self.lib.dvo_b200_sharded_last_error(self.h).decode()}")
+
+    def shard_range(self, total, shard):
+        b, e = C.c_int64(), C.c_int64()
+        self._check(self.lib.dvo_b200_shard_range(total, len(self.devices), shard, C.byref(b), C.byref(e)))
+        return b.value, e.value
+
+    def pyramid_batch(self, intensity, depth, intrinsics, levels):
+        """intensity, depth: float32 arrays [n, h, w] on the host -> n pyramid handles (image i on its shard's device)."""
+        I = np.ascontiguousarray(intensity, dtype=np.float32)
+        Z = np.ascontiguousarray(depth, dtype=np.float32)
+        n, h, w = I.shape
+        out = (C.c_void_p * n)()
+        fx, fy, ox, oy = [float(v) for v in intrinsics]
+        self._check(self.lib.dvo_b200_sharded_pyramid_create_batch(self.h, n, I.ctypes.data, Z.ctypes.data, w, h, fx, fy, ox, oy, levels, out))
+        return [C.c_void_p(v) for v in out]
+
+    def release(self, handles):
+        for p in handles:
+            self.lib.dvo_b200_pyramid_release(p)
+
+    def match_batch(self, refs, curs, cfg: Config, T_init=None):
+        n = len(refs)
+        rh = (C.c_void_p * n)(*[p.value for p in refs])
+        ch = (C.c_void_p * n)(*[p.value for p in curs])
+        T = None
+        if T_init is not None:
+            T = np.ascontiguousarray(np.asarray(T_init, dtype=np.float64).reshape(n, 16))
+        res = (CResult * n)()
+        self._check(self.lib.dvo_b200_match_batch_sharded(self.h, C.byref(cfg), n, rh, ch,
+                                                          T.ctypes.data_as(C.POINTER(C.c_double)) if T is not None else None,
+                                                          res, None, 0))
+        return res

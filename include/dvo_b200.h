@@ -139,6 +139,7 @@ int dvo_b200_pyramid_create_raw_batch(dvo_b200_ctx* ctx, int32_t n, const uint8_
 int dvo_b200_pyramid_create_bgr_batch(dvo_b200_ctx* ctx, int32_t n, const uint8_t* bgr, const uint16_t* raw_depth,
                                       float depth_scale, int32_t width, int32_t height, float fx, float fy, float ox,
                                       float oy, int32_t levels, dvo_b200_pyramid** out /* n handles */);
+int dvo_b200_pyramid_device(const dvo_b200_pyramid* p);   /* CUDA ordinal the pyramid lives on (-1: null handle) */
 int dvo_b200_pyramid_retain(dvo_b200_pyramid* p);   /* boost::shared_ptr semantics of RgbdImagePyramidPtr */
 int dvo_b200_pyramid_release(dvo_b200_pyramid* p);
 int dvo_b200_pyramid_num_levels(const dvo_b200_pyramid* p);
@@ -173,6 +174,36 @@ int dvo_b200_match_batch(dvo_b200_ctx* ctx, const dvo_b200_config* cfg, int32_t 
 int dvo_b200_match_batch_device(dvo_b200_ctx* ctx, const dvo_b200_config* cfg, int32_t n,
                                 dvo_b200_pyramid* const* references, dvo_b200_pyramid* const* currents,
                                 const double* T_init, void* d_results);
+
+/* ---- one process, several GPUs ----------------------------------------------------
+ * The reference's batch producers are single-process C++ loops over independent match() calls
+ * (constraint_proposal_validator.cpp:141-146, keyframe_graph.cpp:587-590).  A dvo_b200_sharded owns one context per
+ * device; a batch of n pairs is cut into contiguous shards of pair indices (dvo_b200_shard_range: the remainder goes to
+ * the first shards -- the same partition the multi-process path dvo_slam_b200/distributed.py uses), each shard runs on
+ * its own host thread and device, and every shard writes its results into its range of the caller's host array.  The
+ * alignments exchange nothing, so a one-process caller needs no communicator; across processes the gather is one NCCL
+ * all-gather of the records left in device memory by dvo_b200_match_batch_device. */
+typedef struct dvo_b200_sharded dvo_b200_sharded;
+/* devices: n_devices CUDA ordinals, or NULL for 0..n_devices-1 (an ordinal may repeat: two shards on one GPU). */
+int dvo_b200_sharded_create(int32_t n_devices, const int32_t* devices, dvo_b200_sharded** out);
+int dvo_b200_sharded_destroy(dvo_b200_sharded* s);
+int32_t dvo_b200_sharded_num_shards(const dvo_b200_sharded* s);
+dvo_b200_ctx* dvo_b200_sharded_ctx(dvo_b200_sharded* s, int32_t shard);     /* the shard's context (owned by s) */
+const char* dvo_b200_sharded_last_error(dvo_b200_sharded* s);
+int dvo_b200_shard_range(int64_t total, int32_t n_shards, int32_t shard, int64_t* begin, int64_t* end);
+/* n images -> n pyramids, image i on the device of the shard that owns index i of n; blocks until the uploads are done */
+int dvo_b200_sharded_pyramid_create_batch(dvo_b200_sharded* s, int32_t n, const float* intensity, const float* depth,
+                                          int32_t width, int32_t height, float fx, float fy, float ox, float oy,
+                                          int32_t levels, dvo_b200_pyramid** out /* n handles */);
+int dvo_b200_sharded_pyramid_create_raw_batch(dvo_b200_sharded* s, int32_t n, const uint8_t* grey, const uint16_t* raw_depth,
+                                              float depth_scale, int32_t width, int32_t height, float fx, float fy,
+                                              float ox, float oy, int32_t levels, dvo_b200_pyramid** out);
+/* dvo_b200_match_batch over all shards: pair i must live on the device of the shard that owns index i of n (as the two
+ * calls above place them), else DVO_B200_ERR_INVALID_ARGUMENT.  Same result layout as dvo_b200_match_batch. */
+int dvo_b200_match_batch_sharded(dvo_b200_sharded* s, const dvo_b200_config* cfg, int32_t n,
+                                 dvo_b200_pyramid* const* references, dvo_b200_pyramid* const* currents,
+                                 const double* T_init, dvo_b200_result* results,
+                                 dvo_b200_iteration_stats* iteration_stats, int32_t max_iteration_stats);
 
 /* One evaluation of the residual stage at a fixed transform (test / debug; also the basis of
  * DenseTracker::computeIntensityErrorImage, dense_tracking.cpp:378-444): 7 planes

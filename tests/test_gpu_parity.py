@@ -356,3 +356,37 @@ def test_full_size_properties_without_oracle(engine):
         assert dt < 4e-3 and dr < 1.5e-3, (i, dt, dr)
         assert np.allclose(res[i].information, res[i].information.T)
         assert np.linalg.eigvalsh(res[i].information).min() > 0
+
+
+def test_one_process_sharded_batch_equals_single_context(engine, full_pairs):
+    """dvo_b200_match_batch_sharded (one context + host thread per shard; SURVEY 8e, the single-process callers of
+    constraint_proposal_validator.cpp:141-146) returns, in pair order, exactly what one context returns.  Shards: every
+    visible GPU, or two shards on the one GPU when only one is visible (the world-size-2 pattern of the gloo tests)."""
+    import torch
+    from dvo_slam_b200.engine import Config, ShardedEngine
+    ndev = torch.cuda.device_count()
+    devices = list(range(ndev)) if ndev > 1 else [0, 0]
+    cfg = Config(first_level=3, last_level=1, max_iterations_per_level=50, precision=1e-4)
+    order = [0, 1, 2, 3, 2, 0, 3]                 # 7 pairs over the shards: uneven ranges
+    I_ref = np.stack([full_pairs[i]["I_ref"] for i in order]); Z_ref = np.stack([full_pairs[i]["Z_ref"] for i in order])
+    I_cur = np.stack([full_pairs[i]["I_cur"] for i in order]); Z_cur = np.stack([full_pairs[i]["Z_cur"] for i in order])
+    K = full_pairs[0]["K"]
+    sh = ShardedEngine(devices)
+    refs = sh.pyramid_batch(I_ref, Z_ref, K, 4)
+    curs = sh.pyramid_batch(I_cur, Z_cur, K, 4)
+    for k in range(len(devices)):
+        b, e = sh.shard_range(len(order), k)
+        assert all(sh.lib.dvo_b200_pyramid_device(p) == devices[k] for p in refs[b:e] + curs[b:e])
+    res = sh.match_batch(refs, curs, cfg)
+    single = {}
+    for i in sorted(set(order)):
+        a = full_pairs[i]
+        single[i] = engine.match(engine.pyramid(a["I_ref"], a["Z_ref"], K, 4), engine.pyramid(a["I_cur"], a["Z_cur"], K, 4), cfg)
+    for j, i in enumerate(order):
+        assert np.array_equal(np.array(res[j].transformation).reshape(4, 4), single[i].transformation)
+        assert res[j].log_likelihood == single[i].log_likelihood and res[j].num_iterations_total == single[i].num_iterations_total
+    if ndev > 1:       # pairs on the wrong device are refused, not silently copied
+        with pytest.raises(RuntimeError, match="belongs to shard"):
+            sh.match_batch(refs[::-1], curs[::-1], cfg)
+    sh.release(refs + curs)
+    sh.close()

@@ -119,3 +119,27 @@ def test_bench_product_arm_fails_loudly_without_a_device():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "1", "--warmup", "1"], capture_output=True, text=True, timeout=300)
     assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
+
+
+def test_c_abi_shard_range_is_the_partition_of_the_multi_process_path():
+    """dvo_b200_shard_range (one process, one thread per device) and distributed.shard_range (one rank per GPU) own the
+    same pair indices; without a device the sharded front end refuses to start (no CPU fallback)."""
+    import ctypes as C
+    import torch
+    from dvo_slam_b200 import engine
+    from dvo_slam_b200.distributed import shard_range
+    L = engine.load_library()
+    for total in (0, 1, 7, 512, 4096, 4099):
+        for n in (1, 2, 3, 8):
+            covered = []
+            for k in range(n):
+                b, e = C.c_int64(), C.c_int64()
+                assert L.dvo_b200_shard_range(total, n, k, C.byref(b), C.byref(e)) == 0
+                assert (b.value, e.value) == shard_range(total, n, k)
+                covered += list(range(b.value, e.value))
+            assert covered == list(range(total))
+    b, e = C.c_int64(), C.c_int64()
+    assert L.dvo_b200_shard_range(10, 2, 2, C.byref(b), C.byref(e)) != 0      # shard out of range
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="no usable CUDA device"):
+            engine.ShardedEngine([0, 0])
