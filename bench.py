@@ -91,6 +91,7 @@ def parse_args():
     ap.add_argument("--config", type=int, default=2, help="BASELINE.json configs index + 1 style: 2/3 = 640x480x5 (default), 5 = 1280x960x6 mu=0.05")
     ap.add_argument("--cpu-sample", type=int, default=0, help="pairs in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-consecutive", action="store_true", help="skip the consecutive-frames e2e leg")
     return ap.parse_args()
 
 
@@ -464,6 +465,58 @@ def run_ours(args, rank, local_rank, world):
     if not worst < 2e-3:
         raise SystemExit(f"e2e leg disagrees with the resident leg: max |dT| = {worst}")
 
+    # ---- e2e on CONSECUTIVE frames (dvo_slam's odometry workload, local_tracker.cpp:172-184: frame k is the current image of
+    # alignment k-1 and the reference of alignment k): B alignments over sequences of 17 frames, every frame uploaded and its
+    # pyramid built ONCE per step.  Reported next to the headline e2e (which uploads 2B images for B independent pairs).
+    e2e_seq = None
+    if not args.no_consecutive and W == 640:
+        SEQ = 16                                   # alignments per sequence
+        nseq = (B + SEQ - 1) // SEQ
+        nfr = nseq * (SEQ + 1)
+        sG = torch.empty((nfr, H, W), dtype=torch.uint8).pin_memory()
+        sD = torch.empty((nfr, H, W), dtype=torch.uint16).pin_memory()
+        for q in range(nseq):
+            frames, _ = synth.make_sequence(10000 + rank * nseq + q, SEQ + 1, scfg, device=dev)
+            for k, (fi, fz) in enumerate(frames):
+                sG[q * (SEQ + 1) + k].copy_(fi.to(torch.uint8))
+                sD[q * (SEQ + 1) + k].copy_(torch.where(torch.isnan(fz), torch.zeros_like(fz), torch.round(fz * 5000.0)).to(torch.int32).to(torch.uint16))
+        torch.cuda.synchronize()
+        ref_idx = [q * (SEQ + 1) + k for q in range(nseq) for k in range(SEQ)][:B]
+
+        def seq_loader(steps, q):
+            for _ in range(steps):
+                q.put(engines[1].pyramid_raw_batch((sG.data_ptr(), sD.data_ptr(), nfr, H, W), 1.0 / 5000.0, K, LEVELS))
+
+        def seq_tracker(steps, q):
+            out = None
+            for _ in range(steps):
+                pyr = q.get()
+                out = engines[0].match_batch([pyr[i] for i in ref_idx], [pyr[i + 1] for i in ref_idx], cfg, raw=True)
+                for p in pyr:
+                    p.release()
+            return out
+
+        def run_seq(steps):
+            q = queue.Queue(maxsize=1)
+            f0 = pool.submit(seq_loader, steps, q)
+            f1 = pool.submit(seq_tracker, steps, q)
+            f0.result()
+            return f1.result()
+
+        run_seq(2)
+        barrier()
+        t0 = time.perf_counter()
+        res_seq = run_seq(args.steps)
+        barrier()
+        ms_seq = torch.tensor([(time.perf_counter() - t0) * 1e3 / args.steps], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms_seq, op=dist.ReduceOp.MAX)
+        ms_seq = float(ms_seq.item())
+        e2e_seq = {"value": total / (ms_seq * 1e-3), "unit": "alignments/s", "ms_per_step": ms_seq,
+                   "h2d_bytes_per_step": nfr * npx * 3, "d2h_bytes_per_step": d2h_per_step,
+                   "workload": f"{nseq} sequences of {SEQ + 1} consecutive frames per GPU = {B} alignments, each frame uploaded once",
+                   "iterations_total_mean": float(np.mean([res_seq[i].num_iterations_total for i in range(B)]))}
+
     # ---- single-pair latency (configs[1]) ----
     lat_ms = None
     if rank == 0:
@@ -514,6 +567,7 @@ def run_ours(args, rank, local_rank, world):
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                              "kernel_share_of_step": stage_ms / ms_per_step if ms_per_step else None,
                              "pair_step_ms_per_step": prof["pair_step"]["ms"] / args.steps},
+                "e2e_consecutive_frames": e2e_seq,
                 "cpu_baseline": cpu, "clocks": clocks, "single_pair_latency_ms": lat_ms}
         print(json.dumps(line))
 

@@ -54,28 +54,13 @@ static void drain_profile(dvo_b200_ctx* ctx) {
 
 namespace {
 
-__global__ void k_convert_raw(const uint8_t* __restrict__ grey, const uint16_t* __restrict__ raw, float scale,
-                              float* __restrict__ I, float* __restrict__ Z, int n) {
-  // benchmark_slam.cpp:58-77: grey u8 -> f32; SurfacePyramid::convertRawDepthImageSse
-  // (surface_pyramid.cpp:65-105): u16 * scale, 0 -> NaN
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  I[i] = (float)grey[i];
-  uint16_t r = raw[i];
-  Z[i] = r == 0 ? __int_as_float(0x7fc00000) : __fmul_rn((float)r, scale);
-}
-
-__global__ void k_convert_bgr(const uint8_t* __restrict__ bgr, const uint16_t* __restrict__ raw, float scale,
-                              float* __restrict__ I, float* __restrict__ Z, int n) {
-  // benchmark_slam.cpp:58-68: cv::cvtColor(rgb, grey, CV_BGR2GRAY) on CV_8UC3, then convertTo(CV_32F).
-  // OpenCV's 8-bit path is fixed point: (B*1868 + G*9617 + R*4899 + (1 << 13)) >> 14.
+__global__ void k_convert_bgr(const uint8_t* __restrict__ bgr, uint8_t* __restrict__ grey, int n) {
+  // benchmark_slam.cpp:58-68: cv::cvtColor(rgb, grey, CV_BGR2GRAY) on CV_8UC3 (convertTo(CV_32F) happens in the pyramid
+  // kernels' loads).  OpenCV's 8-bit path is fixed point: (B*1868 + G*9617 + R*4899 + (1 << 13)) >> 14.
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint8_t* p = bgr + 3 * (size_t)i;
-  const int grey = (1868 * (int)p[0] + 9617 * (int)p[1] + 4899 * (int)p[2] + 8192) >> 14;
-  I[i] = (float)grey;
-  uint16_t r = raw[i];
-  Z[i] = r == 0 ? __int_as_float(0x7fc00000) : __fmul_rn((float)r, scale);
+  grey[i] = (uint8_t)((1868 * (int)p[0] + 9617 * (int)p[1] + 4899 * (int)p[2] + 8192) >> 14);
 }
 
 }  // namespace
@@ -184,21 +169,18 @@ int dvo_b200_pyramid_create_raw_batch(dvo_b200_ctx* ctx, int32_t n, const uint8_
   if (!ctx || !grey || !raw_depth || !out || n <= 0 || width <= 0 || height <= 0)
     return set_error(ctx, DVO_B200_ERR_INVALID_ARGUMENT, "pyramid_create_raw: null/invalid argument");
   cudaSetDevice(ctx->device);
+  // the frames stay in their file representation (3 bytes per pixel) in the device staging area; the pyramid kernels
+  // convert in their loads (no float32 copy of the frame is written, no conversion kernel)
   size_t npx = (size_t)width * height * n;
-  size_t fbytes = npx * sizeof(float);
-  size_t raw_off = 2 * fbytes;
-  int rc = ensure_stage(ctx, raw_off + npx * 3 + 64, 0);
+  const size_t grey_off = (npx * 2 + 255) / 256 * 256;
+  int rc = ensure_stage(ctx, grey_off + npx + 64, 0);
   if (rc) return rc;
-  float* dI = (float*)ctx->d_stage;
-  float* dZ = dI + npx;
-  uint16_t* dR = (uint16_t*)((char*)ctx->d_stage + raw_off);
-  uint8_t* dG = (uint8_t*)((char*)ctx->d_stage + raw_off + npx * 2);
+  uint16_t* dR = (uint16_t*)ctx->d_stage;
+  uint8_t* dG = (uint8_t*)((char*)ctx->d_stage + grey_off);
   DVO_CUDA(ctx, cudaMemcpyAsync(dR, raw_depth, npx * 2, cudaMemcpyHostToDevice, ctx->stream));
   DVO_CUDA(ctx, cudaMemcpyAsync(dG, grey, npx, cudaMemcpyHostToDevice, ctx->stream));
   ctx->h2d_bytes += npx * 3;
-  k_convert_raw<<<(unsigned)((npx + 255) / 256), 256, 0, ctx->stream>>>(dG, dR, depth_scale, dI, dZ, (int)npx);
-  ctx->launches++;
-  return pyramid_build_batch(ctx, n, dI, dZ, width, height, fx, fy, ox, oy, levels, 0.f, 0.f, out);
+  return pyramid_build_batch_input(ctx, n, dG, dR, 1, depth_scale, width, height, fx, fy, ox, oy, levels, 0.f, 0.f, out);
 }
 
 int dvo_b200_pyramid_create_bgr_batch(dvo_b200_ctx* ctx, int32_t n, const uint8_t* bgr, const uint16_t* raw_depth,
@@ -208,20 +190,18 @@ int dvo_b200_pyramid_create_bgr_batch(dvo_b200_ctx* ctx, int32_t n, const uint8_
     return set_error(ctx, DVO_B200_ERR_INVALID_ARGUMENT, "pyramid_create_bgr: null/invalid argument");
   cudaSetDevice(ctx->device);
   size_t npx = (size_t)width * height * n;
-  size_t fbytes = npx * sizeof(float);
-  size_t raw_off = 2 * fbytes;
-  int rc = ensure_stage(ctx, raw_off + npx * 5 + 64, 0);
+  const size_t grey_off = (npx * 2 + 255) / 256 * 256, bgr_off = grey_off + (npx + 255) / 256 * 256;
+  int rc = ensure_stage(ctx, bgr_off + npx * 3 + 64, 0);
   if (rc) return rc;
-  float* dI = (float*)ctx->d_stage;
-  float* dZ = dI + npx;
-  uint16_t* dR = (uint16_t*)((char*)ctx->d_stage + raw_off);
-  uint8_t* dC = (uint8_t*)((char*)ctx->d_stage + raw_off + npx * 2);
+  uint16_t* dR = (uint16_t*)ctx->d_stage;
+  uint8_t* dG = (uint8_t*)((char*)ctx->d_stage + grey_off);
+  uint8_t* dC = (uint8_t*)((char*)ctx->d_stage + bgr_off);
   DVO_CUDA(ctx, cudaMemcpyAsync(dR, raw_depth, npx * 2, cudaMemcpyHostToDevice, ctx->stream));
   DVO_CUDA(ctx, cudaMemcpyAsync(dC, bgr, npx * 3, cudaMemcpyHostToDevice, ctx->stream));
   ctx->h2d_bytes += npx * 5;
-  k_convert_bgr<<<(unsigned)((npx + 255) / 256), 256, 0, ctx->stream>>>(dC, dR, depth_scale, dI, dZ, (int)npx);
+  k_convert_bgr<<<(unsigned)((npx + 255) / 256), 256, 0, ctx->stream>>>(dC, dG, (int)npx);   // 8-bit grey, as cv::cvtColor leaves it
   ctx->launches++;
-  return pyramid_build_batch(ctx, n, dI, dZ, width, height, fx, fy, ox, oy, levels, 0.f, 0.f, out);
+  return pyramid_build_batch_input(ctx, n, dG, dR, 1, depth_scale, width, height, fx, fy, ox, oy, levels, 0.f, 0.f, out);
 }
 
 int dvo_b200_pyramid_create_raw(dvo_b200_ctx* ctx, const uint8_t* grey, const uint16_t* raw_depth, float depth_scale,

@@ -87,6 +87,7 @@ struct dvo_b200_pyramid {
   float* tmpl = nullptr;         // device: per level tx[w], ty[h] point-cloud template (rgbd_image.cpp:197-198)
   float2* tile_range = nullptr;  // device: per level, per tile {min, max} of the non-NaN Z' (min > max: none)
   float sel_ti = 0.f, sel_td = 0.f;  // thresholds the masks were built with
+  std::mutex sel_mu;                 // guards sel_ti / sel_td and the enqueueing of a re-selection
   uint64_t id = 0;
 };
 
@@ -204,6 +205,8 @@ struct ProfScope {
 // pyramid.cu
 int pyramid_build_batch(dvo_b200_ctx* ctx, int n, const float* d_I, const float* d_Z, int w, int h, float fx, float fy,
                         float ox, float oy, int levels, float ti, float td, dvo_b200_pyramid** out);
+int pyramid_build_batch_input(dvo_b200_ctx* ctx, int n, const void* d_I, const void* d_Z, int raw, float zscale, int w, int h,
+                              float fx, float fy, float ox, float oy, int levels, float ti, float td, dvo_b200_pyramid** out);
 int pyramid_reselect(dvo_b200_ctx* ctx, dvo_b200_pyramid* p, float ti, float td);
 void pyramid_free(dvo_b200_pyramid* p);
 void pool_close(dvo_b200_ctx* ctx);

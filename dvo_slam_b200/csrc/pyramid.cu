@@ -14,11 +14,29 @@ namespace {
 
 __device__ __forceinline__ bool is_nan(float v) { return v != v; }
 
+// Level-0 pixels as they were uploaded.  kRaw = false: float32 intensity and float32 depth in metres (NaN = invalid), what
+// benchmark_slam.cpp:46-93 hands to RgbdCameraPyramid::create.  kRaw = true: 8-bit grey and 16-bit raw depth straight from
+// the image files; the loader's conversions -- convertTo(CV_32F) and SurfacePyramid::convertRawDepthImageSse
+// (surface_pyramid.cpp:65-105: u16 * scale, 0 -> NaN) -- happen in the load, no float32 copy of the frame is ever written.
+template <bool kRaw>
+__device__ __forceinline__ float load_intensity(const void* I, size_t i) {
+  if (kRaw) return (float)__ldg(reinterpret_cast<const uint8_t*>(I) + i);
+  return __ldg(reinterpret_cast<const float*>(I) + i);
+}
+template <bool kRaw>
+__device__ __forceinline__ float load_depth(const void* Z, size_t i, float scale) {
+  if (kRaw) {
+    const uint16_t r = __ldg(reinterpret_cast<const uint16_t*>(Z) + i);
+    return r == 0 ? __int_as_float(0x7fc00000) : __fmul_rn((float)r, scale);
+  }
+  return __ldg(reinterpret_cast<const float*>(Z) + i);
+}
+
 // level l intensity = ((a+b)+c)+d)/4 of the 2x2 block of level l-1 (rgbd_image.cpp:38-55), into P0.x (the Z slot is
 // filled by the finish pass).  kFromInput: level 1 reads the input image, which is level 0's intensity.
 // sp / dp: row pitch of the source / destination planes (float2 elements).
-template <bool kFromInput>
-__global__ void k_pyr_intensity_down(const float* __restrict__ I0, size_t in_stride, int aligned, float2* __restrict__ planes,
+template <bool kFromInput, bool kRaw>
+__global__ void k_pyr_intensity_down(const void* __restrict__ I0, size_t in_stride, int aligned, float2* __restrict__ planes,
                                      size_t planes_per_image, size_t src_off, int sw, int sp, size_t dst_off, int dw, int dh,
                                      int dp) {
   int img = blockIdx.y;
@@ -28,12 +46,23 @@ __global__ void k_pyr_intensity_down(const float* __restrict__ I0, size_t in_str
   float2* D = planes + img * planes_per_image + dst_off;
   float a, b, c, d;
   if (kFromInput) {
-    const float* p0 = I0 + (size_t)img * in_stride + (size_t)(2 * y) * sw + 2 * x;
-    if (aligned) {   // even width and image stride: every 2x2 block starts 8-byte aligned
-      const float2 u = __ldg(reinterpret_cast<const float2*>(p0)), v = __ldg(reinterpret_cast<const float2*>(p0 + sw));
-      a = u.x; b = u.y; c = v.x; d = v.y;
+    const size_t i0 = (size_t)img * in_stride + (size_t)(2 * y) * sw + 2 * x;
+    if (kRaw) {
+      const uint8_t* g = reinterpret_cast<const uint8_t*>(I0) + i0;
+      if (aligned) {   // even width and image stride: every 2x2 block starts 2-byte aligned
+        const uchar2 u = __ldg(reinterpret_cast<const uchar2*>(g)), v = __ldg(reinterpret_cast<const uchar2*>(g + sw));
+        a = (float)u.x; b = (float)u.y; c = (float)v.x; d = (float)v.y;
+      } else {
+        a = (float)__ldg(g); b = (float)__ldg(g + 1); c = (float)__ldg(g + sw); d = (float)__ldg(g + sw + 1);
+      }
     } else {
-      a = __ldg(p0); b = __ldg(p0 + 1); c = __ldg(p0 + sw); d = __ldg(p0 + sw + 1);
+      const float* p0 = reinterpret_cast<const float*>(I0) + i0;
+      if (aligned) {   // even width and image stride: every 2x2 block starts 8-byte aligned
+        const float2 u = __ldg(reinterpret_cast<const float2*>(p0)), v = __ldg(reinterpret_cast<const float2*>(p0 + sw));
+        a = u.x; b = u.y; c = v.x; d = v.y;
+      } else {
+        a = __ldg(p0); b = __ldg(p0 + 1); c = __ldg(p0 + sw); d = __ldg(p0 + sw + 1);
+      }
     }
   } else {
     const float2* S = planes + img * planes_per_image + src_off;
@@ -54,9 +83,9 @@ __global__ void k_pyr_intensity_down(const float* __restrict__ I0, size_t in_str
 // intensity that k_pyr_intensity_down left in P0.x.  The selection count / last selected index are derived from
 // the masks afterwards (k_sel_info): no atomics here.  Threads walk the linear pixel index y*w+x (the order of the
 // selection mask); the planes are addressed with the row pitch.
-template <bool kLevel0>
+template <bool kLevel0, bool kRaw>
 __global__ void __launch_bounds__(256)
-k_pyr_finish(const float* __restrict__ I0, const float* __restrict__ Z0, int w0, int n0, float2* __restrict__ planes,
+k_pyr_finish(const void* __restrict__ I0, const void* __restrict__ Z0, float zscale, int w0, int n0, float2* __restrict__ planes,
              size_t planes_per_image, size_t plane_off, int w, int h, int pitch, int level,
              uint32_t* __restrict__ masks, size_t mask_words_per_image, size_t mask_off, float ti, float td) {
   const int img = blockIdx.y;
@@ -71,13 +100,12 @@ k_pyr_finish(const float* __restrict__ I0, const float* __restrict__ Z0, int w0,
     float2* P1 = P0 + plane;
     float2* P2 = P1 + plane;
     float2* P3 = P2 + plane;   // P2 = (I, Z), P3 = (I, Zsel); the depth gradients are not stored
-    const float* Z = Z0 + (size_t)img * n0;
+    const size_t zb = (size_t)img * n0;
     const int xp = max(x - 1, 0), xn = min(x + 1, w - 1), yp = max(y - 1, 0), yn = min(y + 1, h - 1);
     float I, ixp, ixn, iyp, iyn;
     if (kLevel0) {
-      const float* Ii = I0 + (size_t)img * n0;
-      I = __ldg(Ii + idx); ixp = __ldg(Ii + y * w + xp); ixn = __ldg(Ii + y * w + xn);
-      iyp = __ldg(Ii + yp * w + x); iyn = __ldg(Ii + yn * w + x);
+      I = load_intensity<kRaw>(I0, zb + idx); ixp = load_intensity<kRaw>(I0, zb + y * w + xp); ixn = load_intensity<kRaw>(I0, zb + y * w + xn);
+      iyp = load_intensity<kRaw>(I0, zb + yp * w + x); iyn = load_intensity<kRaw>(I0, zb + yn * w + x);
     } else {
       const size_t row = (size_t)y * pitch;
       I = P0[row + x].x; ixp = P0[row + xp].x; ixn = P0[row + xn].x;
@@ -86,9 +114,10 @@ k_pyr_finish(const float* __restrict__ I0, const float* __restrict__ Z0, int w0,
     const float ix = (ixn - ixp) * 0.5f;
     const float iy = (iyn - iyp) * 0.5f;
     const size_t zr = (size_t)(y << level) * w0;
-    const float z = __ldg(Z + zr + (x << level));
-    const float zx = (__ldg(Z + zr + (xn << level)) - __ldg(Z + zr + (xp << level))) * 0.5f;
-    const float zy = (__ldg(Z + (size_t)(yn << level) * w0 + (x << level)) - __ldg(Z + (size_t)(yp << level) * w0 + (x << level))) * 0.5f;
+    const float z = load_depth<kRaw>(Z0, zb + zr + (x << level), zscale);
+    const float zx = (load_depth<kRaw>(Z0, zb + zr + (xn << level), zscale) - load_depth<kRaw>(Z0, zb + zr + (xp << level), zscale)) * 0.5f;
+    const float zy = (load_depth<kRaw>(Z0, zb + (size_t)(yn << level) * w0 + (x << level), zscale) -
+                      load_depth<kRaw>(Z0, zb + (size_t)(yp << level) * w0 + (x << level), zscale)) * 0.5f;
     const bool bad = is_nan(I) || is_nan(ix) || is_nan(iy) || is_nan(z) || is_nan(zx) || is_nan(zy);
     const float zm = bad ? __int_as_float(0x7fc00000) : z;
     const size_t o = (size_t)y * pitch + x;
@@ -272,6 +301,12 @@ void pool_close(dvo_b200_ctx* ctx) {
 
 int pyramid_build_batch(dvo_b200_ctx* ctx, int n, const float* d_I, const float* d_Z, int w, int h, float fx, float fy,
                         float ox, float oy, int levels, float ti, float td, dvo_b200_pyramid** out) {
+  return pyramid_build_batch_input(ctx, n, d_I, d_Z, 0, 0.f, w, h, fx, fy, ox, oy, levels, ti, td, out);
+}
+
+// d_I / d_Z: raw == 0: float32 intensity / float32 depth; raw == 1: 8-bit grey / 16-bit raw depth (depth = raw * zscale, 0 -> NaN)
+int pyramid_build_batch_input(dvo_b200_ctx* ctx, int n, const void* d_I, const void* d_Z, int raw, float zscale, int w, int h,
+                              float fx, float fy, float ox, float oy, int levels, float ti, float td, dvo_b200_pyramid** out) {
   if (n <= 0 || levels < 1 || levels > kMaxLevels || w < 32 || h < 2)
     return set_error(ctx, DVO_B200_ERR_INVALID_ARGUMENT, "pyramid: bad geometry");
   LevelInfo L[kMaxLevels];
@@ -328,15 +363,19 @@ int pyramid_build_batch(dvo_b200_ctx* ctx, int n, const float* d_I, const float*
       ctx->launches += 1;
       if (l == 0) continue;   // level 0 takes its intensity from the input image
       dim3 g((q.n + T - 1) / T, n);
-      if (l == 1) k_pyr_intensity_down<true><<<g, T, 0, st>>>(d_I, (size_t)w * h, (((size_t)w * h) | (size_t)w) % 2 == 0 ? 1 : 0, planes, plane_f2, 0, L[0].w, L[0].pitch, q.plane_off, q.w, q.h, q.pitch);
-      else k_pyr_intensity_down<false><<<g, T, 0, st>>>(nullptr, 0, 0, planes, plane_f2, L[l - 1].plane_off, L[l - 1].w, L[l - 1].pitch, q.plane_off, q.w, q.h, q.pitch);
+      const int aligned = (((size_t)w * h) | (size_t)w) % 2 == 0 ? 1 : 0;
+      if (l == 1 && raw) k_pyr_intensity_down<true, true><<<g, T, 0, st>>>(d_I, (size_t)w * h, aligned, planes, plane_f2, 0, L[0].w, L[0].pitch, q.plane_off, q.w, q.h, q.pitch);
+      else if (l == 1) k_pyr_intensity_down<true, false><<<g, T, 0, st>>>(d_I, (size_t)w * h, aligned, planes, plane_f2, 0, L[0].w, L[0].pitch, q.plane_off, q.w, q.h, q.pitch);
+      else k_pyr_intensity_down<false, false><<<g, T, 0, st>>>(nullptr, 0, 0, planes, plane_f2, L[l - 1].plane_off, L[l - 1].w, L[l - 1].pitch, q.plane_off, q.w, q.h, q.pitch);
       ctx->launches += 1;
     }
     for (int l = 0; l < levels; ++l) {
       const LevelInfo& q = L[l];
       dim3 g((q.words * 32 + T - 1) / T, n);
-      if (l == 0) k_pyr_finish<true><<<g, T, 0, st>>>(d_I, d_Z, w, w * h, planes, plane_f2, q.plane_off, q.w, q.h, q.pitch, l, masks, mask_words, q.mask_off, ti, td);
-      else k_pyr_finish<false><<<g, T, 0, st>>>(d_I, d_Z, w, w * h, planes, plane_f2, q.plane_off, q.w, q.h, q.pitch, l, masks, mask_words, q.mask_off, ti, td);
+      if (l == 0 && raw) k_pyr_finish<true, true><<<g, T, 0, st>>>(d_I, d_Z, zscale, w, w * h, planes, plane_f2, q.plane_off, q.w, q.h, q.pitch, l, masks, mask_words, q.mask_off, ti, td);
+      else if (l == 0) k_pyr_finish<true, false><<<g, T, 0, st>>>(d_I, d_Z, zscale, w, w * h, planes, plane_f2, q.plane_off, q.w, q.h, q.pitch, l, masks, mask_words, q.mask_off, ti, td);
+      else if (raw) k_pyr_finish<false, true><<<g, T, 0, st>>>(d_I, d_Z, zscale, w, w * h, planes, plane_f2, q.plane_off, q.w, q.h, q.pitch, l, masks, mask_words, q.mask_off, ti, td);
+      else k_pyr_finish<false, false><<<g, T, 0, st>>>(d_I, d_Z, zscale, w, w * h, planes, plane_f2, q.plane_off, q.w, q.h, q.pitch, l, masks, mask_words, q.mask_off, ti, td);
       k_sel_info<<<n, 32, 0, st>>>(masks, mask_words, q.mask_off, q.words, sel, sel_ints, l);
       k_drop_odd_last<<<(n + 127) / 128, 128, 0, st>>>(planes, plane_f2, q.plane_off, q.w, q.h, q.pitch, sel, sel_ints, l, n);
       const int ntiles = q.nbands * q.nstrips;
@@ -365,7 +404,15 @@ int pyramid_build_batch(dvo_b200_ctx* ctx, int n, const float* d_I, const float*
   return 0;
 }
 
+// The selection (mask, {S, last}, the Zsel channel of P3) is state of the PYRAMID, shared by every context that aligns
+// against it, while the reference keeps it per tracker (PointSelection, point_selection.cpp:100-113).  Contexts that use
+// the same thresholds -- every caller in dvo_slam: one configuration per tracker family -- never get here twice.  A context
+// that asks for other thresholds rewrites the selection on its stream; the host-side state is guarded by sel_mu and the
+// slab's ready event is re-recorded, so a context that enqueues work on this pyramid LATER waits for the rewrite.  What is
+// not supported: two contexts aligning against one reference pyramid with different thresholds at the same time
+// (limits).
 int pyramid_reselect(dvo_b200_ctx* ctx, dvo_b200_pyramid* p, float ti, float td) {
+  std::lock_guard<std::mutex> lock(p->sel_mu);
   if (p->sel_ti == ti && p->sel_td == td) return 0;
   cudaStream_t st = ctx->stream;
   ProfScope prof(ctx, 4, 3 * p->levels);
@@ -378,6 +425,7 @@ int pyramid_reselect(dvo_b200_ctx* ctx, dvo_b200_pyramid* p, float ti, float td)
     ctx->launches += 3;
   }
   DVO_CUDA(ctx, cudaGetLastError());
+  if (p->slab && p->slab->ready) DVO_CUDA(ctx, cudaEventRecord(p->slab->ready, st));
   p->sel_ti = ti; p->sel_td = td;
   return 0;
 }

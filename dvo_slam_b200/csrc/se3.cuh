@@ -107,13 +107,20 @@ DVO_HD SE3d se3_exp(const double a[6]) {
   const double wx = a[3], wy = a[4], wz = a[5];
   double theta = sqrt(wx * wx + wy * wy + wz * wz);
   double half = 0.5 * theta, imag, real;
+  double sh = 0.0, ch = 1.0, st = 0.0, ct = 1.0;
   if (theta < DVO_SE3_EPS) {
     double t2 = theta * theta, t4 = t2 * t2;
     imag = 0.5 - t2 / 48.0 + t4 / 3840.0;
     real = 1.0 - t2 / 8.0 + t4 / 384.0;
   } else {
-    imag = sin(half) / theta;
-    real = cos(half);
+#ifdef __CUDA_ARCH__
+    sincos(half, &sh, &ch);     // one argument reduction for the pair (same values as sin() / cos())
+    sincos(theta, &st, &ct);
+#else
+    sh = sin(half); ch = cos(half); st = sin(theta); ct = cos(theta);
+#endif
+    imag = sh / theta;
+    real = ch;
   }
   SE3d r;
   r.qw = real; r.qx = imag * wx; r.qy = imag * wy; r.qz = imag * wz;
@@ -129,8 +136,8 @@ DVO_HD SE3d se3_exp(const double a[6]) {
     return r;
   }
   double t2 = theta * theta;
-  c1 = (1.0 - cos(theta)) / t2;
-  c2 = (theta - sin(theta)) / (t2 * theta);
+  c1 = (1.0 - ct) / t2;
+  c2 = (theta - st) / (t2 * theta);
   double cx = wy * a[2] - wz * a[1], cy = wz * a[0] - wx * a[2], cz = wx * a[1] - wy * a[0];  // w x v
   double dx = wy * cz - wz * cy, dy = wz * cx - wx * cz, dz = wx * cy - wy * cx;              // w x (w x v)
   r.tx = a[0] + c1 * cx + c2 * dx;

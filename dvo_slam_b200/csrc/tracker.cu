@@ -726,7 +726,7 @@ struct GroupPlan {
 int level_squad_size(int nstrips, int nbands, int grid, int npairs) {
   const char* env = getenv("DVO_B200_STRIPS_PER_CTA");     // developer override (experiments)
   const int forced_spc = env ? atoi(env) : 0;
-  const double overhead_tiles = 3.0;
+  const double overhead_tiles = 20.0;   // per stage: squad barrier + serial step + pipeline fill, in tile-times (fitted: g = 2..5 within 1 % at batch 512, g >= 6 and g = 1 slower)
   int best_g = 1;
   double best_cost = -1.0;
   for (int spc = 1; spc <= nstrips; ++spc) {
@@ -755,20 +755,25 @@ int plan_groups(const dvo_b200_pyramid* ref, int first, int last, int grid, int 
   }
   int ngroups = 0;
   const bool walk = npairs >= grid / 4 && !getenv("DVO_B200_NO_WALK");
+  const int coarse_tiles = getenv("DVO_B200_COARSE_TILES") ? atoi(getenv("DVO_B200_COARSE_TILES")) : 40;   // developer override
   for (int li = 0; li < nlev;) {
     GroupPlan& G = out[ngroups++];
     G.first_li = li; G.nlev = 1; G.g = g_level[li];
     if (walk) {
       const LevelInfo& L0 = ref->L[first - li];
-      const bool coarse = L0.nstrips * L0.nbands <= 40;
+      const bool coarse = L0.nstrips * L0.nbands <= coarse_tiles;
       if (coarse) G.g = 1;
       while (li + G.nlev < nlev) {
         const LevelInfo& Ln = ref->L[first - (li + G.nlev)];
-        const bool coarse_n = Ln.nstrips * Ln.nbands <= 40;
+        const bool coarse_n = Ln.nstrips * Ln.nbands <= coarse_tiles;
         if (coarse_n != coarse) break;
         if (!coarse) G.g = g_level[li + G.nlev];      // the finest level of the group decides
         G.nlev++;
       }
+    }
+    if (const char* fg = getenv("DVO_B200_FINE_G")) {     // developer override (experiments): squad size of the non-coarse groups
+      const LevelInfo& L0 = ref->L[first - li];
+      if (L0.nstrips * L0.nbands > coarse_tiles && atoi(fg) > 0) G.g = std::min(atoi(fg), grid);
     }
     for (int k = 0; k < G.nlev; ++k) {
       const LevelInfo& L = ref->L[first - (li + k)];

@@ -2,6 +2,7 @@
 // libdvo_core.so surface for the hot path) on top of the C ABI of libdvo_b200.so.
 #include <algorithm>
 #include <cassert>
+#include <cmath>
 #include <cstring>
 #include <cstdlib>
 #include <stdexcept>
@@ -187,6 +188,37 @@ void DenseTracker::Result::setIdentity() {
   Transformation.setIdentity();
   Information.setIdentity();
   LogLikelihood = 0.0;
+}
+
+// dense_tracking_config.cpp:122-135.  EstimateInformation = A + mu*I is symmetric, so the real parts the reference takes from
+// Eigen::EigenSolver are the eigenvalues of a symmetric matrix: cyclic Jacobi rotations on a copy, sorted ascending.
+void DenseTracker::IterationStats::InformationEigenValues(core::Vector6d& eigenvalues) const {
+  double a[6][6];
+  for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) a[i][j] = 0.5 * (EstimateInformation(i, j) + EstimateInformation(j, i));
+  for (int sweep = 0; sweep < 64; ++sweep) {
+    double off = 0.0, diag = 0.0;
+    for (int i = 0; i < 6; ++i) { diag += a[i][i] * a[i][i]; for (int j = i + 1; j < 6; ++j) off += a[i][j] * a[i][j]; }
+    if (!(off > 1e-32 * diag)) break;
+    for (int p = 0; p < 5; ++p)
+      for (int q = p + 1; q < 6; ++q) {
+        if (a[p][q] == 0.0) continue;
+        const double theta = (a[q][q] - a[p][p]) / (2.0 * a[p][q]);
+        const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+        const double cs = 1.0 / std::sqrt(t * t + 1.0), sn = t * cs;
+        for (int k = 0; k < 6; ++k) { const double x = a[k][p], y = a[k][q]; a[k][p] = cs * x - sn * y; a[k][q] = sn * x + cs * y; }
+        for (int k = 0; k < 6; ++k) { const double x = a[p][k], y = a[q][k]; a[p][k] = cs * x - sn * y; a[q][k] = sn * x + cs * y; }
+      }
+  }
+  double ev[6];
+  for (int i = 0; i < 6; ++i) ev[i] = a[i][i];
+  std::sort(ev, ev + 6);
+  for (int i = 0; i < 6; ++i) eigenvalues(i) = ev[i];
+}
+
+double DenseTracker::IterationStats::InformationConditionNumber() const {
+  core::Vector6d ev;
+  InformationEigenValues(ev);
+  return std::abs(ev(5) / ev(0));
 }
 
 bool DenseTracker::LevelStats::HasIterationWithIncrement() const {   // dense_tracking_config.cpp:138-143

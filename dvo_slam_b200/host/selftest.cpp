@@ -116,6 +116,12 @@ int main(int argc, char** argv) {
     eval += buf;
   }
   eval += "]";
+  // keyframe_graph.cpp:370-371: condition number of the last accepted iteration's information matrix
+  const dvo::DenseTracker::IterationStats& last_inc = result.Statistics.Levels.back().LastIterationWithIncrement();
+  const double kappa = last_inc.InformationConditionNumber();
+  std::string kappa_info = "[";
+  for (int a = 0; a < 6; ++a) for (int b = 0; b < 6; ++b) { char buf[40]; std::snprintf(buf, sizeof(buf), "%s%.17g", (a + b) ? ", " : "", last_inc.EstimateInformation(a, b)); kappa_info += buf; }
+  kappa_info += "]";
   // keyframe_tracker.cpp usage pattern: constructed from the first result, add() the following ones, ratios of a later one
   dvo_slam::EntropyRatioTrackingResultEvaluation e2(result);
   dvo_slam::LogLikelihoodTrackingResultEvaluation l2(result);
@@ -153,7 +159,7 @@ int main(int argc, char** argv) {
               int(batch_equal), int(proposals_equal), entropy.ratioWithFirst(r_odometry), entropy.ratioWithAverage(r_odometry),
               loglik.ratioWithFirst(result), nloglik.ratioWithAverage(result), std::log(result.Information.determinant()),
               eval.c_str(), e2.ratioWithFirst(r_reverse), e2.ratioWithAverage(r_reverse), l2.ratioWithFirst(r_reverse), l2.ratioWithAverage(r_reverse),
-              n2.ratioWithFirst(r_reverse), n2.ratioWithAverage(r_reverse), nbatch, batch_first_ms, batch_again_ms);
+              n2.ratioWithFirst(r_reverse), n2.ratioWithAverage(r_reverse), nbatch, batch_first_ms, batch_again_ms, kappa, kappa_info.c_str());
   std::cerr << result.Statistics;
   return 0;
 }

@@ -53,6 +53,8 @@ class DenseTracker {
     double PriorLogLikelihood;
     core::Vector6d EstimateIncrement;
     core::Matrix6d EstimateInformation;
+    void InformationEigenValues(core::Vector6d& eigenvalues) const;   // ascending (dense_tracking_config.cpp:122-127)
+    double InformationConditionNumber() const;                        // |ev(5) / ev(0)| (dense_tracking_config.cpp:129-135)
   };
   typedef std::vector<IterationStats> IterationStatsVector;
 
