@@ -154,7 +154,7 @@ int main(int argc, char** argv) {
   std::printf("], \"second_t\": [%.17g, %.17g, %.17g], \"err_sum\": %.9g, \"level1_w\": %d, \"batch_equal\": %d, \"proposals_equal\": %d, "
               "\"entropy_ratio_first\": %.17g, \"entropy_ratio_avg\": %.17g, \"ll_ratio\": %.17g, \"nll_ratio\": %.17g, \"logdet\": %.17g, "
               "\"eval_results\": %s, \"eval\": {\"entropy_first\": %.17g, \"entropy_avg\": %.17g, \"ll_first\": %.17g, \"ll_avg\": %.17g, "
-              "\"nll_first\": %.17g, \"nll_avg\": %.17g}, \"batch\": %d, \"batch_first_ms\": %.3f, \"batch_again_ms\": %.3f}\n",
+              "\"nll_first\": %.17g, \"nll_avg\": %.17g}, \"batch\": %d, \"batch_first_ms\": %.3f, \"batch_again_ms\": %.3f, \"kappa\": %.17g, \"kappa_info\": %s}\n",
               guess.matrix()(0, 3), guess.matrix()(1, 3), guess.matrix()(2, 3), esum, reference->level(1).intensity.cols,
               int(batch_equal), int(proposals_equal), entropy.ratioWithFirst(r_odometry), entropy.ratioWithAverage(r_odometry),
               loglik.ratioWithFirst(result), nloglik.ratioWithAverage(result), std::log(result.Information.determinant()),
