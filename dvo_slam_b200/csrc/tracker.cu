@@ -349,28 +349,40 @@ struct LevelTail {      // shared memory after the tile pipeline
 };
 constexpr size_t kLevelSmemBytes = sizeof(TilePipe) + sizeof(LevelTail);
 
-struct PersistentArgs {
-  PairState* states;
-  const PairLevel* pls;
+// One segment of a launch: a group of consecutive pyramid levels that a squad of g CTAs walks a pair through.  A launch
+// has one segment, or two (the coarse levels with one CTA per pair, then the fine levels with squads of g CTAs) that the
+// grid runs back to back WITHOUT a grid-wide barrier: a CTA that finds the coarse queue empty moves on to the fine
+// segment, and fine squads take their pairs from a ring of pairs whose coarse levels are done (`ready`).
+struct Segment {
+  const PairLevel* pls;   // descriptors of this segment's levels: [level][pair]
   float* row_exports;     // per squad: h segment summaries (one per image row)
   int* row_base;          // per squad: h exclusive prefixes of valid counts, relative to the owning CTA's first row
   float* cta_exports;     // per squad: g segment summaries
   int* cta_base;          // per squad: g exclusive prefixes
   float* partial;         // per squad: g x kNormalValues
   SquadState* squads;
-  int* next_pair;
+  int* queue;             // next pair (first segment) / next ring slot (second segment of a fused launch)
+  unsigned long long* dbg2;  // optional (timing build): {tiles, inexact tiles, skipped tiles, rounds, rounds of inexact tiles, max / min CTA lifetime}
+  unsigned long long* dbg;   // optional: ns spent per CTA in {stage A, stage B, wait A, wait B, mid, end, queue, total}
+  int nlev;               // pyramid levels of the segment (coarse to fine)
+  int g, nsquads;
+  int strips_per_cta[kMaxLevels];
+  LevelLaunch lp[kMaxLevels];
+};
+
+struct PersistentArgs {
+  PairState* states;
+  int* ready;             // fused launch: ring of (pair + 1) whose first segment is done, 0 = not yet written
+  int* ready_tail;
   int* error_flag;
   dvo_b200_iteration_stats* ilog;
   int max_log;
   const double* T_init;   // per pair 4x4 (device memory) or nullptr
-  int nlev;               // pyramid levels this launch walks every pair through (coarse to fine)
   int skip_begin;         // test hook: the pair state was placed by k_set_state
   float* dump;            // test hook: seven record planes of the (single) pair, or nullptr
-  unsigned long long* dbg2;  // optional (timing build): {tiles, inexact tiles, skipped tiles, rounds, rounds of inexact tiles, max / min CTA lifetime}
-  unsigned long long* dbg;   // optional: ns spent per CTA in {stage A, stage B, wait A, wait B, mid, end, queue, total}
-  int npairs, g, nsquads;
-  int strips_per_cta[kMaxLevels];
-  LevelLaunch lp[kMaxLevels];
+  int npairs;
+  int nseg;               // 1, or 2 = fused coarse + fine segments
+  Segment seg[2];
 };
 
 __device__ __forceinline__ unsigned long long global_ns() {
@@ -417,21 +429,10 @@ __device__ __forceinline__ void squad_wait(SquadState* sq, unsigned episode, int
 }
 
 __global__ void __launch_bounds__(kCtaThreads, 2)
-k_level_persistent(PersistentArgs a) {
+k_level_persistent(const __grid_constant__ PersistentArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   TilePipe& tp = *reinterpret_cast<TilePipe*>(smem_raw);
   LevelTail& lt = *reinterpret_cast<LevelTail*>(smem_raw + sizeof(TilePipe));
-
-  const int squad = blockIdx.x / a.g, rank = blockIdx.x - squad * a.g;
-  if (squad >= a.nsquads) return;   // leftover CTAs
-  SquadState* sq = a.squads + squad;
-  int hmax = 0;
-  for (int li = 0; li < a.nlev; ++li) hmax = max(hmax, a.lp[li].h);
-  float* row_exports = a.row_exports + (size_t)squad * hmax * kSegExportFloats;
-  int* row_base = a.row_base + (size_t)squad * hmax;
-  float* cta_exports = a.cta_exports + (size_t)squad * a.g * kSegExportFloats;
-  int* cta_base = a.cta_base + (size_t)squad * a.g;
-  float* partial = a.partial + (size_t)squad * a.g * kNormalValues;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -441,24 +442,54 @@ k_level_persistent(PersistentArgs a) {
   }
   __syncthreads();
   unsigned tile_count = 0;      // tiles staged / consumed by this CTA since the kernel started
-  unsigned episode = 0;
-  unsigned long long t_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t0 = 0, t1 = 0;
-  const bool timing = a.dbg != nullptr && threadIdx.x == 0;
-  PipeTiming tm;
-#ifdef DVO_PIPE_TIMING
-  tm.on = a.dbg != nullptr && lane == 0 && (warp == 0 || warp == kConsumerWarps);   // one consumer warp and the producer
-#endif
-  const unsigned long long t_start = timing ? global_ns() : 0;
+  const bool fused = a.nseg == 2;
 #define DVO_TICK() do { if (timing) t0 = global_ns(); } while (0)
 #define DVO_TOCK(slot) do { if (timing) { t1 = global_ns(); t_acc[slot] += t1 - t0; t0 = t1; } } while (0)
+
+#pragma unroll 1
+  for (int si = 0; si < a.nseg; ++si) {
+  const Segment& S = a.seg[si];
+  const int squad = blockIdx.x / S.g, rank = blockIdx.x - squad * S.g;
+  if (squad >= S.nsquads) continue;   // leftover CTAs of this segment
+  SquadState* sq = S.squads + squad;
+  int hmax = 0;
+  for (int li = 0; li < S.nlev; ++li) hmax = max(hmax, S.lp[li].h);
+  float* row_exports = S.row_exports + (size_t)squad * hmax * kSegExportFloats;
+  int* row_base = S.row_base + (size_t)squad * hmax;
+  float* cta_exports = S.cta_exports + (size_t)squad * S.g * kSegExportFloats;
+  int* cta_base = S.cta_base + (size_t)squad * S.g;
+  float* partial = S.partial + (size_t)squad * S.g * kNormalValues;
+  unsigned episode = 0;
+  unsigned long long t_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t0 = 0, t1 = 0;
+  const bool timing = S.dbg != nullptr && threadIdx.x == 0;
+  PipeTiming tm;
+#ifdef DVO_PIPE_TIMING
+  tm.on = S.dbg != nullptr && lane == 0 && (warp == 0 || warp == kConsumerWarps);   // one consumer warp and the producer
+#endif
+  const unsigned long long t_start = timing ? global_ns() : 0;
 
   for (;;) {
     DVO_TICK();
     // ---- take the next pair from the queue (the last CTA to arrive does it for the squad) ----
-    if (squad_arrive(sq, episode, a.g, lt.s_flag)) {
+    if (squad_arrive(sq, episode, S.g, lt.s_flag)) {
       if (threadIdx.x == 0) {
-        int p = atomicAdd(a.next_pair, 1);
-        sq->pair = p < a.npairs ? p : -1;
+        int p = atomicAdd(S.queue, 1);
+        if (p >= a.npairs) p = -1;
+        else if (fused && si == 1) {
+          // slot p of the ready ring: filled by the CTA that finishes the coarse levels of some pair (every pair is
+          // pushed exactly once, so every slot < npairs is eventually written)
+          unsigned spins = 0;
+          int v;
+          while ((v = (int)ld_acquire_u32(reinterpret_cast<const unsigned*>(a.ready + p))) == 0) {
+            __nanosleep(200);
+            if (((++spins) & 4095u) == 0u) {
+              if (*reinterpret_cast<volatile int*>(a.error_flag)) break;
+              if (spins > (1u << 24)) { atomicExch(a.error_flag, 1); break; }
+            }
+          }
+          p = v - 1;
+        }
+        sq->pair = p;
         squad_release(sq, episode);
       }
     } else {
@@ -472,16 +503,16 @@ k_level_persistent(PersistentArgs a) {
     PairState& st = a.states[pair];
 
     // ---- the squad walks its pair through the levels of this launch, coarse to fine ----
-    for (int li = 0; li < a.nlev; ++li) {
-    const LevelLaunch& lp = a.lp[li];
-    const PairLevel pl = a.pls[(size_t)li * a.npairs + pair];
+    for (int li = 0; li < S.nlev; ++li) {
+    const LevelLaunch& lp = S.lp[li];
+    const PairLevel pl = S.pls[(size_t)li * a.npairs + pair];
     LevelGeom geo;
     geo.w = lp.w; geo.h = lp.h; geo.n = lp.n; geo.pitch = lp.pitch; geo.nbands = lp.nbands; geo.nstrips = lp.nstrips;
-    geo.strip0 = min(rank * a.strips_per_cta[li], lp.nstrips);
-    geo.strip1 = min(geo.strip0 + a.strips_per_cta[li], lp.nstrips);
+    geo.strip0 = min(rank * S.strips_per_cta[li], lp.nstrips);
+    geo.strip1 = min(geo.strip0 + S.strips_per_cta[li], lp.nstrips);
     const int row0 = min(geo.strip0 * kTileH, lp.h), row1 = min(geo.strip1 * kTileH, lp.h);
     if (!a.skip_begin) {   // DenseTracker::match, start of a level: the last CTA to arrive initialises the pair's level state
-      if (squad_arrive(sq, episode, a.g, lt.s_flag)) {
+      if (squad_arrive(sq, episode, S.g, lt.s_flag)) {
         if (threadIdx.x == 0) {
           level_begin(st, pl, a.T_init, pair, lp);
           squad_release(sq, episode);
@@ -509,10 +540,10 @@ k_level_persistent(PersistentArgs a) {
         if (lane == 0) store_seg_export(mine, cta_exports + (size_t)rank * kSegExportFloats);
       }
       DVO_TOCK(0);
-      if (squad_arrive(sq, episode, a.g, lt.s_flag)) {
+      if (squad_arrive(sq, episode, S.g, lt.s_flag)) {
         DVO_TOCK(2);
         if (warp == 0) {
-          pair_mid_warp(st, pair, cta_exports, cta_base, a.g, nullptr, lp, a.ilog, a.max_log, lt.comb);
+          pair_mid_warp(st, pair, cta_exports, cta_base, S.g, nullptr, lp, a.ilog, a.max_log, lt.comb);
           if (lane == 0) squad_release(sq, episode);
         }
         __syncthreads();
@@ -561,9 +592,9 @@ k_level_persistent(PersistentArgs a) {
         partial[(size_t)rank * kNormalValues + threadIdx.x] = s;
       }
       DVO_TOCK(1);
-      if (squad_arrive(sq, episode, a.g, lt.s_flag)) {
+      if (squad_arrive(sq, episode, S.g, lt.s_flag)) {
         DVO_TOCK(3);
-        pair_end_cta(st, pl, pair, partial, a.g, nullptr, lp, a.ilog, a.max_log, lt.end, [&] { squad_release(sq, episode); }, a.dbg2 ? a.dbg2 + 64 : nullptr);
+        pair_end_cta(st, pl, pair, partial, S.g, nullptr, lp, a.ilog, a.max_log, lt.end, [&] { squad_release(sq, episode); }, S.dbg2 ? S.dbg2 + 64 : nullptr);
         __syncthreads();
         DVO_TOCK(5);
       } else {
@@ -576,20 +607,26 @@ k_level_persistent(PersistentArgs a) {
     }
     if (*reinterpret_cast<volatile int*>(a.error_flag)) break;
     }   // levels
+    if (fused && si == 0 && threadIdx.x == 0) {   // this pair's coarse levels are done: hand it to the fine squads (g == 1 here)
+      __threadfence();
+      const int slot = atomicAdd(a.ready_tail, 1);
+      asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(a.ready + slot), "r"(pair + 1) : "memory");
+    }
   }
   if (timing) {
     t_acc[7] = global_ns() - t_start;
-    for (int i = 0; i < 8; ++i) atomicAdd(a.dbg + i, t_acc[i]);
+    for (int i = 0; i < 8; ++i) atomicAdd(S.dbg + i, t_acc[i]);
   }
 #ifdef DVO_PIPE_TIMING
   if (tm.on) {   // cycles: consumer warp 0 {stage A, wait full A, stage B, wait full B}, producer {descriptor, wait empty}
-    if (warp == 0) { atomicAdd(a.dbg + 8, tm.rounds_a); atomicAdd(a.dbg + 9, tm.wait_full_a); atomicAdd(a.dbg + 10, tm.rounds_b); atomicAdd(a.dbg + 11, tm.wait_full_b); }
-    else { atomicAdd(a.dbg + 12, tm.produce); atomicAdd(a.dbg + 13, tm.wait_empty); atomicAdd(a.dbg + 14, tm.rounds_a); atomicAdd(a.dbg + 15, tm.rounds_b); }
-    if (warp == 0) { atomicAdd(a.dbg2 + 3, tm.rounds); atomicAdd(a.dbg2 + 4, tm.slow_rounds); }
-    else { atomicAdd(a.dbg2 + 0, tm.tiles); atomicAdd(a.dbg2 + 1, tm.tiles_inexact); atomicAdd(a.dbg2 + 2, tm.tiles_skipped); }
+    if (warp == 0) { atomicAdd(S.dbg + 8, tm.rounds_a); atomicAdd(S.dbg + 9, tm.wait_full_a); atomicAdd(S.dbg + 10, tm.rounds_b); atomicAdd(S.dbg + 11, tm.wait_full_b); }
+    else { atomicAdd(S.dbg + 12, tm.produce); atomicAdd(S.dbg + 13, tm.wait_empty); atomicAdd(S.dbg + 14, tm.rounds_a); atomicAdd(S.dbg + 15, tm.rounds_b); }
+    if (warp == 0) { atomicAdd(S.dbg2 + 3, tm.rounds); atomicAdd(S.dbg2 + 4, tm.slow_rounds); }
+    else { atomicAdd(S.dbg2 + 0, tm.tiles); atomicAdd(S.dbg2 + 1, tm.tiles_inexact); atomicAdd(S.dbg2 + 2, tm.tiles_skipped); }
   }
-  if (timing) { atomicMax(a.dbg2 + 5, t_acc[7]); atomicMin(a.dbg2 + 6, t_acc[7]); }
+  if (timing) { atomicMax(S.dbg2 + 5, t_acc[7]); atomicMin(S.dbg2 + 6, t_acc[7]); }
 #endif
+  }   // segments
 #undef DVO_TICK
 #undef DVO_TOCK
 }
@@ -835,38 +872,77 @@ LevelLaunch make_level_launch(const LevelInfo& L, const dvo_b200_config* cfg, in
   return lp;
 }
 
-void add_need(ScratchNeed& need, int hmax, const GroupPlan& pl) {
-  need.row_export_floats = std::max(need.row_export_floats, (size_t)pl.nsquads * hmax * kSegExportFloats);
-  need.row_base_ints = std::max(need.row_base_ints, (size_t)pl.nsquads * hmax);
-  need.cta_export_floats = std::max(need.cta_export_floats, (size_t)pl.nsquads * pl.g * kSegExportFloats);
-  need.cta_base_ints = std::max(need.cta_base_ints, (size_t)pl.nsquads * pl.g);
-  need.partial_floats = std::max(need.partial_floats, (size_t)pl.nsquads * pl.g * kNormalValues);
-  need.squads = std::max(need.squads, (size_t)pl.nsquads + 1);
+// scratch of one launch = the sum over its segments (they are live at the same time); the workspace keeps the maximum
+ScratchNeed segment_need(int hmax, const GroupPlan& pl) {
+  ScratchNeed s;
+  s.row_export_floats = (size_t)pl.nsquads * hmax * kSegExportFloats;
+  s.row_base_ints = (size_t)pl.nsquads * hmax;
+  s.cta_export_floats = (size_t)pl.nsquads * pl.g * kSegExportFloats;
+  s.cta_base_ints = (size_t)pl.nsquads * pl.g;
+  s.partial_floats = (size_t)pl.nsquads * pl.g * kNormalValues;
+  s.squads = (size_t)pl.nsquads;
+  return s;
+}
+void add_launch_need(ScratchNeed& need, int nseg, const int* hmax, const GroupPlan* plans, int npairs) {
+  ScratchNeed sum;
+  for (int s = 0; s < nseg; ++s) {
+    const ScratchNeed q = segment_need(hmax[s], plans[s]);
+    sum.row_export_floats += q.row_export_floats; sum.row_base_ints += q.row_base_ints; sum.cta_export_floats += q.cta_export_floats;
+    sum.cta_base_ints += q.cta_base_ints; sum.partial_floats += q.partial_floats; sum.squads += q.squads;
+  }
+  sum.squads += 1 + ((size_t)npairs * sizeof(int) + sizeof(SquadState) - 1) / sizeof(SquadState);   // counters + ready ring
+  need.row_export_floats = std::max(need.row_export_floats, sum.row_export_floats);
+  need.row_base_ints = std::max(need.row_base_ints, sum.row_base_ints);
+  need.cta_export_floats = std::max(need.cta_export_floats, sum.cta_export_floats);
+  need.cta_base_ints = std::max(need.cta_base_ints, sum.cta_base_ints);
+  need.partial_floats = std::max(need.partial_floats, sum.partial_floats);
+  need.squads = std::max(need.squads, sum.squads);
 }
 
-// enqueue the persistent kernel of one group of levels (squad states zeroed first); `tail` receives {queue head, error flag}
-int launch_group(dvo_b200_ctx* ctx, const LevelLaunch* lps, const GroupPlan& plan, const PairLevel* d_pls, const double* d_Tinit,
-                 int npairs, int max_log, float* dump, int skip_begin, int group_index, int** tail_out) {
+// Enqueue one persistent launch of nseg (1 or 2) segments; squad states, queues, the ready ring and the error flag are
+// zeroed first.  lps / d_pls: per segment.  `flag_out` receives the device address of the launch's error flag.
+int launch_segments(dvo_b200_ctx* ctx, int nseg, const LevelLaunch (*lps)[kMaxLevels], const GroupPlan* plans, const int* hmax,
+                    const PairLevel* const* d_pls, const double* d_Tinit, int npairs, int max_log, float* dump, int skip_begin,
+                    int group_index, int** flag_out) {
   Workspace& ws = ctx->ws;
   cudaStream_t st = ctx->stream;
-  // squad states, queue head and error flag (last SquadState slot) start at zero
-  DVO_CUDA(ctx, cudaMemsetAsync(ws.d_squads, 0, sizeof(SquadState) * (plan.nsquads + 1), st));
+  size_t nsq = 0;
+  for (int s = 0; s < nseg; ++s) nsq += plans[s].nsquads;
+  const size_t ring_states = ((size_t)npairs * sizeof(int) + sizeof(SquadState) - 1) / sizeof(SquadState);
+  DVO_CUDA(ctx, cudaMemsetAsync(ws.d_squads, 0, sizeof(SquadState) * (nsq + 1 + ring_states), st));
   PersistentArgs pa;
-  pa.states = ws.d_state; pa.pls = d_pls;
-  pa.row_exports = ws.d_row_exports; pa.row_base = ws.d_row_base; pa.cta_exports = ws.d_cta_exports; pa.cta_base = ws.d_cta_base;
-  pa.partial = ws.d_normal_partial;
-  pa.squads = reinterpret_cast<SquadState*>(ws.d_squads);
-  int* tail = reinterpret_cast<int*>(pa.squads + plan.nsquads);
-  pa.next_pair = tail; pa.error_flag = tail + 1;
+  pa.states = ws.d_state;
+  SquadState* squads = reinterpret_cast<SquadState*>(ws.d_squads);
+  int* counters = reinterpret_cast<int*>(squads + nsq);      // {queue 0, queue 1, ready tail, error flag}
+  pa.ready = reinterpret_cast<int*>(squads + nsq + 1);
+  pa.ready_tail = counters + 2; pa.error_flag = counters + 3;
   pa.ilog = ws.d_iter_log; pa.max_log = max_log;
-  pa.T_init = d_Tinit; pa.nlev = plan.nlev; pa.skip_begin = skip_begin;
+  pa.T_init = d_Tinit; pa.skip_begin = skip_begin;
   pa.dump = dump;
-  pa.dbg = ctx->d_dbg ? ctx->d_dbg + 16 * std::min(group_index, 7) : nullptr;
-  pa.dbg2 = ctx->d_dbg ? ctx->d_dbg + 128 + 8 * std::min(group_index, 7) : nullptr;
-  pa.npairs = npairs; pa.g = plan.g; pa.nsquads = plan.nsquads;
-  for (int k = 0; k < kMaxLevels; ++k) {
-    pa.strips_per_cta[k] = k < plan.nlev ? plan.strips_per_cta[k] : 0;
-    if (k < plan.nlev) pa.lp[k] = lps[k];
+  pa.npairs = npairs; pa.nseg = nseg;
+  ScratchNeed off;
+  size_t sq_off = 0;
+  for (int s = 0; s < nseg; ++s) {
+    Segment& S = pa.seg[s];
+    const GroupPlan& plan = plans[s];
+    S.pls = d_pls[s];
+    S.row_exports = ws.d_row_exports + off.row_export_floats; S.row_base = ws.d_row_base + off.row_base_ints;
+    S.cta_exports = ws.d_cta_exports + off.cta_export_floats; S.cta_base = ws.d_cta_base + off.cta_base_ints;
+    S.partial = ws.d_normal_partial + off.partial_floats;
+    S.squads = squads + sq_off;
+    S.queue = counters + s;
+    const int slot = std::min(group_index + s, 7);
+    S.dbg = ctx->d_dbg ? ctx->d_dbg + 16 * slot : nullptr;
+    S.dbg2 = ctx->d_dbg ? ctx->d_dbg + 128 + 8 * slot : nullptr;
+    S.nlev = plan.nlev; S.g = plan.g; S.nsquads = plan.nsquads;
+    for (int k = 0; k < kMaxLevels; ++k) {
+      S.strips_per_cta[k] = k < plan.nlev ? plan.strips_per_cta[k] : 0;
+      if (k < plan.nlev) S.lp[k] = lps[s][k];
+    }
+    const ScratchNeed q = segment_need(hmax[s], plan);
+    off.row_export_floats += q.row_export_floats; off.row_base_ints += q.row_base_ints; off.cta_export_floats += q.cta_export_floats;
+    off.cta_base_ints += q.cta_base_ints; off.partial_floats += q.partial_floats;
+    sq_off += plan.nsquads;
   }
   {
     ProfScope prof(ctx, 0);
@@ -876,7 +952,7 @@ int launch_group(dvo_b200_ctx* ctx, const LevelLaunch* lps, const GroupPlan& pla
                                               dim3(kCtaThreads), args, kLevelSmemBytes, st));
     ctx->launches++;
   }
-  *tail_out = tail;
+  *flag_out = pa.error_flag;
   return 0;
 }
 
@@ -896,12 +972,18 @@ int tracker_match_batch(dvo_b200_ctx* ctx, const dvo_b200_config* cfg, int n, dv
   const int grid = ctx->num_sms * ctx->ctas_per_sm;
   GroupPlan groups[kMaxLevels];
   const int ngroups = plan_groups(refs[0], first, last, grid, n, groups);
-  ScratchNeed need;
+  int hmaxs[kMaxLevels];
   for (int gi = 0; gi < ngroups; ++gi) {
-    int hmax = 0;
-    for (int k = 0; k < groups[gi].nlev; ++k) hmax = std::max(hmax, refs[0]->L[first - (groups[gi].first_li + k)].h);
-    add_need(need, hmax, groups[gi]);
+    hmaxs[gi] = 0;
+    for (int k = 0; k < groups[gi].nlev; ++k) hmaxs[gi] = std::max(hmaxs[gi], refs[0]->L[first - (groups[gi].first_li + k)].h);
   }
+  // A coarse group (one CTA per pair) followed by a fine group runs as ONE launch of two segments: no grid-wide barrier and
+  // no launch boundary between them, so the CTAs that run out of coarse pairs start on fine pairs while the long coarse
+  // pairs are still iterating.
+  const bool fuse = ngroups == 2 && groups[0].g == 1 && !getenv("DVO_B200_NO_FUSE");
+  ScratchNeed need;
+  if (fuse) add_launch_need(need, 2, hmaxs, groups, n);
+  else for (int gi = 0; gi < ngroups; ++gi) add_launch_need(need, 1, hmaxs + gi, groups + gi, n);
   rc = ensure_workspace(ctx, n * nlev, need, max_log);     // d_pair_level holds the descriptors of every level
   if (rc) return rc;
 
@@ -935,18 +1017,23 @@ int tracker_match_batch(dvo_b200_ctx* ctx, const dvo_b200_config* cfg, int n, dv
 
   for (int i = 0; i < 8; ++i) ws.h_active[i] = 0;
   if (max_log > 0) DVO_CUDA(ctx, cudaMemsetAsync(ws.d_iter_log, 0, sizeof(dvo_b200_iteration_stats) * (size_t)n * max_log, st));
+  LevelLaunch lps[kMaxLevels][kMaxLevels];
+  const PairLevel* d_pls[kMaxLevels];
   for (int gi = 0; gi < ngroups; ++gi) {
     const GroupPlan& G = groups[gi];
-    LevelLaunch lps[kMaxLevels];
     for (int k = 0; k < G.nlev; ++k) {
       const int li = G.first_li + k, level = first - li;
-      lps[k] = make_level_launch(refs[0]->L[level], cfg, li, level);
+      lps[gi][k] = make_level_launch(refs[0]->L[level], cfg, li, level);
     }
-    int* tail = nullptr;
-    if ((rc = launch_group(ctx, lps, G, ws.d_pair_level + (size_t)G.first_li * n, have_init ? ws.d_tinit : nullptr, n, max_log, nullptr,
-                           0, gi, &tail)))
+    d_pls[gi] = ws.d_pair_level + (size_t)G.first_li * n;
+  }
+  const int nlaunch = fuse ? 1 : ngroups;
+  for (int gi = 0; gi < nlaunch; ++gi) {
+    int* flag = nullptr;
+    if ((rc = launch_segments(ctx, fuse ? 2 : 1, lps + gi, groups + gi, hmaxs + gi, d_pls + gi, have_init ? ws.d_tinit : nullptr, n, max_log,
+                              nullptr, 0, gi, &flag)))
       return rc;
-    DVO_CUDA(ctx, cudaMemcpyAsync(&ws.h_active[level_flag_slot(gi)], tail + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+    DVO_CUDA(ctx, cudaMemcpyAsync(&ws.h_active[level_flag_slot(gi)], flag, sizeof(int), cudaMemcpyDeviceToHost, st));
   }
   // results
   dvo_b200_result* d_res = (dvo_b200_result*)d_results_user;
@@ -961,7 +1048,7 @@ int tracker_match_batch(dvo_b200_ctx* ctx, const dvo_b200_config* cfg, int n, dv
     ctx->launches++;
   }
   DVO_CUDA(ctx, cudaGetLastError());
-  ctx->pending_level_flags = ngroups;   // checked at the next synchronisation point (device-results variant)
+  ctx->pending_level_flags = nlaunch;   // checked at the next synchronisation point (device-results variant)
   if (h_results) {
     size_t bytes = sizeof(dvo_b200_result) * n;
     if (bytes > ctx->h_results_bytes) {
@@ -1023,7 +1110,8 @@ int tracker_linearize(dvo_b200_ctx* ctx, const dvo_b200_config* cfg, dvo_b200_py
     plan_groups(ref, level, level, ctx->num_sms * ctx->ctas_per_sm, 1, tmp);
     plan = tmp[0];
     ScratchNeed need;
-    add_need(need, L.h, plan);
+    const int hm = L.h;
+    add_launch_need(need, 1, &hm, &plan, 1);
     if (planes7) need.dump_floats = 7 * (size_t)L.n;
     if ((rc = ensure_workspace(ctx, 1, need, 0))) return rc;
   }
@@ -1045,10 +1133,14 @@ int tracker_linearize(dvo_b200_ctx* ctx, const dvo_b200_config* cfg, dvo_b200_py
   k_set_state<<<1, 1, 0, st>>>(ws.d_state, ws.d_pair_level, (const double*)ctx->d_stage,
                                (const float*)((char*)ctx->d_stage + 128), use_weights, lp);
   ctx->launches += 1;
-  int* tail = nullptr;
+  int* flag = nullptr;
   ws.h_active[0] = 0;
-  if ((rc = launch_group(ctx, &lp, plan, ws.d_pair_level, nullptr, 1, 0, planes7 ? ws.d_dump : nullptr, 1, 0, &tail))) return rc;
-  DVO_CUDA(ctx, cudaMemcpyAsync(&ws.h_active[0], tail + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+  LevelLaunch lps[1][kMaxLevels];
+  lps[0][0] = lp;
+  const int hm = L.h;
+  const PairLevel* d_pls[1] = {ws.d_pair_level};
+  if ((rc = launch_segments(ctx, 1, lps, &plan, &hm, d_pls, nullptr, 1, 0, planes7 ? ws.d_dump : nullptr, 1, 0, &flag))) return rc;
+  DVO_CUDA(ctx, cudaMemcpyAsync(&ws.h_active[0], flag, sizeof(int), cudaMemcpyDeviceToHost, st));
   DVO_CUDA(ctx, cudaGetLastError());
   PairState* hs = nullptr;
   if ((rc = ensure_stage(ctx, 0, sizeof(PairState) + 64))) return rc;
