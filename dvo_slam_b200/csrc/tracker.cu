@@ -792,7 +792,7 @@ int plan_groups(const dvo_b200_pyramid* ref, int first, int last, int grid, int 
   }
   int ngroups = 0;
   const bool walk = npairs >= grid / 4 && !getenv("DVO_B200_NO_WALK");
-  const int coarse_tiles = getenv("DVO_B200_COARSE_TILES") ? atoi(getenv("DVO_B200_COARSE_TILES")) : 40;   // developer override
+  const int coarse_tiles = getenv("DVO_B200_COARSE_TILES") ? atoi(getenv("DVO_B200_COARSE_TILES")) : 110;   // levels up to 320x240 (105 tiles): one CTA per pair; env = developer override
   for (int li = 0; li < nlev;) {
     GroupPlan& G = out[ngroups++];
     G.first_li = li; G.nlev = 1; G.g = g_level[li];
