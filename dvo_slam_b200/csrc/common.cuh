@@ -48,7 +48,10 @@ struct LevelInfo {
 
 // tile geometry of the level kernel (tracker.cu) and of the per-tile depth ranges (pyramid.cu)
 constexpr int kTileW = 128;    // reference pixels per tile row: 4 warp rounds
-constexpr int kTileH = 7;      // tile rows = consumer warps of a CTA (warp q walks row q of every tile of a strip); 7 consumers +
+#ifndef DVO_TILE_H
+#define DVO_TILE_H 7
+#endif
+constexpr int kTileH = DVO_TILE_H;      // tile rows = consumer warps of a CTA (warp q walks row q of every tile of a strip); 7 consumers +
                                // 1 producer warp = 256 threads, two CTAs per SM at 128 registers per thread
 
 struct Slab;
