@@ -13,3 +13,7 @@ if [ "$2" = "c5" ]; then
   timeout 600 python bench.py --config 5 --steps 3 --no-cpu-baseline > gpurun_out/bench_c5.json 2> gpurun_out/bench_c5.err
   echo "bench c5 exit $?"; cat gpurun_out/bench_c5.json; tail -5 gpurun_out/bench_c5.err
 fi
+if [ "$3" = "ref" ]; then
+  timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err
+  echo "bench ref exit $?"; cat gpurun_out/bench_ref.json | cut -c1-600; tail -3 gpurun_out/bench_ref.err
+fi
