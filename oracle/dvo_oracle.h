@@ -11,12 +11,15 @@
  * Eigen/OpenCV/Sophus code that cannot be compiled in this image (those libraries are
  * absent), so the arithmetic is restated with plain arrays.
  *
- * PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures for this
- * path and cannot be built here, so this oracle is not pinned
- * against reference outputs.  It is pinned only against (a) analytic ground truth of the
- * synthetic scene, (b) closed-form identities (SE(3) exp/log round trips, LDLT residuals),
- * (c) its own FAITHFUL<->EXACT spread, and (d) the committed fixtures under tests/golden/
- * which were generated by this oracle (regression pins, not reference pins).
+ * PARITY PINNED against the reference's own object code (tests/test_reference_pin.py): the reference ships no tests,
+ * golden vectors or fixtures for this path and its build system cannot run here, but its
+ * hot-path translation units dvo_core/src/{dense_tracking_impl,core/math_sse,core/intrinsic_matrix}.cpp compile unmodified
+ * against header-only container stand-ins (oracle/ref_shim/, recipe: oracle/Makefile target `ref`, output oracle/_ref/).
+ * FAITHFUL mode equals that object code (-O2: arithmetic in program order) BIT FOR BIT on every golden case: counts,
+ * validity, every residual-record value, P, log-likelihood, A, b; whole alignments driven through the reference's
+ * functions have identical control flow.  What remains restated without a reference-side pin: the control flow of
+ * dense_tracking.cpp (needs Sophus), the pyramid of rgbd_image.cpp (needs OpenCV proper), Sophus SE3 exp/log and Eigen's
+ * LDLT -- pinned against analytic ground truth and closed-form identities (tests/test_oracle.py).
  *
  * Modes (orc_mode flags) -- each flag reproduces one numerical quirk of the reference:
  *   rcp_approx        _mm_rcp_ps in projection and weights   (dense_tracking_impl.cpp:192,700)

@@ -2,7 +2,9 @@
 
 The reference ships no golden vectors and cannot be built here, so these fixtures are
 produced by the oracle (oracle/liboracle.so) on seeded synthetic inputs: they pin the oracle against
-regressions and give the GPU tests fixed inputs; they are NOT reference outputs ("parity unpinned").
+regressions and give the GPU tests fixed inputs; they are NOT reference outputs.  The FAITHFUL-mode numbers in
+them are, however, what the reference's own object code produces on the same inputs, bit for bit
+(tests/test_reference_pin.py runs both on these fixtures).
 Inputs are stored as uint8 intensity + uint16 raw depth (TUM style, 1/5000 m), i.e. exactly what
 benchmark_slam.cpp:46-93 would load from disk.
 """

@@ -1,6 +1,7 @@
 """CPU tests of the oracle (test infrastructure) against its committed fixtures, closed-form
-identities and analytic ground truth.  The reference has no tests or goldens:
-"parity unpinned" -- these pin the oracle itself."""
+identities and analytic ground truth.  The reference has no tests or goldens; the pin against the
+reference's own object code is tests/test_reference_pin.py -- these pin the parts that file cannot reach (pyramid, SE(3),
+LDL^T, control flow) and the fixtures."""
 import numpy as np
 import pytest
 
