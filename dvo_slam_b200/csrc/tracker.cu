@@ -712,7 +712,7 @@ int ensure_workspace(dvo_b200_ctx* ctx, int npairs, const ScratchNeed& need, int
   if ((size_t)npairs > ws.cap_pairs) {
     if (ws.d_pair_level) { cudaStreamSynchronize(ctx->stream); cudaFree(ws.d_pair_level); cudaFree(ws.d_state); }
     ws.d_pair_level = nullptr; ws.d_state = nullptr; ws.cap_pairs = 0;
-    DVO_CUDA(ctx, cudaMalloc((void**)&ws.d_pair_level, sizeof(PairLevel) * npairs));
+    DVO_CUDA(ctx, cudaMalloc((void**)&ws.d_pair_level, sizeof(PairLevel) * npairs + 16));   // k_stage_words copies whole 16-byte words
     DVO_CUDA(ctx, cudaMalloc((void**)&ws.d_state, sizeof(PairState) * npairs));
     ws.cap_pairs = npairs;
   }
