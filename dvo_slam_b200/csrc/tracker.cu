@@ -374,6 +374,7 @@ struct PersistentArgs {
   PairState* states;
   int* ready;             // fused launch: ring of (pair + 1) whose first segment is done, 0 = not yet written
   int* ready_tail;
+  int* arrivals;          // CTAs that have entered the second segment
   int* error_flag;
   dvo_b200_iteration_stats* ilog;
   int max_log;
@@ -449,7 +450,17 @@ k_level_persistent(const __grid_constant__ PersistentArgs a) {
 #pragma unroll 1
   for (int si = 0; si < a.nseg; ++si) {
   const Segment& S = a.seg[si];
-  const int squad = blockIdx.x / S.g, rank = blockIdx.x - squad * S.g;
+  // Squads of the second segment of a fused launch form in ORDER OF ARRIVAL: the CTAs leave the first segment at very
+  // different times (1 or 2 coarse pairs each, 3..40 iterations per level), and a squad made of neighbouring block indices
+  // would wait for its slowest member (measured: 24 % of the fine segment's CTA time).
+  int cta_index = blockIdx.x;
+  if (fused && si == 1) {
+    if (threadIdx.x == 0) lt.s_flag[1] = atomicAdd(a.arrivals, 1);
+    __syncthreads();
+    cta_index = lt.s_flag[1];
+    __syncthreads();
+  }
+  const int squad = cta_index / S.g, rank = cta_index - squad * S.g;
   if (squad >= S.nsquads) continue;   // leftover CTAs of this segment
   SquadState* sq = S.squads + squad;
   int hmax = 0;
@@ -915,7 +926,7 @@ int launch_segments(dvo_b200_ctx* ctx, int nseg, const LevelLaunch (*lps)[kMaxLe
   SquadState* squads = reinterpret_cast<SquadState*>(ws.d_squads);
   int* counters = reinterpret_cast<int*>(squads + nsq);      // {queue 0, queue 1, ready tail, error flag}
   pa.ready = reinterpret_cast<int*>(squads + nsq + 1);
-  pa.ready_tail = counters + 2; pa.error_flag = counters + 3;
+  pa.ready_tail = counters + 2; pa.error_flag = counters + 3; pa.arrivals = counters + 4;
   pa.ilog = ws.d_iter_log; pa.max_log = max_log;
   pa.T_init = d_Tinit; pa.skip_begin = skip_begin;
   pa.dump = dump;
