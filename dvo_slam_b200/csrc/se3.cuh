@@ -202,7 +202,8 @@ DVO_HD void ldlt_solve6(const double Ain[36], const double bin[6], double x[6]) 
     for (int i = k + 1; i < n; ++i) if (piv == i) idx[i] = ik;
     idx[k] = ip;
   }
-  double A[6][6], y[6];
+  double A[6][6], y[6], rd[6];     // rd: reciprocal pivots (one division per pivot; Eigen divides element by element,
+                                   // which differs in the last bit of a double -- far below every tolerance of this path)
 #pragma unroll
   for (int i = 0; i < n; ++i) {
     y[i] = bin[idx[i]];
@@ -214,12 +215,13 @@ DVO_HD void ldlt_solve6(const double Ain[36], const double bin[6], double x[6]) 
 #pragma unroll
     for (int j = 0; j < k; ++j) A[k][k] -= A[k][j] * A[k][j] * A[j][j];
     const double d = A[k][k];
+    rd[k] = (d != 0.0) ? 1.0 / d : 0.0;
 #pragma unroll
     for (int i = k + 1; i < n; ++i) {
       double s = A[i][k];
 #pragma unroll
       for (int j = 0; j < k; ++j) s -= A[i][j] * A[k][j] * A[j][j];
-      A[i][k] = (d != 0.0) ? s / d : 0.0;
+      A[i][k] = s * rd[k];
     }
   }
 #pragma unroll
@@ -231,7 +233,7 @@ DVO_HD void ldlt_solve6(const double Ain[36], const double bin[6], double x[6]) 
   for (int i = 0; i < n; ++i) dmax = fmax(dmax, fabs(A[i][i]));
   const double tol = fmax(dmax * DBL_EPSILON, 1.0 / DBL_MAX);
 #pragma unroll
-  for (int i = 0; i < n; ++i) y[i] = fabs(A[i][i]) > tol ? y[i] / A[i][i] : 0.0;
+  for (int i = 0; i < n; ++i) y[i] = fabs(A[i][i]) > tol ? y[i] * rd[i] : 0.0;
 #pragma unroll
   for (int i = n - 1; i >= 0; --i)
 #pragma unroll

@@ -197,97 +197,128 @@ __device__ __forceinline__ void load_stage_consts(const PairState& st, const Pai
   c.first_iteration = __ldcg(&st.iteration) == 0;
 }
 
-// ---- producer duty: one warp stages one tile ---------------------------------------------------------------
+// ---- producer duty: one warp stages the tiles of a stage ------------------------------------------------------
 // Tiles are numbered per CTA since the kernel started (`t`): buffer = t % kStages, mbarrier phase parity =
 // (t / kStages) & 1.  The warp waits until all consumers have released the buffer's previous tile.
+//
+// The window of a tile follows from eight projections (four corner rays x {zmin, zmax}): eight lanes.  The warp
+// therefore prepares FOUR tiles at a time (lane >> 3 selects the tile), which also overlaps the global-memory
+// latency of their depth ranges and template entries, and then issues the copies tile by tile; the two words
+// that describe a window travel from the tile's lane group to the whole warp by shuffle.  (One tile per trip made
+// the producer the slowest warp of the CTA in stage A: ~600 instructions and two dependent global loads per tile
+// against ~500 instructions per consumer warp.)
 template <bool kStageB>
-__device__ __noinline__ void produce_tile(TilePipe& tp, const PairLevel& pl, const LevelGeom& g, const StageConsts& c, int s, int b,
-                                          unsigned t, int* error_flag, PipeTiming& tm) {
-  const int lane = threadIdx.x & 31;
+__device__ __noinline__ void produce_tiles(TilePipe& tp, const PairLevel& pl, const LevelGeom& g, const StageConsts& c, unsigned tbase,
+                                           int ntiles, int* error_flag, PipeTiming& tm) {
+  const int lane = threadIdx.x & 31, sub = lane >> 3;
   const float2* cur = kStageB ? pl.c3 : pl.c0;
-  const int bufi = t % kStages;
-  const long long tp0 = DVO_CLOCK(tm);
-  StageBuf& sb = tp.buf[bufi];
-  const int y0 = s * kTileH, rows = min(kTileH, g.h - y0);
-  const int x0 = b * kTileW, bw = min(kTileW, g.w - x0);
-  const unsigned ref_row_bytes = (unsigned)((bw + 1) & ~1) * 8u;
-  // ---- window of the current image: corner rays x {zmin, zmax} (lane & 7 selects the corner) ----
-  const float2 zr = __ldg(pl.rrange + (size_t)s * g.nbands + b);
-  TileDesc d;
-  d.skip = 0; d.origin = 0; d.ulo = 0; d.ucount = 0; d.vlo = 0; d.vcount = 0; d.exact = 0; d.pad_ = 0;
-  int ncols = 0, nrows = 0, win_bx0 = 0, win_row_lo = 0;
-  if (!(zr.x <= zr.y)) {
-    d.skip = 1;                       // no non-NaN reference depth: nothing is selected in this tile
-  } else {
-    const float z = (lane & 4) ? zr.y : zr.x;
-    const float tx = __ldg(pl.rtmpl + ((lane & 1) ? x0 + bw - 1 : x0));
-    const float ty = __ldg(pl.rtmpl + g.w + ((lane & 2) ? y0 + rows - 1 : y0));
-    const float px = tx * z, py = ty * z;
-    const f2 XY = fma2(c.k0, bc(px), fma2(c.k1, bc(py), fma2(c.k2, bc(z), c.k3)));
-    const float Zt = fmaf(c.k8, px, fmaf(c.k9, py, fmaf(c.k10, z, c.k11)));
-    const float iz = 1.0f / Zt;
-    float umin = lo(XY) * iz, vmin = hi(XY) * iz, umax = umin, vmax = vmin;
-    bool front = Zt > 1e-6f && umin == umin && vmin == vmin;
+  int s_issue = g.strip0, b_issue = 0;       // tile i0 + k in issue order
+  for (int i0 = 0; i0 < ntiles; i0 += 4) {
+    const long long tp0 = DVO_CLOCK(tm);
+    // ---- windows of tiles i0 .. i0+3: corner rays x {zmin, zmax} (lane & 7 selects the corner, lane >> 3 the tile) ----
+    unsigned wordA, wordD;   // skip | exact << 1 | ncols << 2 | nrows << 10;  bx0 | (row_lo + 1) << 16
+    {
+      const int ii = min(i0 + sub, ntiles - 1);
+      const int sd = ii / g.nbands;
+      const int s = g.strip0 + sd, b = ii - sd * g.nbands;
+      const int y0 = s * kTileH, rows = min(kTileH, g.h - y0);
+      const int x0 = b * kTileW, bw = min(kTileW, g.w - x0);
+      const float2 zr = __ldg(pl.rrange + (size_t)s * g.nbands + b);
+      const float txc = __ldg(pl.rtmpl + ((lane & 1) ? x0 + bw - 1 : x0));
+      const float tyc = __ldg(pl.rtmpl + g.w + ((lane & 2) ? y0 + rows - 1 : y0));
+      const bool has_depth = zr.x <= zr.y;          // false: no non-NaN reference depth, nothing is selected in this tile
+      const float z = (lane & 4) ? zr.y : zr.x;
+      const float px = txc * z, py = tyc * z;
+      const f2 XY = fma2(c.k0, bc(px), fma2(c.k1, bc(py), fma2(c.k2, bc(z), c.k3)));
+      const float Zt = fmaf(c.k8, px, fmaf(c.k9, py, fmaf(c.k10, z, c.k11)));
+      const float iz = 1.0f / Zt;
+      float umin = lo(XY) * iz, vmin = hi(XY) * iz, umax = umin, vmax = vmin;
+      const bool front_lane = Zt > 1e-6f && umin == umin && vmin == vmin;
 #pragma unroll
-    for (int off = 1; off < 8; off <<= 1) {
-      umin = fminf(umin, __shfl_xor_sync(kFullMask, umin, off)); umax = fmaxf(umax, __shfl_xor_sync(kFullMask, umax, off));
-      vmin = fminf(vmin, __shfl_xor_sync(kFullMask, vmin, off)); vmax = fmaxf(vmax, __shfl_xor_sync(kFullMask, vmax, off));
+      for (int off = 1; off < 8; off <<= 1) {       // stays inside the aligned group of eight lanes
+        umin = fminf(umin, __shfl_xor_sync(kFullMask, umin, off)); umax = fmaxf(umax, __shfl_xor_sync(kFullMask, umax, off));
+        vmin = fminf(vmin, __shfl_xor_sync(kFullMask, vmin, off)); vmax = fmaxf(vmax, __shfl_xor_sync(kFullMask, vmax, off));
+      }
+      const bool front = ((__ballot_sync(kFullMask, front_lane) >> (sub * 8)) & 0xffu) == 0xffu;
+      // clamp before the float -> int conversions; the slack below covers the rounding of the per-pixel projection
+      umin = fmaxf(umin, -8.f); vmin = fmaxf(vmin, -8.f); umax = fminf(umax, (float)g.w + 8.f); vmax = fminf(vmax, (float)g.h + 8.f);
+      int skip = 0, exact = 0, ncols = 0, nrows = 0, bx0 = 0, row_lo = 0;
+      if (!has_depth) {
+        skip = 1;
+      } else if (!front) {
+        // a corner behind the camera: the hull argument does not hold; stage no window, every tap is gathered
+      } else if (umax < -1.f || vmax < -1.f || umin > (float)g.w || vmin > (float)g.h) {
+        skip = 1;                       // the whole tile projects outside the current image
+      } else {
+        const int col_lo = max((int)floorf(umin) - 2, 0), col_hi = min((int)floorf(umax) + 3, g.w - 1);
+        row_lo = max((int)floorf(vmin) - 2, -1);
+        const int row_hi = min((int)floorf(vmax) + 3, g.h);
+        bx0 = col_lo & ~1;
+        ncols = (col_hi + 2 - bx0) & ~1;              // even count covering [bx0, col_hi]
+        bool whole = true;
+        if (ncols > kWinCols) { bx0 += ((ncols - kWinCols) / 2) & ~1; ncols = kWinCols; whole = false; }
+        nrows = row_hi - row_lo + 1;
+        if (nrows > kWinRows) { row_lo += (nrows - kWinRows) / 2; nrows = kWinRows; whole = false; }
+        if (ncols < 4 || nrows < 4) { ncols = 0; nrows = 0; bx0 = 0; row_lo = 0; }
+        else exact = whole ? 1 : 0;
+      }
+      wordA = (unsigned)skip | ((unsigned)exact << 1) | ((unsigned)ncols << 2) | ((unsigned)nrows << 10);
+      wordD = (unsigned)bx0 | ((unsigned)(row_lo + 1) << 16);
     }
-    front = __all_sync(kFullMask, front);
-    // clamp before the float -> int conversions; the slack below covers the rounding of the per-pixel projection
-    umin = fmaxf(umin, -8.f); vmin = fmaxf(vmin, -8.f); umax = fminf(umax, (float)g.w + 8.f); vmax = fminf(vmax, (float)g.h + 8.f);
-    if (!front) {
-      // a corner behind the camera: the hull argument does not hold; stage no window, every tap is gathered
-    } else if (umax < -1.f || vmax < -1.f || umin > (float)g.w || vmin > (float)g.h) {
-      d.skip = 1;                     // the whole tile projects outside the current image
-    } else {
-      const int col_lo = max((int)floorf(umin) - 2, 0), col_hi = min((int)floorf(umax) + 3, g.w - 1);
-      int row_lo = max((int)floorf(vmin) - 2, -1), row_hi = min((int)floorf(vmax) + 3, g.h);
-      int bx0 = col_lo & ~1;
-      ncols = (col_hi + 2 - bx0) & ~1;              // even count covering [bx0, col_hi]
-      bool whole = true;
-      if (ncols > kWinCols) { bx0 += ((ncols - kWinCols) / 2) & ~1; ncols = kWinCols; whole = false; }
-      nrows = row_hi - row_lo + 1;
-      if (nrows > kWinRows) { row_lo += (nrows - kWinRows) / 2; nrows = kWinRows; whole = false; }
-      if (ncols < 4 || nrows < 4) { ncols = 0; nrows = 0; }
-      else {
-        d.exact = whole ? 1 : 0;
-        win_bx0 = bx0; win_row_lo = row_lo;
-        d.origin = (row_lo * kWinCols + bx0) * 8;
+    DVO_ADD(tm, produce, DVO_CLOCK(tm) - tp0);
+    // ---- issue: tile by tile, in order ----
+    const int kmax = min(4, ntiles - i0);
+    for (int k = 0; k < kmax; ++k) {
+      const unsigned t = tbase + (unsigned)(i0 + k);
+      const int bufi = t % kStages;
+      StageBuf& sb = tp.buf[bufi];
+      const unsigned wa = __shfl_sync(kFullMask, wordA, k * 8), wd = __shfl_sync(kFullMask, wordD, k * 8);
+      const int s = s_issue, b = b_issue;
+      if (++b_issue == g.nbands) { b_issue = 0; ++s_issue; }
+      const int y0 = s * kTileH, rows = min(kTileH, g.h - y0);
+      const int x0 = b * kTileW, bw = min(kTileW, g.w - x0);
+      const unsigned ref_row_bytes = (unsigned)((bw + 1) & ~1) * 8u;
+      const int skip = (int)(wa & 1u), ncols = (int)((wa >> 2) & 0xffu), nrows = (int)(wa >> 10);
+      const int win_bx0 = (int)(wd & 0xffffu), win_row_lo = (int)(wd >> 16) - 1;
+      TileDesc d;
+      d.skip = skip; d.exact = (int)((wa >> 1) & 1u); d.pad_ = 0;
+      d.origin = 0; d.ulo = 0; d.ucount = 0; d.vlo = 0; d.vcount = 0;
+      if (ncols) {
+        d.origin = (win_row_lo * kWinCols + win_bx0) * 8;
         // columns are clamped per tap (max(u0-1, 0), min(u0+2, w-1)); rows -1 and h are staged as replicas
-        d.ulo = bx0 == 0 ? 0 : bx0 + 1;
-        const int uhi = (bx0 + ncols - 1 >= g.w - 1) ? g.w - 2 : bx0 + ncols - 3;
+        d.ulo = win_bx0 == 0 ? 0 : win_bx0 + 1;
+        const int uhi = (win_bx0 + ncols - 1 >= g.w - 1) ? g.w - 2 : win_bx0 + ncols - 3;
         d.ucount = max(uhi - d.ulo + 1, 0);
-        d.vlo = row_lo + 1;
+        d.vlo = win_row_lo + 1;
         d.vcount = max(nrows - 3, 0);
       }
+      const unsigned win_row_bytes = (unsigned)ncols * 8u;
+      const unsigned tx_bytes = (unsigned)((bw + 3) & ~3) * 4u;
+      const unsigned total = skip ? 0u : (unsigned)rows * ref_row_bytes * (kStageB ? 2u : 1u) + (unsigned)nrows * win_row_bytes + tx_bytes;
+      // the descriptor is ready: now wait until the consumers have released the buffer's previous tile
+      const long long tp1 = DVO_CLOCK(tm);
+      mbar_wait(&tp.empty[bufi], ((t / kStages) & 1u) ^ 1u, error_flag);
+      DVO_ADD(tm, wait_empty, DVO_CLOCK(tm) - tp1);
+      DVO_ADD(tm, tiles, 1); DVO_ADD(tm, tiles_inexact, (!d.skip && !d.exact) ? 1 : 0); DVO_ADD(tm, tiles_skipped, d.skip ? 1 : 0);
+      if (lane == 0) {
+        tp.desc[bufi] = d;
+        if (total) mbar_arrive_expect_tx(&tp.full[bufi], total);
+        else mbar_arrive(&tp.full[bufi]);
+      }
+      __syncwarp();
+      if (!skip) {
+        if (lane < rows) {
+          const size_t off = (size_t)(y0 + lane) * g.pitch + x0;
+          bulk_g2s(&sb.ref0[lane][0], pl.r0 + off, ref_row_bytes, &tp.full[bufi]);
+          if (kStageB) bulk_g2s(&sb.ref1[lane][0], pl.r1 + off, ref_row_bytes, &tp.full[bufi]);
+        }
+        if (lane < nrows) {
+          const int yy = min(max(win_row_lo + lane, 0), g.h - 1);
+          bulk_g2s(&sb.win[lane][0], cur + (size_t)yy * g.pitch + win_bx0, win_row_bytes, &tp.full[bufi]);
+        }
+        if (lane == 31) bulk_g2s(&sb.tx[0], pl.rtmpl + x0, tx_bytes, &tp.full[bufi]);
+      }
     }
-  }
-  const unsigned win_row_bytes = (unsigned)ncols * 8u;
-  const unsigned tx_bytes = (unsigned)((bw + 3) & ~3) * 4u;
-  const unsigned total = d.skip ? 0u : (unsigned)rows * ref_row_bytes * (kStageB ? 2u : 1u) + (unsigned)nrows * win_row_bytes + tx_bytes;
-  // the descriptor is ready: now wait until the consumers have released the buffer's previous tile
-  const long long tp1 = DVO_CLOCK(tm);
-  mbar_wait(&tp.empty[bufi], ((t / kStages) & 1u) ^ 1u, error_flag);
-  DVO_ADD(tm, produce, tp1 - tp0); DVO_ADD(tm, wait_empty, DVO_CLOCK(tm) - tp1);
-  DVO_ADD(tm, tiles, 1); DVO_ADD(tm, tiles_inexact, (!d.skip && !d.exact) ? 1 : 0); DVO_ADD(tm, tiles_skipped, d.skip ? 1 : 0);
-  if (lane == 0) {
-    tp.desc[bufi] = d;
-    if (total) mbar_arrive_expect_tx(&tp.full[bufi], total);
-    else mbar_arrive(&tp.full[bufi]);
-  }
-  __syncwarp();
-  if (!d.skip) {
-    if (lane < rows) {
-      const size_t off = (size_t)(y0 + lane) * g.pitch + x0;
-      bulk_g2s(&sb.ref0[lane][0], pl.r0 + off, ref_row_bytes, &tp.full[bufi]);
-      if (kStageB) bulk_g2s(&sb.ref1[lane][0], pl.r1 + off, ref_row_bytes, &tp.full[bufi]);
-    }
-    if (lane < nrows) {
-      const int yy = min(max(win_row_lo + lane, 0), g.h - 1);
-      bulk_g2s(&sb.win[lane][0], cur + (size_t)yy * g.pitch + win_bx0, win_row_bytes, &tp.full[bufi]);
-    }
-    if (lane == 31) bulk_g2s(&sb.tx[0], pl.rtmpl + x0, tx_bytes, &tp.full[bufi]);
   }
 }
 
@@ -641,9 +672,7 @@ __device__ __forceinline__ void stage_a_run(TilePipe& tp, const PairLevel& pl, c
   const unsigned tbase = tile_count;
   tile_count += ntiles;
   if (q == kConsumerWarps) {   // the producer warp
-    int i = 0;
-    for (int s = g.strip0; s < g.strip1; ++s)
-      for (int b = 0; b < g.nbands; ++b, ++i) produce_tile<false>(tp, pl, g, c, s, b, tbase + i, error_flag, tm);
+    produce_tiles<false>(tp, pl, g, c, tbase, ntiles, error_flag, tm);
     return;
   }
   int i = 0;
@@ -656,6 +685,7 @@ __device__ __forceinline__ void stage_a_run(TilePipe& tp, const PairLevel& pl, c
     for (int b = 0; b < g.nbands; ++b, ++i) {
       const unsigned t = tbase + i;
       const int bufi = t % kStages;
+      const int x0 = b * kTileW, bw = min(kTileW, g.w - x0);
       const long long tw0 = DVO_CLOCK(tm);
       mbar_wait(&tp.full[bufi], (t / kStages) & 1u, error_flag);
       DVO_ADD(tm, wait_full_a, DVO_CLOCK(tm) - tw0);
@@ -663,7 +693,6 @@ __device__ __forceinline__ void stage_a_run(TilePipe& tp, const PairLevel& pl, c
       const TileDesc d = tp.desc[bufi];
       if (row_ok && !d.skip) {
         const WinView wv = make_view(sb, d, pl.c0, g);
-        const int x0 = b * kTileW, bw = min(kTileW, g.w - x0);
         const int nr = (bw + 31) >> 5;
         unsigned refa = pin(smem_u32(&sb.ref0[q][0]) + lane * 8);
         unsigned txa = pin(smem_u32(&sb.tx[0]) + lane * 4);
@@ -676,7 +705,7 @@ __device__ __forceinline__ void stage_a_run(TilePipe& tp, const PairLevel& pl, c
           const f2 rz1 = second ? lds_f2_at(refa + 256) : pk(0.f, __int_as_float(0x7fc00000));
           const float tx0 = lds_f32(txa), tx1 = second ? lds_f32(txa + 128) : 0.f;
           float z0 = hi(rz0), z1 = hi(rz1);
-          if (bw < kTileW) {   // past a partial band: stale shared memory
+          if (bw < kTileW) {   // past a partial band: not this band's pixels
             z0 = (r * 32 < xlim) ? z0 : __int_as_float(0x7fc00000);
             z1 = (r * 32 + 32 < xlim) ? z1 : __int_as_float(0x7fc00000);
           }
@@ -798,9 +827,7 @@ __device__ __forceinline__ void stage_b_run(TilePipe& tp, const PairLevel& pl, c
   const int keep_rank = (int)max(min(n_keep - cta_base, (long long)0x7fffffff), (long long)-1);   // first dropped rank, CTA-relative
   tile_count += ntiles;
   if (q == kConsumerWarps) {   // the producer warp
-    int i = 0;
-    for (int s = g.strip0; s < g.strip1; ++s)
-      for (int b = 0; b < g.nbands; ++b, ++i) produce_tile<true>(tp, pl, g, c, s, b, tbase + i, error_flag, tm);
+    produce_tiles<true>(tp, pl, g, c, tbase, ntiles, error_flag, tm);
     return;
   }
   int i = 0;
@@ -813,12 +840,12 @@ __device__ __forceinline__ void stage_b_run(TilePipe& tp, const PairLevel& pl, c
     for (int b = 0; b < g.nbands; ++b, ++i) {
       const unsigned t = tbase + i;
       const int bufi = t % kStages;
+      const int x0 = b * kTileW, bw = min(kTileW, g.w - x0);
       const long long tw0 = DVO_CLOCK(tm);
       mbar_wait(&tp.full[bufi], (t / kStages) & 1u, error_flag);
       DVO_ADD(tm, wait_full_b, DVO_CLOCK(tm) - tw0);
       const StageBuf& sb = tp.buf[bufi];
       const TileDesc d = tp.desc[bufi];
-      const int x0 = b * kTileW, bw = min(kTileW, g.w - x0);
       if (row_ok && !d.skip) {
         const WinView wv = make_view(sb, d, pl.c3, g);
         const int nr = (bw + 31) >> 5;

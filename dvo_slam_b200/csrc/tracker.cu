@@ -353,6 +353,7 @@ constexpr size_t kLevelSmemBytes = sizeof(TilePipe) + sizeof(LevelTail);
 // has one segment, or two (the coarse levels with one CTA per pair, then the fine levels with squads of g CTAs) that the
 // grid runs back to back WITHOUT a grid-wide barrier: a CTA that finds the coarse queue empty moves on to the fine
 // segment, and fine squads take their pairs from a ring of pairs whose coarse levels are done (`ready`).
+constexpr int kMaxSeg = 4;   // segments of one launch: the coarse levels, then up to three slices of the fine levels
 struct Segment {
   const PairLevel* pls;   // descriptors of this segment's levels: [level][pair]
   float* row_exports;     // per squad: h segment summaries (one per image row)
@@ -361,7 +362,12 @@ struct Segment {
   int* cta_base;          // per squad: g exclusive prefixes
   float* partial;         // per squad: g x kNormalValues
   SquadState* squads;
-  int* queue;             // next pair (first segment) / next ring slot (second segment of a fused launch)
+  int* queue;             // next pair (first segment) / next slot of this segment's ready ring (later segments of a fused launch)
+  int* ready;             // fused launch, segments >= 1: ring of (pair + 1) whose coarse levels are done, 0 = not yet written
+  int* ready_tail;
+  int* arrivals;          // CTAs that have entered this segment (squads of segments >= 1 form in order of arrival)
+  int pair_begin;         // segments >= 1 of a fused launch own the pairs [pair_begin, pair_begin + npairs_seg)
+  int npairs_seg;         // pairs handed out by this segment's queue
   unsigned long long* dbg2;  // optional (timing build): {tiles, inexact tiles, skipped tiles, rounds, rounds of inexact tiles, max / min CTA lifetime}
   unsigned long long* dbg;   // optional: ns spent per CTA in {stage A, stage B, wait A, wait B, mid, end, queue, total}
   int nlev;               // pyramid levels of the segment (coarse to fine)
@@ -372,9 +378,6 @@ struct Segment {
 
 struct PersistentArgs {
   PairState* states;
-  int* ready;             // fused launch: ring of (pair + 1) whose first segment is done, 0 = not yet written
-  int* ready_tail;
-  int* arrivals;          // CTAs that have entered the second segment
   int* error_flag;
   dvo_b200_iteration_stats* ilog;
   int max_log;
@@ -382,8 +385,8 @@ struct PersistentArgs {
   int skip_begin;         // test hook: the pair state was placed by k_set_state
   float* dump;            // test hook: seven record planes of the (single) pair, or nullptr
   int npairs;
-  int nseg;               // 1, or 2 = fused coarse + fine segments
-  Segment seg[2];
+  int nseg;               // 1, or >= 2 = fused launch: coarse segment + slices of the fine levels
+  Segment seg[kMaxSeg];
 };
 
 __device__ __forceinline__ unsigned long long global_ns() {
@@ -443,7 +446,7 @@ k_level_persistent(const __grid_constant__ PersistentArgs a) {
   }
   __syncthreads();
   unsigned tile_count = 0;      // tiles staged / consumed by this CTA since the kernel started
-  const bool fused = a.nseg == 2;
+  const bool fused = a.nseg >= 2;
 #define DVO_TICK() do { if (timing) t0 = global_ns(); } while (0)
 #define DVO_TOCK(slot) do { if (timing) { t1 = global_ns(); t_acc[slot] += t1 - t0; t0 = t1; } } while (0)
 
@@ -454,8 +457,8 @@ k_level_persistent(const __grid_constant__ PersistentArgs a) {
   // different times (1 or 2 coarse pairs each, 3..40 iterations per level), and a squad made of neighbouring block indices
   // would wait for its slowest member (measured: 24 % of the fine segment's CTA time).
   int cta_index = blockIdx.x;
-  if (fused && si == 1) {
-    if (threadIdx.x == 0) lt.s_flag[1] = atomicAdd(a.arrivals, 1);
+  if (fused && si >= 1) {
+    if (threadIdx.x == 0) lt.s_flag[1] = atomicAdd(S.arrivals, 1);
     __syncthreads();
     cta_index = lt.s_flag[1];
     __syncthreads();
@@ -485,13 +488,13 @@ k_level_persistent(const __grid_constant__ PersistentArgs a) {
     if (squad_arrive(sq, episode, S.g, lt.s_flag)) {
       if (threadIdx.x == 0) {
         int p = atomicAdd(S.queue, 1);
-        if (p >= a.npairs) p = -1;
-        else if (fused && si == 1) {
-          // slot p of the ready ring: filled by the CTA that finishes the coarse levels of some pair (every pair is
-          // pushed exactly once, so every slot < npairs is eventually written)
+        if (p >= S.npairs_seg) p = -1;
+        else if (fused && si >= 1) {
+          // slot p of this segment's ready ring: filled by the CTA that finishes the coarse levels of one of the
+          // segment's pairs (every pair is pushed exactly once, so every slot < npairs_seg is eventually written)
           unsigned spins = 0;
           int v;
-          while ((v = (int)ld_acquire_u32(reinterpret_cast<const unsigned*>(a.ready + p))) == 0) {
+          while ((v = (int)ld_acquire_u32(reinterpret_cast<const unsigned*>(S.ready + p))) == 0) {
             __nanosleep(200);
             if (((++spins) & 4095u) == 0u) {
               if (*reinterpret_cast<volatile int*>(a.error_flag)) break;
@@ -619,9 +622,13 @@ k_level_persistent(const __grid_constant__ PersistentArgs a) {
     if (*reinterpret_cast<volatile int*>(a.error_flag)) break;
     }   // levels
     if (fused && si == 0 && threadIdx.x == 0) {   // this pair's coarse levels are done: hand it to the fine squads (g == 1 here)
+      // The fine segments own fixed ranges of the pair index (not of the order of arrival), so which squad size a pair
+      // gets -- and with it the rounding of its sums -- does not depend on timing.
+      int k = 1;
+      while (k + 1 < a.nseg && pair >= a.seg[k + 1].pair_begin) ++k;
       __threadfence();
-      const int slot = atomicAdd(a.ready_tail, 1);
-      asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(a.ready + slot), "r"(pair + 1) : "memory");
+      const int slot = atomicAdd(a.seg[k].ready_tail, 1);
+      asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(a.seg[k].ready + slot), "r"(pair + 1) : "memory");
     }
   }
   if (timing) {
@@ -763,6 +770,7 @@ struct GroupPlan {
   int g;                // CTAs per squad
   int nsquads;          // squads in the grid
   int strips_per_cta[kMaxLevels];
+  int pair_begin, npairs;   // the pairs this segment's queue hands out (a slice of the batch for the fine segments of a fused launch)
 };
 
 // Squad size for one level on its own.  A squad of g CTAs gives each CTA spc = ceil(nstrips / g) strips.  Small squads keep
@@ -829,6 +837,7 @@ int plan_groups(const dvo_b200_pyramid* ref, int first, int last, int grid, int 
       G.strips_per_cta[k] = (L.nstrips + g_eff - 1) / g_eff;
     }
     G.nsquads = std::min(grid / G.g, std::max(npairs, 1));
+    G.pair_begin = 0; G.npairs = npairs;
     li += G.nlev;
   }
   return ngroups;
@@ -924,9 +933,9 @@ int launch_segments(dvo_b200_ctx* ctx, int nseg, const LevelLaunch (*lps)[kMaxLe
   PersistentArgs pa;
   pa.states = ws.d_state;
   SquadState* squads = reinterpret_cast<SquadState*>(ws.d_squads);
-  int* counters = reinterpret_cast<int*>(squads + nsq);      // {queue 0, queue 1, ready tail, error flag}
-  pa.ready = reinterpret_cast<int*>(squads + nsq + 1);
-  pa.ready_tail = counters + 2; pa.error_flag = counters + 3; pa.arrivals = counters + 4;
+  int* counters = reinterpret_cast<int*>(squads + nsq);      // one zeroed 128-byte line: {queue[4], ready tail[4], arrivals[4], error flag}
+  int* ring = reinterpret_cast<int*>(squads + nsq + 1);      // npairs slots: the ready rings of the fine segments, by pair range
+  pa.error_flag = counters + 3 * kMaxSeg;
   pa.ilog = ws.d_iter_log; pa.max_log = max_log;
   pa.T_init = d_Tinit; pa.skip_begin = skip_begin;
   pa.dump = dump;
@@ -941,7 +950,9 @@ int launch_segments(dvo_b200_ctx* ctx, int nseg, const LevelLaunch (*lps)[kMaxLe
     S.cta_exports = ws.d_cta_exports + off.cta_export_floats; S.cta_base = ws.d_cta_base + off.cta_base_ints;
     S.partial = ws.d_normal_partial + off.partial_floats;
     S.squads = squads + sq_off;
-    S.queue = counters + s;
+    S.queue = counters + s; S.ready_tail = counters + kMaxSeg + s; S.arrivals = counters + 2 * kMaxSeg + s;
+    S.pair_begin = plan.pair_begin; S.npairs_seg = plan.npairs;
+    S.ready = ring + plan.pair_begin;
     const int slot = std::min(group_index + s, 7);
     S.dbg = ctx->d_dbg ? ctx->d_dbg + 16 * slot : nullptr;
     S.dbg2 = ctx->d_dbg ? ctx->d_dbg + 128 + 8 * slot : nullptr;
@@ -992,8 +1003,54 @@ int tracker_match_batch(dvo_b200_ctx* ctx, const dvo_b200_config* cfg, int n, dv
   // no launch boundary between them, so the CTAs that run out of coarse pairs start on fine pairs while the long coarse
   // pairs are still iterating.
   const bool fuse = ngroups == 2 && groups[0].g == 1 && !getenv("DVO_B200_NO_FUSE");
+  // Fused launch: the fine group is cut into up to three slices of the pair index with squads of g, 2g and 4g CTAs.  Pairs
+  // come off a queue, so with one squad size the launch ends with most squads idle while a few finish pairs that need two
+  // or three times the mean number of iterations (measured at batch 512: 16 % of the CTA time).  The last pairs of the
+  // batch, which also leave the coarse segment last, therefore go to wider squads that finish a pair in a half / a quarter
+  // of the time; the slice a pair belongs to is fixed by its index, so results do not depend on timing.
+  GroupPlan segs[kMaxSeg];
+  int seg_hmax[kMaxSeg];
+  int nseg = 1;
+  if (fuse) {
+    segs[0] = groups[0]; seg_hmax[0] = hmaxs[0];
+    const GroupPlan& F = groups[1];
+    int min_strips = 1 << 30;
+    for (int k = 0; k < F.nlev; ++k) min_strips = std::min(min_strips, refs[0]->L[first - (F.first_li + k)].nstrips);
+    int counts[3] = {n, 0, 0};
+    {
+      int c2 = 0, c3 = 0;
+      const int g2 = 2 * F.g, g3 = 4 * F.g;
+      if (g2 <= min_strips && g2 <= grid) c2 = (int)(1.8 * (grid / g2) + 0.5);
+      if (c2 && g3 <= min_strips && g3 <= grid) c3 = (int)(1.8 * (grid / g3) + 0.5);
+      if (const char* e = getenv("DVO_B200_TAIL")) {       // developer override: "c2,c3" pairs for the 2g and 4g slices
+        int a2 = 0, a3 = 0;
+        if (sscanf(e, "%d,%d", &a2, &a3) >= 1) { c2 = (g2 <= min_strips && g2 <= grid) ? a2 : 0; c3 = (c2 && g3 <= min_strips && g3 <= grid) ? a3 : 0; }
+      }
+      const int keep = 2 * (grid / F.g);                     // the first slice keeps at least two pairs per squad
+      if (n - c2 - c3 < keep) c3 = 0;
+      if (n - c2 < keep) c2 = 0;
+      counts[0] = n - c2 - c3; counts[1] = c2; counts[2] = c3;
+    }
+    int begin = 0;
+    for (int k = 0; k < 3; ++k) {
+      if (counts[k] <= 0) continue;
+      GroupPlan& G = segs[nseg];
+      G = F;
+      G.g = F.g << k;
+      for (int j = 0; j < G.nlev; ++j) {
+        const LevelInfo& L = refs[0]->L[first - (G.first_li + j)];
+        const int g_eff = std::min(G.g, L.nstrips);
+        G.strips_per_cta[j] = (L.nstrips + g_eff - 1) / g_eff;
+      }
+      G.pair_begin = begin; G.npairs = counts[k];
+      G.nsquads = std::min(grid / G.g, std::max(counts[k], 1));
+      seg_hmax[nseg] = hmaxs[1];
+      begin += counts[k];
+      ++nseg;
+    }
+  }
   ScratchNeed need;
-  if (fuse) add_launch_need(need, 2, hmaxs, groups, n);
+  if (fuse) add_launch_need(need, nseg, seg_hmax, segs, n);
   else for (int gi = 0; gi < ngroups; ++gi) add_launch_need(need, 1, hmaxs + gi, groups + gi, n);
   rc = ensure_workspace(ctx, n * nlev, need, max_log);     // d_pair_level holds the descriptors of every level
   if (rc) return rc;
@@ -1039,12 +1096,26 @@ int tracker_match_batch(dvo_b200_ctx* ctx, const dvo_b200_config* cfg, int n, dv
     d_pls[gi] = ws.d_pair_level + (size_t)G.first_li * n;
   }
   const int nlaunch = fuse ? 1 : ngroups;
-  for (int gi = 0; gi < nlaunch; ++gi) {
+  if (fuse) {
+    LevelLaunch seg_lps[kMaxSeg][kMaxLevels];
+    const PairLevel* seg_pls[kMaxSeg];
+    for (int sgi = 0; sgi < nseg; ++sgi) {
+      const int gi = sgi == 0 ? 0 : 1;
+      for (int k = 0; k < groups[gi].nlev; ++k) seg_lps[sgi][k] = lps[gi][k];
+      seg_pls[sgi] = d_pls[gi];
+    }
     int* flag = nullptr;
-    if ((rc = launch_segments(ctx, fuse ? 2 : 1, lps + gi, groups + gi, hmaxs + gi, d_pls + gi, have_init ? ws.d_tinit : nullptr, n, max_log,
-                              nullptr, 0, gi, &flag)))
+    if ((rc = launch_segments(ctx, nseg, seg_lps, segs, seg_hmax, seg_pls, have_init ? ws.d_tinit : nullptr, n, max_log, nullptr, 0, 0, &flag)))
       return rc;
-    DVO_CUDA(ctx, cudaMemcpyAsync(&ws.h_active[level_flag_slot(gi)], flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    DVO_CUDA(ctx, cudaMemcpyAsync(&ws.h_active[level_flag_slot(0)], flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+  } else {
+    for (int gi = 0; gi < nlaunch; ++gi) {
+      int* flag = nullptr;
+      if ((rc = launch_segments(ctx, 1, lps + gi, groups + gi, hmaxs + gi, d_pls + gi, have_init ? ws.d_tinit : nullptr, n, max_log,
+                                nullptr, 0, gi, &flag)))
+        return rc;
+      DVO_CUDA(ctx, cudaMemcpyAsync(&ws.h_active[level_flag_slot(gi)], flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    }
   }
   // results
   dvo_b200_result* d_res = (dvo_b200_result*)d_results_user;

@@ -27,9 +27,16 @@ for spc in spcs:
     eng.profile_read(reset=True)
     eng.profile_enable(True)
     t0 = time.perf_counter()
-    for _ in range(steps): res = eng.match_batch(refs, curs, cfg, raw=True)
+    hashes = []
+    for _ in range(steps):
+        res = eng.match_batch(refs, curs, cfg, raw=True)
     eng.synchronize()
     ms = (time.perf_counter() - t0) * 1e3 / steps
+    import hashlib
+    for _ in range(2):     # run-to-run determinism of the batch (outside the timed region)
+        rr = eng.match_batch(refs, curs, cfg)
+        hashes.append(hashlib.md5(b"".join(np.asarray(r.transformation).tobytes() + np.asarray(r.information).tobytes() for r in rr)).hexdigest()[:12])
+    print("result hashes of two more runs:", hashes, "deterministic" if len(set(hashes)) == 1 else "NOT DETERMINISTIC")
     pix = sum((W >> res[i].levels[l].id) * (H >> res[i].levels[l].id) * res[i].levels[l].num_iterations for i in range(B) for l in range(res[i].num_levels))
     its = np.array([[res[i].levels[l].num_iterations for l in range(res[i].num_levels)] for i in range(B)])
     print("iterations per level (coarse->fine): mean", np.round(its.mean(0), 2), "max", its.max(0), "p99", np.percentile(its, 99, axis=0))
