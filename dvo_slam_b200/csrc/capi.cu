@@ -247,19 +247,23 @@ int dvo_b200_pyramid_download(dvo_b200_ctx* ctx, const dvo_b200_pyramid* p, int3
   const LevelInfo& L = p->L[level];
   size_t N = L.n;
   const size_t plane = (size_t)L.pitch * L.h;      // float2 elements per plane, rows padded to the pitch
-  std::vector<float> tmp(6 * plane);
+  const size_t nrec = (size_t)L.nbands * L.nstrips * dvo_b200::kRecF2;
+  std::vector<float> tmp(4 * plane), rec(2 * nrec);
   if (ctx) DVO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   if (p->slab && p->slab->ready) DVO_CUDA(ctx, cudaEventSynchronize(p->slab->ready));   // the pyramid's own build has finished
-  DVO_CUDA(ctx, cudaMemcpy(tmp.data(), p->planes + L.plane_off, sizeof(float) * 6 * plane, cudaMemcpyDeviceToHost));
-  if (ctx) ctx->d2h_bytes += sizeof(float) * 6 * plane;
-  // device planes: P0 = (I, Z'), P1 = (Ix, Iy), P2 = (I, Z).  The depth gradients are not stored (the tracker forms
-  // them from P2 on the fly): restate calculateDerivativeX/Y<float> on the true depth (rgbd_image.cpp:419-472).
-  auto Zt = [&](int y, int x) { return tmp[4 * plane + 2 * ((size_t)y * L.pitch + x) + 1]; };
+  DVO_CUDA(ctx, cudaMemcpy(tmp.data(), p->planes + L.plane_off, sizeof(float) * 4 * plane, cudaMemcpyDeviceToHost));
+  DVO_CUDA(ctx, cudaMemcpy(rec.data(), p->planes + L.rec_off, sizeof(float) * 2 * nrec, cudaMemcpyDeviceToHost));
+  if (ctx) ctx->d2h_bytes += sizeof(float) * (4 * plane + 2 * nrec);
+  // device layout: P0 = (I, Z'), P2 = (I, Z) row-major; (Ix, Iy) in the reference tile records.  The depth gradients are not
+  // stored (the tracker forms them from P2 on the fly): restate calculateDerivativeX/Y<float> on the true depth
+  // (rgbd_image.cpp:419-472).
+  auto Zt = [&](int y, int x) { return tmp[2 * plane + 2 * ((size_t)y * L.pitch + x) + 1]; };
   for (int y = 0; y < L.h; ++y)
     for (int x = 0; x < L.w; ++x) {
       const size_t o = 2 * ((size_t)y * L.pitch + x), i = (size_t)y * L.w + x;
+      const size_t g = 2 * (dvo_b200::rec_cell(x, y, L.nbands) + dvo_b200::kRecP1);
       planes6[0 * N + i] = tmp[o]; planes6[1 * N + i] = tmp[o + 1];
-      planes6[2 * N + i] = tmp[2 * plane + o]; planes6[3 * N + i] = tmp[2 * plane + o + 1];
+      planes6[2 * N + i] = rec[g]; planes6[3 * N + i] = rec[g + 1];
       const int xp = x > 0 ? x - 1 : 0, xn = x < L.w - 1 ? x + 1 : L.w - 1, yp = y > 0 ? y - 1 : 0, yn = y < L.h - 1 ? y + 1 : L.h - 1;
       const float dzx = Zt(y, xn) - Zt(y, xp), dzy = Zt(yn, x) - Zt(yp, x);
       planes6[4 * N + i] = dzx * 0.5f; planes6[5 * N + i] = dzy * 0.5f;

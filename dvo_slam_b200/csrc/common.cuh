@@ -40,7 +40,8 @@ struct LevelInfo {
   int pitch;                   // row pitch of the planes in float2 elements (w rounded up to even)
   int nbands, nstrips;         // tiles of kTileW x kTileH reference pixels: nbands x nstrips
   float fx, fy, ox, oy;        // IntrinsicMatrix of this level (intrinsic_matrix.cpp:90-93: whole K * 0.5)
-  size_t plane_off;            // float2 offset of P0 inside dvo_b200_pyramid::planes (P_k = + k*pitch*h)
+  size_t plane_off;            // float2 offset of P0 = (I, Z') inside dvo_b200_pyramid::planes; P2 = (I, Z) follows at + pitch*h
+  size_t rec_off;              // float2 offset of the reference tile records (kRecF2 each, tile = strip * nbands + band)
   size_t mask_off;             // uint32 offset inside sel_mask
   size_t tmpl_off;             // float offset of tx[w] then ty[h] inside tmpl
   size_t range_off;            // float2 offset of the per-tile depth range {zmin, zmax} inside tile_range
@@ -53,6 +54,19 @@ constexpr int kTileW = 128;    // reference pixels per tile row: 4 warp rounds
 #endif
 constexpr int kTileH = DVO_TILE_H;      // tile rows = consumer warps of a CTA (warp q walks row q of every tile of a strip); 7 consumers +
                                // 1 producer warp = 256 threads, two CTAs per SM at 128 registers per thread
+
+// Reference tile record: everything the level kernel reads of the REFERENCE image for one tile, contiguous in HBM so that
+// one bulk copy stages it (row-major planes cost one copy per tile row and plane: 14 of the ~29 copies of a stage-B tile):
+//   kTileH rows x kTileW of (I, Zsel)   Zsel = depth where the pixel is a selected reference point, NaN elsewhere
+//   kTileW floats tx                     point-cloud template of the tile's columns
+//   kTileH rows x kTileW of (Ix, Iy)     only stage B copies this part
+// Cells outside the image hold (0, NaN) / 0 / (0, 0).
+constexpr int kRecTx = kTileH * kTileW;              // float2 offset of tx[]
+constexpr int kRecP1 = kRecTx + kTileW / 2;          // float2 offset of the gradient rows
+constexpr int kRecF2 = kRecP1 + kTileH * kTileW;     // float2 elements per record (14 848 bytes)
+__host__ __device__ __forceinline__ size_t rec_cell(int x, int y, int nbands) {   // (I, Zsel) of pixel (x, y) relative to the level's records
+  return (size_t)((y / kTileH) * nbands + x / kTileW) * kRecF2 + (size_t)(y % kTileH) * kTileW + (x % kTileW);
+}
 
 struct Slab;
 // Pool of released slabs of one context, keyed by size (release -> reuse instead of cudaFree).  Pyramids are
@@ -98,7 +112,7 @@ namespace dvo_b200 {
 
 // ---- per-pair device state ---------------------------------------------------------------------
 struct PairLevel {              // what one alignment reads at the current level (uploaded per level)
-  const float2* r0; const float2* r1;  // reference P3 (I, Zsel), P1 (Ix, Iy)
+  const float2* r0; const float2* r1;  // reference tile records of the level (r1: unused, kept for layout)
   const uint32_t* rmask;               // reference selection mask
   const int* rsel;                     // {S, last selected pixel}
   const float* rtmpl;                  // tx[w], ty[h]

@@ -86,7 +86,7 @@ __global__ void k_pyr_intensity_down(const void* __restrict__ I0, size_t in_stri
 template <bool kLevel0, bool kRaw>
 __global__ void __launch_bounds__(256)
 k_pyr_finish(const void* __restrict__ I0, const void* __restrict__ Z0, float zscale, int w0, int n0, float2* __restrict__ planes,
-             size_t planes_per_image, size_t plane_off, int w, int h, int pitch, int level,
+             size_t planes_per_image, size_t plane_off, size_t rec_off, int nbands, int w, int h, int pitch, int level,
              uint32_t* __restrict__ masks, size_t mask_words_per_image, size_t mask_off, float ti, float td) {
   const int img = blockIdx.y;
   const int n = w * h;
@@ -97,9 +97,8 @@ k_pyr_finish(const void* __restrict__ I0, const void* __restrict__ Z0, float zsc
     const int y = idx / w, x = idx - y * w;
     const size_t plane = (size_t)pitch * h;
     float2* P0 = planes + img * planes_per_image + plane_off;
-    float2* P1 = P0 + plane;
-    float2* P2 = P1 + plane;
-    float2* P3 = P2 + plane;   // P2 = (I, Z), P3 = (I, Zsel); the depth gradients are not stored
+    float2* P2 = P0 + plane;   // P2 = (I, Z); the depth gradients are not stored
+    float2* rec = planes + img * planes_per_image + rec_off;   // reference tile records: (I, Zsel) and (Ix, Iy)
     const size_t zb = (size_t)img * n0;
     const int xp = max(x - 1, 0), xn = min(x + 1, w - 1), yp = max(y - 1, 0), yn = min(y + 1, h - 1);
     float I, ixp, ixn, iyp, iyn;
@@ -124,17 +123,37 @@ k_pyr_finish(const void* __restrict__ I0, const void* __restrict__ Z0, float zsc
     // ValidPointAndGradientThresholdPredicate::isPointOk (point_selection.h:63-66)
     sel = !bad && (fabsf(ix) > ti || fabsf(iy) > ti || fabsf(zx) > td || fabsf(zy) > td);
     const float nanv = __int_as_float(0x7fc00000);
+    const size_t rc = rec_cell(x, y, nbands);
     P0[o] = make_float2(I, zm);
-    P1[o] = make_float2(ix, iy);
     P2[o] = make_float2(I, z);
-    P3[o] = make_float2(I, sel ? z : nanv);
-    if (x == w - 1 && pitch > w) {   // the pad column of an odd width: never selected, never a valid tap
-      P0[o + 1] = make_float2(0.f, nanv); P1[o + 1] = make_float2(0.f, 0.f);
-      P2[o + 1] = make_float2(0.f, nanv); P3[o + 1] = make_float2(0.f, nanv);
+    rec[rc] = make_float2(I, sel ? z : nanv);
+    rec[rc + kRecP1] = make_float2(ix, iy);
+    if (x == w - 1 && pitch > w) {   // the pad column of an odd width: never a valid tap
+      P0[o + 1] = make_float2(0.f, nanv);
+      P2[o + 1] = make_float2(0.f, nanv);
     }
   }
   const unsigned m = __ballot_sync(0xffffffffu, sel);
   if ((threadIdx.x & 31) == 0 && idx < ((n + 31) / 32) * 32) masks[img * mask_words_per_image + mask_off + (idx >> 5)] = m;
+}
+
+// The parts of the reference tile records that no pixel owns: cells of border tiles outside the image (never selected)
+// and the tx[] slice of every tile.  One thread per record cell; runs after k_template.
+__global__ void k_rec_fill(float2* __restrict__ planes, size_t planes_per_image, size_t rec_off, int nbands, int ntiles, int w, int h,
+                           const float* __restrict__ tmpl, size_t tmpl_per_image, size_t tmpl_off) {
+  const int img = blockIdx.y;
+  const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cell >= ntiles * kTileH * kTileW) return;
+  const int tile = cell / (kTileH * kTileW), rcell = cell - tile * (kTileH * kTileW);
+  const int r = rcell / kTileW, cx = rcell - r * kTileW;
+  const int s = tile / nbands, b = tile - s * nbands;
+  const int x = b * kTileW + cx, y = s * kTileH + r;
+  float2* rec = planes + img * planes_per_image + rec_off + (size_t)tile * kRecF2;
+  if (x >= w || y >= h) {
+    rec[rcell] = make_float2(0.f, __int_as_float(0x7fc00000));
+    rec[kRecP1 + rcell] = make_float2(0.f, 0.f);
+  }
+  if (r == 0) reinterpret_cast<float*>(rec + kRecTx)[cx] = x < w ? tmpl[img * tmpl_per_image + tmpl_off + x] : 0.f;
 }
 
 // {min, max} of the non-NaN Z' of every tile of kTileW x kTileH pixels (one warp per tile).  The level kernel
@@ -187,34 +206,35 @@ __global__ void k_sel_info(const uint32_t* __restrict__ masks, size_t mask_words
 
 // computeResidualsSse walks the point list two at a time and skips the last point of an odd list
 // (dense_tracking_impl.cpp:169): that point is unselected in the reference plane.  Runs after k_sel_info.
-__global__ void k_drop_odd_last(float2* __restrict__ planes, size_t planes_per_image, size_t plane_off, int w, int h, int pitch,
+__global__ void k_drop_odd_last(float2* __restrict__ planes, size_t planes_per_image, size_t rec_off, int nbands, int w,
                                 const int* __restrict__ sel_info, int sel_info_per_image, int level, int nimg) {
   const int img = blockIdx.x * blockDim.x + threadIdx.x;
   if (img >= nimg) return;
   const int S = sel_info[img * sel_info_per_image + 2 * level], last = sel_info[img * sel_info_per_image + 2 * level + 1];
   if ((S & 1) && last >= 0) {
     const int y = last / w, x = last - y * w;
-    float2* P3 = planes + img * planes_per_image + plane_off + 3 * (size_t)pitch * h;
-    P3[(size_t)y * pitch + x].y = __int_as_float(0x7fc00000);
+    float2* rec = planes + img * planes_per_image + rec_off;
+    rec[rec_cell(x, y, nbands)].y = __int_as_float(0x7fc00000);
   }
 }
 
 // recompute the selection mask and the reference plane of one level for non-default thresholds
-__global__ void k_reselect(float2* __restrict__ P0, int w, int h, int pitch, uint32_t* __restrict__ mask, float ti,
-                           float td) {
+__global__ void k_reselect(const float2* __restrict__ P0, float2* __restrict__ rec, int nbands, int w, int h, int pitch,
+                           uint32_t* __restrict__ mask, float ti, float td) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int n = w * h;
   bool sel = false;
   if (idx < n) {
     const int y = idx / w, x = idx - y * w;
     const size_t plane = (size_t)pitch * h, o = (size_t)y * pitch + x;
-    const float2* P2 = P0 + 2 * plane;
+    const float2* P2 = P0 + plane;
+    const size_t rc = rec_cell(x, y, nbands);
     const int xp = max(x - 1, 0), xn = min(x + 1, w - 1), yp = max(y - 1, 0), yn = min(y + 1, h - 1);
-    const float2 a = P0[o], b = P0[plane + o];
+    const float2 a = P0[o], b = rec[rc + kRecP1];
     const float zx = (P2[(size_t)y * pitch + xn].y - P2[(size_t)y * pitch + xp].y) * 0.5f;
     const float zy = (P2[(size_t)yn * pitch + x].y - P2[(size_t)yp * pitch + x].y) * 0.5f;
     sel = !is_nan(a.y) && (fabsf(b.x) > ti || fabsf(b.y) > ti || fabsf(zx) > td || fabsf(zy) > td);
-    P0[3 * plane + o] = make_float2(a.x, sel ? a.y : __int_as_float(0x7fc00000));
+    rec[rc] = make_float2(a.x, sel ? a.y : __int_as_float(0x7fc00000));
   }
   unsigned m = __ballot_sync(0xffffffffu, sel);
   if ((threadIdx.x & 31) == 0 && idx < ((n + 31) / 32) * 32) mask[idx >> 5] = m;
@@ -327,7 +347,8 @@ int pyramid_build_batch_input(dvo_b200_ctx* ctx, int n, const void* d_I, const v
     q.pitch = (q.w + 1) & ~1;
     q.nbands = (q.w + kTileW - 1) / kTileW;
     q.nstrips = (q.h + kTileH - 1) / kTileH;
-    q.plane_off = plane_f2; plane_f2 += 4 * (size_t)q.pitch * q.h;
+    q.plane_off = plane_f2; plane_f2 += 2 * (size_t)q.pitch * q.h;                       // P0, P2 (row-major, even pitch)
+    q.rec_off = plane_f2; plane_f2 += (size_t)q.nbands * q.nstrips * kRecF2;               // reference tile records
     q.mask_off = mask_words; mask_words += q.words;
     q.tmpl_off = tmpl_floats; tmpl_floats += (size_t)((q.w + q.h + 3) & ~3);   // every level's tx[] starts 16-byte aligned (bulk copies)
     q.range_off = range_f2; range_f2 += (size_t)q.nbands * q.nstrips;
@@ -372,13 +393,16 @@ int pyramid_build_batch_input(dvo_b200_ctx* ctx, int n, const void* d_I, const v
     for (int l = 0; l < levels; ++l) {
       const LevelInfo& q = L[l];
       dim3 g((q.words * 32 + T - 1) / T, n);
-      if (l == 0 && raw) k_pyr_finish<true, true><<<g, T, 0, st>>>(d_I, d_Z, zscale, w, w * h, planes, plane_f2, q.plane_off, q.w, q.h, q.pitch, l, masks, mask_words, q.mask_off, ti, td);
-      else if (l == 0) k_pyr_finish<true, false><<<g, T, 0, st>>>(d_I, d_Z, zscale, w, w * h, planes, plane_f2, q.plane_off, q.w, q.h, q.pitch, l, masks, mask_words, q.mask_off, ti, td);
-      else if (raw) k_pyr_finish<false, true><<<g, T, 0, st>>>(d_I, d_Z, zscale, w, w * h, planes, plane_f2, q.plane_off, q.w, q.h, q.pitch, l, masks, mask_words, q.mask_off, ti, td);
-      else k_pyr_finish<false, false><<<g, T, 0, st>>>(d_I, d_Z, zscale, w, w * h, planes, plane_f2, q.plane_off, q.w, q.h, q.pitch, l, masks, mask_words, q.mask_off, ti, td);
+      if (l == 0 && raw) k_pyr_finish<true, true><<<g, T, 0, st>>>(d_I, d_Z, zscale, w, w * h, planes, plane_f2, q.plane_off, q.rec_off, q.nbands, q.w, q.h, q.pitch, l, masks, mask_words, q.mask_off, ti, td);
+      else if (l == 0) k_pyr_finish<true, false><<<g, T, 0, st>>>(d_I, d_Z, zscale, w, w * h, planes, plane_f2, q.plane_off, q.rec_off, q.nbands, q.w, q.h, q.pitch, l, masks, mask_words, q.mask_off, ti, td);
+      else if (raw) k_pyr_finish<false, true><<<g, T, 0, st>>>(d_I, d_Z, zscale, w, w * h, planes, plane_f2, q.plane_off, q.rec_off, q.nbands, q.w, q.h, q.pitch, l, masks, mask_words, q.mask_off, ti, td);
+      else k_pyr_finish<false, false><<<g, T, 0, st>>>(d_I, d_Z, zscale, w, w * h, planes, plane_f2, q.plane_off, q.rec_off, q.nbands, q.w, q.h, q.pitch, l, masks, mask_words, q.mask_off, ti, td);
       k_sel_info<<<n, 32, 0, st>>>(masks, mask_words, q.mask_off, q.words, sel, sel_ints, l);
-      k_drop_odd_last<<<(n + 127) / 128, 128, 0, st>>>(planes, plane_f2, q.plane_off, q.w, q.h, q.pitch, sel, sel_ints, l, n);
+      k_drop_odd_last<<<(n + 127) / 128, 128, 0, st>>>(planes, plane_f2, q.rec_off, q.nbands, q.w, sel, sel_ints, l, n);
       const int ntiles = q.nbands * q.nstrips;
+      k_rec_fill<<<dim3((ntiles * kTileH * kTileW + T - 1) / T, n), T, 0, st>>>(planes, plane_f2, q.rec_off, q.nbands, ntiles, q.w, q.h,
+                                                                              tmpl, tmpl_floats, q.tmpl_off);
+      ctx->launches += 1;
       k_tile_range<<<dim3((ntiles + 7) / 8, n), 256, 0, st>>>(planes, plane_f2, q.plane_off, q.w, q.h, q.pitch, q.nbands, ntiles,
                                                               ranges, range_f2, q.range_off);
       ctx->launches += 4;
@@ -419,9 +443,10 @@ int pyramid_reselect(dvo_b200_ctx* ctx, dvo_b200_pyramid* p, float ti, float td)
   for (int l = 0; l < p->levels; ++l) {
     const LevelInfo& q = p->L[l];
     const int T = 256;
-    k_reselect<<<(q.words * 32 + T - 1) / T, T, 0, st>>>(p->planes + q.plane_off, q.w, q.h, q.pitch, p->sel_mask + q.mask_off, ti, td);
+    k_reselect<<<(q.words * 32 + T - 1) / T, T, 0, st>>>(p->planes + q.plane_off, p->planes + q.rec_off, q.nbands, q.w, q.h, q.pitch,
+                                                         p->sel_mask + q.mask_off, ti, td);
     k_sel_info<<<1, 32, 0, st>>>(p->sel_mask, 0, q.mask_off, q.words, p->sel_info, 0, l);
-    k_drop_odd_last<<<1, 32, 0, st>>>(p->planes, 0, q.plane_off, q.w, q.h, q.pitch, p->sel_info, 0, l, 1);
+    k_drop_odd_last<<<1, 32, 0, st>>>(p->planes, 0, q.rec_off, q.nbands, q.w, p->sel_info, 0, l, 1);
     ctx->launches += 3;
   }
   DVO_CUDA(ctx, cudaGetLastError());

@@ -67,13 +67,26 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, u
                "r"(bytes)
                : "memory");
 }
+// try_wait may suspend the thread in hardware until the phase completes or a time limit passes; the explicit limit (ns)
+// keeps the polling loop around it from spinning (measured: 7 % of all issued instructions were this loop).
+#ifndef DVO_TRYWAIT_HINT_NS
+#define DVO_TRYWAIT_HINT_NS 0
+#endif
 __device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned parity) {
   unsigned ok;
+#if DVO_TRYWAIT_HINT_NS > 0
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"((unsigned)DVO_TRYWAIT_HINT_NS)
+      : "memory");
+#else
   asm volatile(
       "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
       : "r"(smem_u32(bar)), "r"(parity)
       : "memory");
+#endif
   return ok != 0;
 }
 // Bounded wait: a lost transaction must never hang the GPU.  try_wait suspends in hardware for a
@@ -87,6 +100,43 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
     }
   }
 }
+// the same on 32-bit shared-window addresses (the consumers keep the pipe's base address in a register: going through
+// generic pointers re-derives the shared window from special registers at every tile)
+__device__ __forceinline__ bool mbar_try_wait_s(unsigned bar, unsigned parity) {
+  unsigned ok;
+#if DVO_TRYWAIT_HINT_NS > 0
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"((unsigned)DVO_TRYWAIT_HINT_NS)
+      : "memory");
+#else
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+#endif
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_s(unsigned bar, unsigned parity, int* error_flag) {
+  unsigned spins = 0;
+  while (!mbar_try_wait_s(bar, parity)) {
+    if (((++spins) & 0xfffu) == 0u) {
+      if (*reinterpret_cast<volatile int*>(error_flag)) break;
+      if (spins > (1u << 24)) { atomicExch(error_flag, 2); break; }
+    }
+  }
+}
+__device__ __forceinline__ void mbar_arrive_s(unsigned bar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.release.cta.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ int4 lds_i4(unsigned addr) {
+  int4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+
 // global -> shared bulk copy of `bytes` (multiple of 16, both addresses 16-byte aligned); completion is
 // counted on `bar` (SASS: UBLKCP)
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar) {
@@ -117,6 +167,7 @@ __device__ __forceinline__ f2 lds_f2_at(unsigned addr) {
 // Loop-invariant addresses and constants that the compiler would otherwise re-derive from special registers and
 // kernel parameters in every round (S2R + a dozen integer ops): pin them in a register.
 __device__ __forceinline__ unsigned pin(unsigned v) { asm volatile("" : "+r"(v)); return v; }
+__device__ __forceinline__ int pin(int v) { asm volatile("" : "+r"(v)); return v; }
 __device__ __forceinline__ float pin(float v) { asm volatile("" : "+f"(v)); return v; }
 template <typename T>
 __device__ __forceinline__ const T* pin(const T* p) { asm volatile("" : "+l"(p)); return p; }
@@ -132,16 +183,20 @@ struct __align__(16) TileDesc {   // written by the producer before it arms the 
   int pad_;
 };
 struct __align__(128) StageBuf {
-  float2 ref0[kTileH][kTileW];       // reference P3 rows of the tile: (I, Zsel)
-  float2 ref1[kTileH][kTileW];       // reference P1 rows (stage B): (Ix, Iy)
+  // the reference tile record (common.cuh), filled by ONE bulk copy: stage A takes the first two members, stage B all three
+  float2 ref0[kTileH][kTileW];       // (I, Zsel) rows of the tile
+  float tx[kTileW];                  // point-cloud template of the tile's columns
+  float2 ref1[kTileH][kTileW];       // (Ix, Iy) rows (stage B)
   float2 win[kWinRows][kWinCols];    // window of the current image (P0 in stage A, P2 in stage B)
-  float tx[kTileW];                  // point-cloud template of the band's columns
 };
+static_assert(offsetof(StageBuf, tx) == kRecTx * sizeof(float2) && offsetof(StageBuf, ref1) == kRecP1 * sizeof(float2) &&
+              offsetof(StageBuf, win) == kRecF2 * sizeof(float2), "StageBuf must mirror the reference tile record");
 struct TilePipe {
   StageBuf buf[kStages];
   unsigned long long full[kStages], empty[kStages];
   TileDesc desc[kStages];
 };
+static_assert(sizeof(TileDesc) == 32 && offsetof(TilePipe, desc) % 16 == 0, "TileDesc is read as two 16-byte words");
 
 // developer timing (build with -DDVO_PIPE_TIMING, run with DVO_B200_TIMING=1): cycles one warp of the CTA spends
 // waiting on the pipeline.  Compiled out of the product build.
@@ -275,9 +330,6 @@ __device__ __noinline__ void produce_tiles(TilePipe& tp, const PairLevel& pl, co
       const unsigned wa = __shfl_sync(kFullMask, wordA, k * 8), wd = __shfl_sync(kFullMask, wordD, k * 8);
       const int s = s_issue, b = b_issue;
       if (++b_issue == g.nbands) { b_issue = 0; ++s_issue; }
-      const int y0 = s * kTileH, rows = min(kTileH, g.h - y0);
-      const int x0 = b * kTileW, bw = min(kTileW, g.w - x0);
-      const unsigned ref_row_bytes = (unsigned)((bw + 1) & ~1) * 8u;
       const int skip = (int)(wa & 1u), ncols = (int)((wa >> 2) & 0xffu), nrows = (int)(wa >> 10);
       const int win_bx0 = (int)(wd & 0xffffu), win_row_lo = (int)(wd >> 16) - 1;
       TileDesc d;
@@ -293,8 +345,8 @@ __device__ __noinline__ void produce_tiles(TilePipe& tp, const PairLevel& pl, co
         d.vcount = max(nrows - 3, 0);
       }
       const unsigned win_row_bytes = (unsigned)ncols * 8u;
-      const unsigned tx_bytes = (unsigned)((bw + 3) & ~3) * 4u;
-      const unsigned total = skip ? 0u : (unsigned)rows * ref_row_bytes * (kStageB ? 2u : 1u) + (unsigned)nrows * win_row_bytes + tx_bytes;
+      const unsigned rec_bytes = (unsigned)(kStageB ? kRecF2 : kRecP1) * 8u;       // stage A stops before the gradient rows
+      const unsigned total = skip ? 0u : rec_bytes + (unsigned)nrows * win_row_bytes;
       // the descriptor is ready: now wait until the consumers have released the buffer's previous tile
       const long long tp1 = DVO_CLOCK(tm);
       mbar_wait(&tp.empty[bufi], ((t / kStages) & 1u) ^ 1u, error_flag);
@@ -307,16 +359,11 @@ __device__ __noinline__ void produce_tiles(TilePipe& tp, const PairLevel& pl, co
       }
       __syncwarp();
       if (!skip) {
-        if (lane < rows) {
-          const size_t off = (size_t)(y0 + lane) * g.pitch + x0;
-          bulk_g2s(&sb.ref0[lane][0], pl.r0 + off, ref_row_bytes, &tp.full[bufi]);
-          if (kStageB) bulk_g2s(&sb.ref1[lane][0], pl.r1 + off, ref_row_bytes, &tp.full[bufi]);
-        }
         if (lane < nrows) {
           const int yy = min(max(win_row_lo + lane, 0), g.h - 1);
           bulk_g2s(&sb.win[lane][0], cur + (size_t)yy * g.pitch + win_bx0, win_row_bytes, &tp.full[bufi]);
         }
-        if (lane == 31) bulk_g2s(&sb.tx[0], pl.rtmpl + x0, tx_bytes, &tp.full[bufi]);
+        if (lane == 31) bulk_g2s(&sb.ref0[0][0], pl.r0 + (size_t)(s * g.nbands + b) * kRecF2, rec_bytes, &tp.full[bufi]);
       }
     }
   }
@@ -649,18 +696,18 @@ __device__ __forceinline__ void scale_state_export(ScaleState& st, int lane, flo
 }
 
 // ---- consumers ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ WinView make_view(const StageBuf& sb, const TileDesc& d, const float2* plane, const LevelGeom& g) {
+// `bufs`: shared-window address of the stage buffer; TileDesc as the two 16-byte words it is stored as
+__device__ __forceinline__ WinView make_view(unsigned bufs, const int4& d0, const int4& d1, const float2* plane, int w, int h, int pitch) {
   WinView wv;
-  const unsigned w0 = smem_u32(&sb.win[0][0]);
-  wv.base = pin(w0 - (unsigned)d.origin);
+  const unsigned w0 = bufs + (unsigned)offsetof(StageBuf, win);
+  wv.base = pin(w0 - (unsigned)d0.y);                       // TileDesc: {skip, origin, ulo, ucount}, {vlo, vcount, exact, pad}
   wv.safe = pin(w0 + (unsigned)((kWinCols + 1) * 8));
   wv.plane = plane;
-  wv.exact = d.exact != 0;
-  wv.ulo = d.ulo; wv.ucount = d.ucount; wv.vlo = d.vlo; wv.vcount = d.vcount;
-  wv.w = g.w; wv.h = g.h; wv.pitch = g.pitch;
+  wv.exact = d1.z != 0;
+  wv.ulo = d0.z; wv.ucount = d0.w; wv.vlo = d1.x; wv.vcount = d1.y;
+  wv.w = w; wv.h = h; wv.pitch = pitch;
   return wv;
 }
-
 // Stage A over this CTA's strips: warp q walks image row strip*kTileH + q band by band, carries the pairwise
 // scale state across the bands (they are consecutive pixels of the row) and writes one segment summary per row
 // to row_exports[y * kSegExportFloats].  Warp kConsumerWarps is the producer: it stages the same tiles, kStages ahead.
@@ -676,26 +723,32 @@ __device__ __forceinline__ void stage_a_run(TilePipe& tp, const PairLevel& pl, c
     return;
   }
   int i = 0;
+  // loop invariants in registers (the level geometry otherwise comes from constant memory through a dynamic index)
+  const unsigned tp_s = pin(smem_u32(&tp));
+  const unsigned my_ref = pin((unsigned)(offsetof(StageBuf, ref0) + (q * kTileW + lane) * 8));
+  const unsigned my_tx = pin((unsigned)(offsetof(StageBuf, tx) + lane * 4));
+  const int gw = pin(g.w), gh = pin(g.h), gnb = pin(g.nbands), gpitch = g.pitch;
   for (int s = g.strip0; s < g.strip1; ++s) {
     const int y = s * kTileH + q;
-    const bool row_ok = y < g.h;
-    const float ty = __ldg(pl.rtmpl + g.w + min(y, g.h - 1));
+    const bool row_ok = y < gh;
+    const float ty = __ldg(pl.rtmpl + gw + min(y, gh - 1));
     ScaleState ss;
     scale_state_init(ss);
-    for (int b = 0; b < g.nbands; ++b, ++i) {
+    for (int b = 0; b < gnb; ++b, ++i) {
       const unsigned t = tbase + i;
-      const int bufi = t % kStages;
-      const int x0 = b * kTileW, bw = min(kTileW, g.w - x0);
+      const unsigned bufi = t % kStages;
+      const int x0 = b * kTileW, bw = min(kTileW, gw - x0);
       const long long tw0 = DVO_CLOCK(tm);
-      mbar_wait(&tp.full[bufi], (t / kStages) & 1u, error_flag);
+      mbar_wait_s(tp_s + (unsigned)offsetof(TilePipe, full) + bufi * 8u, (t / kStages) & 1u, error_flag);
       DVO_ADD(tm, wait_full_a, DVO_CLOCK(tm) - tw0);
-      const StageBuf& sb = tp.buf[bufi];
-      const TileDesc d = tp.desc[bufi];
-      if (row_ok && !d.skip) {
-        const WinView wv = make_view(sb, d, pl.c0, g);
+      const unsigned bufs = tp_s + bufi * (unsigned)sizeof(StageBuf);
+      const int4 d0 = lds_i4(tp_s + (unsigned)offsetof(TilePipe, desc) + bufi * 32u);
+      if (row_ok && !d0.x) {
+        const int4 d1 = lds_i4(tp_s + (unsigned)offsetof(TilePipe, desc) + bufi * 32u + 16u);
+        const WinView wv = make_view(bufs, d0, d1, pl.c0, gw, gh, gpitch);
         const int nr = (bw + 31) >> 5;
-        unsigned refa = pin(smem_u32(&sb.ref0[q][0]) + lane * 8);
-        unsigned txa = pin(smem_u32(&sb.tx[0]) + lane * 4);
+        unsigned refa = bufs + my_ref;
+        unsigned txa = bufs + my_tx;
         const int xlim = bw - lane;        // lane's column r*32+lane is inside the band iff r*32 < xlim
         // two rounds per trip: their projection / tap / blend chains are independent and interleave
 #pragma unroll 1
@@ -720,7 +773,7 @@ __device__ __forceinline__ void stage_a_run(TilePipe& tp, const PairLevel& pl, c
         }
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tp.empty[bufi]);
+      if (lane == 0) mbar_arrive_s(tp_s + (unsigned)offsetof(TilePipe, empty) + bufi * 8u);
     }
     if (row_ok) scale_state_export(ss, lane, row_exports + (size_t)y * kSegExportFloats);
   }
@@ -831,31 +884,36 @@ __device__ __forceinline__ void stage_b_run(TilePipe& tp, const PairLevel& pl, c
     return;
   }
   int i = 0;
+  const unsigned tp_s = pin(smem_u32(&tp));
+  const unsigned my_ref = (unsigned)(offsetof(StageBuf, ref0) + (q * kTileW + lane) * 8);
+  const unsigned my_tx = (unsigned)(offsetof(StageBuf, tx) + lane * 4);
+  const int gw = g.w, gh = g.h, gnb = g.nbands, gpitch = g.pitch;
   for (int s = g.strip0; s < g.strip1; ++s) {
     const int y = s * kTileH + q;
-    const bool row_ok = y < g.h;
-    const float ty = __ldg(pl.rtmpl + g.w + min(y, g.h - 1));
+    const bool row_ok = y < gh;
+    const float ty = __ldg(pl.rtmpl + gw + min(y, gh - 1));
     int rank = 0;              // rank of the row's first point inside this CTA (n < 2^31)
     if (cta_has_tail && row_ok) rank = __ldcg(row_base + y);
-    for (int b = 0; b < g.nbands; ++b, ++i) {
+    for (int b = 0; b < gnb; ++b, ++i) {
       const unsigned t = tbase + i;
-      const int bufi = t % kStages;
-      const int x0 = b * kTileW, bw = min(kTileW, g.w - x0);
+      const unsigned bufi = t % kStages;
+      const int x0 = b * kTileW, bw = min(kTileW, gw - x0);
       const long long tw0 = DVO_CLOCK(tm);
-      mbar_wait(&tp.full[bufi], (t / kStages) & 1u, error_flag);
+      mbar_wait_s(tp_s + (unsigned)offsetof(TilePipe, full) + bufi * 8u, (t / kStages) & 1u, error_flag);
       DVO_ADD(tm, wait_full_b, DVO_CLOCK(tm) - tw0);
-      const StageBuf& sb = tp.buf[bufi];
-      const TileDesc d = tp.desc[bufi];
-      if (row_ok && !d.skip) {
-        const WinView wv = make_view(sb, d, pl.c3, g);
+      const unsigned bufs = tp_s + bufi * (unsigned)sizeof(StageBuf);
+      const int4 d0 = lds_i4(tp_s + (unsigned)offsetof(TilePipe, desc) + bufi * 32u);
+      if (row_ok && !d0.x) {
+        const int4 d1 = lds_i4(tp_s + (unsigned)offsetof(TilePipe, desc) + bufi * 32u + 16u);
+        const WinView wv = make_view(bufs, d0, d1, pl.c3, gw, gh, gpitch);
         const int nr = (bw + 31) >> 5;
-        unsigned refa = pin(smem_u32(&sb.ref0[q][0]) + lane * 8);
-        unsigned txa = pin(smem_u32(&sb.tx[0]) + lane * 4);
+        unsigned refa = bufs + my_ref;
+        unsigned txa = bufs + my_tx;
         const int xlim = bw - lane;
 #pragma unroll 1
         for (int r = 0; r < nr; ++r, refa += 256, txa += 128) {
           const f2 rz = lds_f2_at(refa);
-          const f2 gr = lds_f2<sizeof(float2) * kTileW * kTileH>(refa);     // ref1 follows ref0 in the stage buffer
+          const f2 gr = lds_f2<sizeof(float2) * kRecP1>(refa);              // the gradient rows of the record
           const float tx = lds_f32(txa);
           float z = hi(rz);
           if (bw < kTileW) z = (r * 32 < xlim) ? z : __int_as_float(0x7fc00000);
@@ -869,7 +927,7 @@ __device__ __forceinline__ void stage_b_run(TilePipe& tp, const PairLevel& pl, c
             keep = valid && (rank + __popc(m & lt_mask)) < keep_rank;
             rank += __popc(m);
           }
-          if (kDump && r * 32 < xlim) dump_record(dump, (size_t)y * g.w + x0 + r * 32 + lane, valid, E, G, H, z);
+          if (kDump && r * 32 < xlim) dump_record(dump, (size_t)y * gw + x0 + r * 32 + lane, valid, E, G, H, z);
           // rejected points: zero weight and finite stand-ins (their own values may be NaN)
           const float ei = valid ? lo(E) : 0.f, ez = valid ? hi(E) : 0.f;
           const float wall = student_weight(c, ei, ez);
@@ -878,10 +936,10 @@ __device__ __forceinline__ void stage_b_run(TilePipe& tp, const PairLevel& pl, c
           stage_b_pixel(acc, cb, wgt, keep, ei, ez, valid ? G : 0ull, valid ? H : 0ull, valid ? z : 1.0f, valid ? tx : 0.f, ty);
         }
       } else if (kDump && row_ok) {
-        for (int xl = lane; xl < bw; xl += 32) dump_record(dump, (size_t)y * g.w + x0 + xl, false, 0ull, 0ull, 0ull, 0.f);
+        for (int xl = lane; xl < bw; xl += 32) dump_record(dump, (size_t)y * gw + x0 + xl, false, 0ull, 0ull, 0ull, 0.f);
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tp.empty[bufi]);
+      if (lane == 0) mbar_arrive_s(tp_s + (unsigned)offsetof(TilePipe, empty) + bufi * 8u);
     }
   }
 }

@@ -871,12 +871,12 @@ void fill_pair_levels(PairLevel* h, int n, dvo_b200_pyramid* const* refs, dvo_b2
     const LevelInfo& cl = c->L[level];
     PairLevel& q = h[i];
     const size_t plane = (size_t)rl.pitch * rl.h;
-    q.r0 = r->planes + rl.plane_off + 3 * plane; q.r1 = r->planes + rl.plane_off + plane;
+    q.r0 = r->planes + rl.rec_off; q.r1 = q.r0;
     q.rmask = r->sel_mask + rl.mask_off;
     q.rsel = r->sel_info + 2 * level;
     q.rtmpl = r->tmpl + rl.tmpl_off;
     q.rrange = r->tile_range + rl.range_off;
-    q.c0 = c->planes + cl.plane_off; q.c3 = q.c0 + 2 * plane;
+    q.c0 = c->planes + cl.plane_off; q.c3 = q.c0 + plane;
     q.cfx = cl.fx; q.cfy = cl.fy; q.cox = cl.ox; q.coy = cl.oy;
     // PointSelection::getMaximumNumberOfPoints (point_selection.cpp:68-71)
     q.max_valid_pixels = (long long)(size_t)((double)r->L[0].n * pow(0.25, (double)level));
