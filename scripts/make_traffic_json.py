@@ -45,8 +45,8 @@ def main():
     rows = list(csv.reader(out.splitlines()))
     hdr, units, body = rows[0], rows[1], rows[2:]
     n = len(body)
-    assert n % 2 == 0 and n > 0, f"{n} launches in the report: expected two steps"
-    step = body[n // 2:]
+    assert n == 1 or (n % 2 == 0 and n > 0), f"{n} launches in the report: expected one step, or a warm-up step and a step"
+    step = body if n == 1 else body[n // 2:]
     col = {k: hdr.index(k) for k in KEEP if k in hdr}
 
     def to_bytes(r, k):
