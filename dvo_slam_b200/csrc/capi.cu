@@ -107,7 +107,7 @@ int dvo_b200_destroy(dvo_b200_ctx* ctx) {
   for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
   Workspace& ws = ctx->ws;
   cudaFree(ws.d_pair_level); cudaFree(ws.d_state); cudaFree(ws.d_row_exports); cudaFree(ws.d_row_base);
-  cudaFree(ws.d_cta_exports); cudaFree(ws.d_cta_base); cudaFree(ws.d_normal_partial); cudaFree(ws.d_dump); cudaFree(ws.d_tinit);
+  cudaFree(ws.d_strip_exports); cudaFree(ws.d_strip_base); cudaFree(ws.d_row_partial); cudaFree(ws.d_strip_partial); cudaFree(ws.d_dump); cudaFree(ws.d_tinit);
   cudaFree(ws.d_iter_log); cudaFree(ws.d_squads);
   if (ws.h_active) cudaFreeHost(ws.h_active);
   pool_close(ctx);

@@ -568,6 +568,44 @@ __device__ __forceinline__ void store_seg_export(const SegT<double>& s, float* e
   e[7] = (float)s.wf; e[8] = (float)s.wl;
 }
 
+// Strip summaries.  Everything above a row is combined in an order that depends only on the level's geometry, never on how
+// the strips are spread over CTAs: the rows of a strip in order (one thread), the strips of the level by
+// combine_strip_exports_warp (fixed chunks per lane, then an in-order tree), all in fp64 without intermediate rounding.
+// Results are therefore bit-identical whatever the squad size: a batch of any size returns what single alignments return.
+constexpr int kStripExportDoubles = 12;   // n, S0[3], S1[3], wf, wl, ol[3]
+__device__ __forceinline__ void store_strip_export(const SegT<double>& s, double* e) {
+  e[0] = (double)s.n;
+  for (int k = 0; k < 3; ++k) { e[1 + k] = s.S0[k]; e[4 + k] = s.S1[k]; e[9 + k] = s.ol[k]; }
+  e[7] = s.wf; e[8] = s.wl;
+}
+__device__ __forceinline__ SegT<double> load_strip_export(const double* e) {
+  SegT<double> s;
+  double v[kStripExportDoubles];
+#pragma unroll
+  for (int i = 0; i < kStripExportDoubles; ++i) v[i] = __ldcg(e + i);     // written by other SMs in the same kernel
+  s.n = (long long)v[0];
+  s.S0[0] = v[1]; s.S0[1] = v[2]; s.S0[2] = v[3];
+  s.S1[0] = v[4]; s.S1[1] = v[5]; s.S1[2] = v[6];
+  s.wf = v[7]; s.wl = v[8]; s.ol[0] = v[9]; s.ol[1] = v[10]; s.ol[2] = v[11];
+  return s;
+}
+// one thread: rows [y0, y1) of one strip, in order -> the strip's summary; row_base[y] = valid points of the strip before row y
+__device__ __forceinline__ void combine_strip_rows(const float* row_exports, int y0, int y1, int* row_base, double* strip_export) {
+  SegT<double> acc;
+  acc.n = 0; acc.wf = acc.wl = 0;
+  for (int k = 0; k < 3; ++k) acc.S0[k] = acc.S1[k] = acc.ol[k] = 0;
+#pragma unroll
+  for (int k = 0; k < kTileH; ++k) {     // fixed trip count: the rows' loads are independent and overlap
+    const int y = y0 + k;
+    if (y < y1) {
+      const SegT<double> r = load_seg_export(row_exports + (size_t)y * kSegExportFloats);
+      row_base[y] = (int)acc.n;
+      acc = combine_seg<double>(acc, r);
+    }
+  }
+  store_strip_export(acc, strip_export);
+}
+
 // One warp combines `count` segment exports (kSegExportFloats floats each, in row-major pixel order) into one and
 // writes the exclusive prefix of their valid counts to base_out[0..count) (rank base of each segment).
 struct SegCombineSmem {
@@ -603,6 +641,42 @@ __device__ __forceinline__ SegT<double> combine_exports_warp(const float* e, int
     run += __float_as_int(__ldcg(e + (size_t)t * kSegExportFloats));
   }
   const SegT<double> all = sm.lanes[0];
+  __syncwarp();
+  return all;
+}
+
+// The same over the `count` strip summaries of a level; base_out[0 .. count] = exclusive prefix of the strips' valid counts
+// (base_out[count] = all valid points).
+__device__ __forceinline__ SegT<double> combine_strip_exports_warp(const double* e, int count, int* base_out, SegCombineSmem& sm) {
+  const int lane = threadIdx.x & 31;
+  const int chunk = (count + 31) / 32;
+  const int t0 = min(lane * chunk, count), t1 = min(t0 + chunk, count);
+  SegT<double> acc;
+  acc.n = 0; acc.wf = acc.wl = 0;
+  for (int k = 0; k < 3; ++k) acc.S0[k] = acc.S1[k] = acc.ol[k] = 0;
+  for (int t = t0; t < t1; ++t) acc = combine_seg<double>(acc, load_strip_export(e + (size_t)t * kStripExportDoubles));
+  sm.lanes[lane] = acc;
+  {   // exclusive prefix of the lane counts
+    long long incl = acc.n;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      long long v = __shfl_up_sync(kFullMask, incl, off);
+      if (lane >= off) incl += v;
+    }
+    sm.lane_base[lane] = incl - acc.n;
+  }
+  __syncwarp();
+  for (int off = 1; off < 32; off <<= 1) {   // in-order tree combine
+    if ((lane & (2 * off - 1)) == 0) sm.lanes[lane] = combine_seg<double>(sm.lanes[lane], sm.lanes[lane + off]);
+    __syncwarp();
+  }
+  long long run = sm.lane_base[lane];
+  for (int t = t0; t < t1; ++t) {
+    base_out[t] = (int)run;
+    run += (long long)__ldcg(e + (size_t)t * kStripExportDoubles);
+  }
+  const SegT<double> all = sm.lanes[0];
+  if (lane == 31) base_out[count] = (int)all.n;
   __syncwarp();
   return all;
 }
@@ -790,6 +864,8 @@ constexpr int kNormalValues = 28;   // log-likelihood sum, 21 upper-triangular A
 // Accumulators of stage B for one thread.  A is kept as pairs of adjacent columns of one row
 // (A[r][2c], A[r][2c+1]); rows 1, 3 and 5 carry one redundant lower-triangle entry so that every
 // update is a packed FMA of a broadcast row factor with a column pair.
+struct StageBAcc;
+__device__ __forceinline__ void stage_b_values(const StageBAcc& acc, float out[]);
 struct StageBAcc {
   f2 r0[3], r1[3], r2[2], r3[2], r4, r5;   // 12 pairs
   f2 b[3];
@@ -850,6 +926,26 @@ __device__ __forceinline__ void stage_b_pixel(StageBAcc& acc, const StageBConsts
   stage_b_rank1(acc, V1, wgt * c.wd1, -ez);
 }
 
+// Sum the kNormalValues accumulators of a row over the 32 lanes of its warp in a fixed order (halving exchange: partner
+// lane ^ 16, ^ 8, ... ^ 1; 31 shuffles instead of 5 x 28) and store the row's totals: lane l ends up with value l.
+__device__ __forceinline__ void flush_row_partial(const StageBAcc& acc, int lane, float* row_out) {
+  float a[32];
+  stage_b_values(acc, a);
+#pragma unroll
+  for (int i = kNormalValues; i < 32; ++i) a[i] = 0.f;
+#pragma unroll
+  for (int half = 16; half >= 1; half >>= 1) {
+    const bool up = (lane & half) != 0;
+#pragma unroll
+    for (int j = 0; j < half; ++j) {
+      const float mine = up ? a[half + j] : a[j];
+      const float send = up ? a[j] : a[half + j];
+      a[j] = mine + __shfl_xor_sync(kFullMask, send, half);
+    }
+  }
+  if (lane < kNormalValues) row_out[lane] = a[0];
+}
+
 // optional per-pixel dump of the residual records (dvo_b200_residual_image): seven planes of n floats
 struct RecordDump {
   float* planes;   // nullptr: off
@@ -870,9 +966,9 @@ __device__ __noinline__ void dump_record(const RecordDump& dump, size_t i, bool 
 // computeCompleteDataLogLikelihood (dense_tracking_impl.cpp:413-422).
 template <bool kDump>
 __device__ __forceinline__ void stage_b_run(TilePipe& tp, const PairLevel& pl, const LevelGeom& g, const StageConsts& c,
-                                            const StageBConsts& cb, const int* row_base, long long cta_base, long long n_keep,
-                                            bool cta_has_tail, const RecordDump& dump, StageBAcc& acc, unsigned& tile_count,
-                                            int* error_flag, PipeTiming& tm) {
+                                            const StageBConsts& cb, const int* row_base, const int* strip_base, long long cta_base,
+                                            long long n_keep, bool cta_has_tail, const RecordDump& dump, float* row_partial,
+                                            unsigned& tile_count, int* error_flag, PipeTiming& tm) {
   const int lane = threadIdx.x & 31, q = threadIdx.x >> 5;
   const unsigned lt_mask = (1u << lane) - 1u;
   const int ntiles = (g.strip1 - g.strip0) * g.nbands;
@@ -893,7 +989,9 @@ __device__ __forceinline__ void stage_b_run(TilePipe& tp, const PairLevel& pl, c
     const bool row_ok = y < gh;
     const float ty = __ldg(pl.rtmpl + gw + min(y, gh - 1));
     int rank = 0;              // rank of the row's first point inside this CTA (n < 2^31)
-    if (cta_has_tail && row_ok) rank = __ldcg(row_base + y);
+    if (cta_has_tail && row_ok) rank = (__ldcg(strip_base + s) - (int)cta_base) + __ldcg(row_base + y);
+    StageBAcc acc;             // one image row at a time: the row's sums leave the warp in a fixed order (flush_row_partial)
+    stage_b_init(acc);
     for (int b = 0; b < gnb; ++b, ++i) {
       const unsigned t = tbase + i;
       const unsigned bufi = t % kStages;
@@ -941,12 +1039,13 @@ __device__ __forceinline__ void stage_b_run(TilePipe& tp, const PairLevel& pl, c
       __syncwarp();
       if (lane == 0) mbar_arrive_s(tp_s + (unsigned)offsetof(TilePipe, empty) + bufi * 8u);
     }
+    if (row_ok) flush_row_partial(acc, lane, row_partial + (size_t)y * kNormalValues);
   }
 }
 
 // flush the product of the pending log-likelihood terms and unpack: out[0] = ll sum,
 // out[1..21] = A upper triangle (row-major), out[22..27] = b
-__device__ __forceinline__ void stage_b_values(const StageBAcc& acc, float out[kNormalValues]) {
+__device__ __forceinline__ void stage_b_values(const StageBAcc& acc, float out[]) {
   out[0] = acc.llsum * 0.69314718055994531f;
   out[1] = lo(acc.r0[0]); out[2] = hi(acc.r0[0]); out[3] = lo(acc.r0[1]); out[4] = hi(acc.r0[1]); out[5] = lo(acc.r0[2]); out[6] = hi(acc.r0[2]);
   out[7] = hi(acc.r1[0]); out[8] = lo(acc.r1[1]); out[9] = hi(acc.r1[1]); out[10] = lo(acc.r1[2]); out[11] = hi(acc.r1[2]);

@@ -116,12 +116,12 @@ __global__ void k_stage_words(const uint4* __restrict__ src, uint4* __restrict__
   if (i < n16) dst[i] = src[i];
 }
 
-// one warp per pair: combine the CTA summaries of the squad in order -> covariance -> P_k (dense_tracking.cpp:276-295).
-// e: the squad's g CTA exports; cta_base: exclusive prefix of their valid counts (output).
-__device__ __noinline__ void pair_mid_warp(PairState& st, int pair, const float* e, int* cta_base, int g, int* active,
+// one warp per pair: combine the strip summaries of the level in order -> covariance -> P_k (dense_tracking.cpp:276-295).
+// e: the level's nstrips strip summaries; strip_base: nstrips + 1 exclusive prefixes of their valid counts (output).
+__device__ __noinline__ void pair_mid_warp(PairState& st, int pair, const double* e, int* strip_base, int nstrips, int* active,
                                            const LevelLaunch& lp, dvo_b200_iteration_stats* ilog, int max_log, SegCombineSmem& sm) {
   const int lane = threadIdx.x & 31;
-  const SegT<double> all = combine_exports_warp(e, g, cta_base, sm);
+  const SegT<double> all = combine_strip_exports_warp(e, nstrips, strip_base, sm);
   if (lane == 0) {
     long long n = all.n;
     st.n = n;
@@ -180,7 +180,7 @@ struct PairEndSmem {
 };
 
 template <typename Release>
-__device__ __noinline__ void pair_end_cta(PairState& st, const PairLevel& pl, int pair, const float* partial, int ntiles,
+__device__ __noinline__ void pair_end_cta(PairState& st, const PairLevel& pl, int pair, const double* partial, int ntiles,
                                              int* active, const LevelLaunch& lp, dvo_b200_iteration_stats* ilog, int max_log,
                                              PairEndSmem& sm, Release release, unsigned long long* tcrit = nullptr) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -191,19 +191,19 @@ __device__ __noinline__ void pair_end_cta(PairState& st, const PairLevel& pl, in
   auto phase = [&](int k) {
     if (tcrit) { unsigned long long tn; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tn)); atomicAdd(tcrit + k, tn - tph); tph = tn; }
   };
-  {   // fp64 sum of the partials: warp q takes tiles q, q+4, ... with independent loads in flight
+  {   // fp64 sum of the level's strip partials in a fixed order: warp q takes strips q, q+4, ... with independent loads in flight
     double v = 0.0;
     if (lane < kNormalValues && warp < kEndWarps) {
-      const float* p = partial + lane;
+      const double* p = partial + lane;
       int t = warp;
       for (; t + 3 * kEndWarps < ntiles; t += 4 * kEndWarps) {
-        const float a0 = __ldcg(p + (size_t)t * kNormalValues);
-        const float a1 = __ldcg(p + (size_t)(t + kEndWarps) * kNormalValues);
-        const float a2 = __ldcg(p + (size_t)(t + 2 * kEndWarps) * kNormalValues);
-        const float a3 = __ldcg(p + (size_t)(t + 3 * kEndWarps) * kNormalValues);
-        v += (double)a0; v += (double)a1; v += (double)a2; v += (double)a3;
+        const double a0 = __ldcg(p + (size_t)t * kNormalValues);
+        const double a1 = __ldcg(p + (size_t)(t + kEndWarps) * kNormalValues);
+        const double a2 = __ldcg(p + (size_t)(t + 2 * kEndWarps) * kNormalValues);
+        const double a3 = __ldcg(p + (size_t)(t + 3 * kEndWarps) * kNormalValues);
+        v += a0; v += a1; v += a2; v += a3;
       }
-      for (; t < ntiles; t += kEndWarps) v += (double)__ldcg(p + (size_t)t * kNormalValues);
+      for (; t < ntiles; t += kEndWarps) v += __ldcg(p + (size_t)t * kNormalValues);
     }
     if (warp < kEndWarps) sm.part[warp][lane] = v;
   }
@@ -358,9 +358,10 @@ struct Segment {
   const PairLevel* pls;   // descriptors of this segment's levels: [level][pair]
   float* row_exports;     // per squad: h segment summaries (one per image row)
   int* row_base;          // per squad: h exclusive prefixes of valid counts, relative to the owning CTA's first row
-  float* cta_exports;     // per squad: g segment summaries
-  int* cta_base;          // per squad: g exclusive prefixes
-  float* partial;         // per squad: g x kNormalValues
+  double* strip_exports;  // per squad: one scale summary per strip (kStripExportDoubles)
+  int* strip_base;        // per squad: nstrips + 1 exclusive prefixes of the strips' valid counts
+  float* row_partial;     // per squad: kNormalValues per image row (stage B)
+  double* strip_partial;  // per squad: kNormalValues per strip, the strip's rows summed in fp64
   SquadState* squads;
   int* queue;             // next pair (first segment) / next slot of this segment's ready ring (later segments of a fused launch)
   int* ready;             // fused launch, segments >= 1: ring of (pair + 1) whose coarse levels are done, 0 = not yet written
@@ -470,9 +471,11 @@ k_level_persistent(const __grid_constant__ PersistentArgs a) {
   for (int li = 0; li < S.nlev; ++li) hmax = max(hmax, S.lp[li].h);
   float* row_exports = S.row_exports + (size_t)squad * hmax * kSegExportFloats;
   int* row_base = S.row_base + (size_t)squad * hmax;
-  float* cta_exports = S.cta_exports + (size_t)squad * S.g * kSegExportFloats;
-  int* cta_base = S.cta_base + (size_t)squad * S.g;
-  float* partial = S.partial + (size_t)squad * S.g * kNormalValues;
+  const int smax = (hmax + kTileH - 1) / kTileH;      // strips of the tallest level of the segment
+  double* strip_exports = S.strip_exports + (size_t)squad * smax * kStripExportDoubles;
+  int* strip_base = S.strip_base + (size_t)squad * (smax + 1);
+  float* row_partial = S.row_partial + (size_t)squad * hmax * kNormalValues;
+  double* strip_partial = S.strip_partial + (size_t)squad * smax * kNormalValues;
   unsigned episode = 0;
   unsigned long long t_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t0 = 0, t1 = 0;
   const bool timing = S.dbg != nullptr && threadIdx.x == 0;
@@ -549,15 +552,17 @@ k_level_persistent(const __grid_constant__ PersistentArgs a) {
         DVO_ADD(tm, rounds_a, DVO_CLOCK(tm) - ts0);
       }
       __syncthreads();
-      if (warp == 0) {   // this CTA's rows, in order -> one summary; row_base: rank of each row's first point inside the CTA
-        const SegT<double> mine = combine_exports_warp(row_exports + (size_t)row0 * kSegExportFloats, row1 - row0, row_base + row0, lt.comb);
-        if (lane == 0) store_seg_export(mine, cta_exports + (size_t)rank * kSegExportFloats);
+      // this CTA's strips: the rows of a strip in order -> the strip's summary (one thread per strip); row_base: rank of each
+      // row's first point inside its strip
+      for (int j = threadIdx.x; j < geo.strip1 - geo.strip0; j += kCtaThreads) {
+        const int sj = geo.strip0 + j;
+        combine_strip_rows(row_exports, sj * kTileH, min(sj * kTileH + kTileH, lp.h), row_base, strip_exports + (size_t)sj * kStripExportDoubles);
       }
       DVO_TOCK(0);
       if (squad_arrive(sq, episode, S.g, lt.s_flag)) {
         DVO_TOCK(2);
         if (warp == 0) {
-          pair_mid_warp(st, pair, cta_exports, cta_base, S.g, nullptr, lp, a.ilog, a.max_log, lt.comb);
+          pair_mid_warp(st, pair, strip_exports, strip_base, lp.nstrips, nullptr, lp, a.ilog, a.max_log, lt.comb);
           if (lane == 0) squad_release(sq, episode);
         }
         __syncthreads();
@@ -576,39 +581,35 @@ k_level_persistent(const __grid_constant__ PersistentArgs a) {
         load_stage_consts(st, pl, lp.w, lp.h, true, c);
         StageBConsts cb;
         load_stage_b_consts(st, cb);
-        StageBAcc acc;
-        stage_b_init(acc);
         const long long n_keep = __ldcg(&st.n_keep);
-        const long long my_base = __ldcg(&cta_base[rank]);
-        const long long my_n = __float_as_int(__ldcg(cta_exports + (size_t)rank * kSegExportFloats));
+        const long long my_base = __ldcg(&strip_base[geo.strip0]);
+        const long long my_n = __ldcg(&strip_base[geo.strip1]) - my_base;
         RecordDump dump;
         dump.planes = a.dump; dump.n = lp.n;
         const long long ts0 = DVO_CLOCK(tm);
-        if (a.dump) stage_b_run<true>(tp, pl, geo, c, cb, row_base, my_base, n_keep, my_base + my_n > n_keep, dump, acc, tile_count, a.error_flag, tm);
-        else stage_b_run<false>(tp, pl, geo, c, cb, row_base, my_base, n_keep, my_base + my_n > n_keep, dump, acc, tile_count, a.error_flag, tm);
+        if (a.dump) stage_b_run<true>(tp, pl, geo, c, cb, row_base, strip_base, my_base, n_keep, my_base + my_n > n_keep, dump, row_partial, tile_count, a.error_flag, tm);
+        else stage_b_run<false>(tp, pl, geo, c, cb, row_base, strip_base, my_base, n_keep, my_base + my_n > n_keep, dump, row_partial, tile_count, a.error_flag, tm);
         DVO_ADD(tm, rounds_b, DVO_CLOCK(tm) - ts0);
-        float v[kNormalValues];
-        stage_b_values(acc, v);
-#pragma unroll
-        for (int i = 0; i < kNormalValues; ++i) {
-#pragma unroll
-          for (int off = 16; off > 0; off >>= 1) v[i] += __shfl_xor_sync(kFull, v[i], off);
-        }
-        if (lane == 0 && warp < kConsumerWarps) {
-#pragma unroll
-          for (int i = 0; i < kNormalValues; ++i) lt.red[warp][i] = v[i];
-        }
       }
       __syncthreads();
-      if (threadIdx.x < kNormalValues) {
-        float s = 0.f;
-        for (int k = 0; k < kConsumerWarps; ++k) s += lt.red[k][threadIdx.x];
-        partial[(size_t)rank * kNormalValues + threadIdx.x] = s;
+      // the rows of each of this CTA's strips, in order, in fp64: one thread per (strip, value)
+      for (int it = threadIdx.x; it < (geo.strip1 - geo.strip0) * kNormalValues; it += kCtaThreads) {
+        const int j = it / kNormalValues, i = it - j * kNormalValues;
+        const int sj = geo.strip0 + j;
+        const int nrow = min(kTileH, lp.h - sj * kTileH);
+        const float* rp = row_partial + (size_t)sj * kTileH * kNormalValues + i;
+        float r[kTileH];
+#pragma unroll
+        for (int k = 0; k < kTileH; ++k) r[k] = k < nrow ? __ldcg(rp + (size_t)k * kNormalValues) : 0.f;   // independent loads
+        double v = 0.0;
+#pragma unroll
+        for (int k = 0; k < kTileH; ++k) v += (double)r[k];      // a missing row adds an exact zero
+        strip_partial[(size_t)sj * kNormalValues + i] = v;
       }
       DVO_TOCK(1);
       if (squad_arrive(sq, episode, S.g, lt.s_flag)) {
         DVO_TOCK(3);
-        pair_end_cta(st, pl, pair, partial, S.g, nullptr, lp, a.ilog, a.max_log, lt.end, [&] { squad_release(sq, episode); }, S.dbg2 ? S.dbg2 + 64 : nullptr);
+        pair_end_cta(st, pl, pair, strip_partial, lp.nstrips, nullptr, lp, a.ilog, a.max_log, lt.end, [&] { squad_release(sq, episode); }, S.dbg2 ? S.dbg2 + 64 : nullptr);
         __syncthreads();
         DVO_TOCK(5);
       } else {
@@ -721,7 +722,8 @@ int grow(dvo_b200_ctx* ctx, T*& ptr, size_t& cap, size_t need) {
 }
 
 struct ScratchNeed {
-  size_t row_export_floats = 0, row_base_ints = 0, cta_export_floats = 0, cta_base_ints = 0, partial_floats = 0, squads = 0;
+  size_t row_export_floats = 0, row_base_ints = 0, strip_export_doubles = 0, strip_base_ints = 0, row_partial_floats = 0,
+         strip_partial_doubles = 0, squads = 0;
   size_t dump_floats = 0;
 };
 
@@ -737,9 +739,10 @@ int ensure_workspace(dvo_b200_ctx* ctx, int npairs, const ScratchNeed& need, int
   int rc;
   if ((rc = grow(ctx, ws.d_row_exports, ws.cap_row_exports, need.row_export_floats))) return rc;
   if ((rc = grow(ctx, ws.d_row_base, ws.cap_row_base, need.row_base_ints))) return rc;
-  if ((rc = grow(ctx, ws.d_cta_exports, ws.cap_cta_exports, need.cta_export_floats))) return rc;
-  if ((rc = grow(ctx, ws.d_cta_base, ws.cap_cta_base, need.cta_base_ints))) return rc;
-  if ((rc = grow(ctx, ws.d_normal_partial, ws.cap_partial, need.partial_floats))) return rc;
+  if ((rc = grow(ctx, ws.d_strip_exports, ws.cap_strip_exports, need.strip_export_doubles))) return rc;
+  if ((rc = grow(ctx, ws.d_strip_base, ws.cap_strip_base, need.strip_base_ints))) return rc;
+  if ((rc = grow(ctx, ws.d_row_partial, ws.cap_row_partial, need.row_partial_floats))) return rc;
+  if ((rc = grow(ctx, ws.d_strip_partial, ws.cap_strip_partial, need.strip_partial_doubles))) return rc;
   if ((rc = grow(ctx, ws.d_squads, ws.cap_squads, need.squads * sizeof(SquadState)))) return rc;
   if ((rc = grow(ctx, ws.d_dump, ws.cap_dump, need.dump_floats))) return rc;
   if (!ws.h_active) DVO_CUDA(ctx, cudaMallocHost((void**)&ws.h_active, sizeof(int) * 8));
@@ -897,9 +900,11 @@ ScratchNeed segment_need(int hmax, const GroupPlan& pl) {
   ScratchNeed s;
   s.row_export_floats = (size_t)pl.nsquads * hmax * kSegExportFloats;
   s.row_base_ints = (size_t)pl.nsquads * hmax;
-  s.cta_export_floats = (size_t)pl.nsquads * pl.g * kSegExportFloats;
-  s.cta_base_ints = (size_t)pl.nsquads * pl.g;
-  s.partial_floats = (size_t)pl.nsquads * pl.g * kNormalValues;
+  const size_t smax = (size_t)(hmax + kTileH - 1) / kTileH;
+  s.strip_export_doubles = (size_t)pl.nsquads * smax * kStripExportDoubles;
+  s.strip_base_ints = (size_t)pl.nsquads * (smax + 1);
+  s.row_partial_floats = (size_t)pl.nsquads * hmax * kNormalValues;
+  s.strip_partial_doubles = (size_t)pl.nsquads * smax * kNormalValues;
   s.squads = (size_t)pl.nsquads;
   return s;
 }
@@ -907,15 +912,17 @@ void add_launch_need(ScratchNeed& need, int nseg, const int* hmax, const GroupPl
   ScratchNeed sum;
   for (int s = 0; s < nseg; ++s) {
     const ScratchNeed q = segment_need(hmax[s], plans[s]);
-    sum.row_export_floats += q.row_export_floats; sum.row_base_ints += q.row_base_ints; sum.cta_export_floats += q.cta_export_floats;
-    sum.cta_base_ints += q.cta_base_ints; sum.partial_floats += q.partial_floats; sum.squads += q.squads;
+    sum.row_export_floats += q.row_export_floats; sum.row_base_ints += q.row_base_ints; sum.strip_export_doubles += q.strip_export_doubles;
+    sum.strip_base_ints += q.strip_base_ints; sum.row_partial_floats += q.row_partial_floats;
+    sum.strip_partial_doubles += q.strip_partial_doubles; sum.squads += q.squads;
   }
   sum.squads += 1 + ((size_t)npairs * sizeof(int) + sizeof(SquadState) - 1) / sizeof(SquadState);   // counters + ready ring
   need.row_export_floats = std::max(need.row_export_floats, sum.row_export_floats);
   need.row_base_ints = std::max(need.row_base_ints, sum.row_base_ints);
-  need.cta_export_floats = std::max(need.cta_export_floats, sum.cta_export_floats);
-  need.cta_base_ints = std::max(need.cta_base_ints, sum.cta_base_ints);
-  need.partial_floats = std::max(need.partial_floats, sum.partial_floats);
+  need.strip_export_doubles = std::max(need.strip_export_doubles, sum.strip_export_doubles);
+  need.strip_base_ints = std::max(need.strip_base_ints, sum.strip_base_ints);
+  need.row_partial_floats = std::max(need.row_partial_floats, sum.row_partial_floats);
+  need.strip_partial_doubles = std::max(need.strip_partial_doubles, sum.strip_partial_doubles);
   need.squads = std::max(need.squads, sum.squads);
 }
 
@@ -947,8 +954,8 @@ int launch_segments(dvo_b200_ctx* ctx, int nseg, const LevelLaunch (*lps)[kMaxLe
     const GroupPlan& plan = plans[s];
     S.pls = d_pls[s];
     S.row_exports = ws.d_row_exports + off.row_export_floats; S.row_base = ws.d_row_base + off.row_base_ints;
-    S.cta_exports = ws.d_cta_exports + off.cta_export_floats; S.cta_base = ws.d_cta_base + off.cta_base_ints;
-    S.partial = ws.d_normal_partial + off.partial_floats;
+    S.strip_exports = ws.d_strip_exports + off.strip_export_doubles; S.strip_base = ws.d_strip_base + off.strip_base_ints;
+    S.row_partial = ws.d_row_partial + off.row_partial_floats; S.strip_partial = ws.d_strip_partial + off.strip_partial_doubles;
     S.squads = squads + sq_off;
     S.queue = counters + s; S.ready_tail = counters + kMaxSeg + s; S.arrivals = counters + 2 * kMaxSeg + s;
     S.pair_begin = plan.pair_begin; S.npairs_seg = plan.npairs;
@@ -962,8 +969,8 @@ int launch_segments(dvo_b200_ctx* ctx, int nseg, const LevelLaunch (*lps)[kMaxLe
       if (k < plan.nlev) S.lp[k] = lps[s][k];
     }
     const ScratchNeed q = segment_need(hmax[s], plan);
-    off.row_export_floats += q.row_export_floats; off.row_base_ints += q.row_base_ints; off.cta_export_floats += q.cta_export_floats;
-    off.cta_base_ints += q.cta_base_ints; off.partial_floats += q.partial_floats;
+    off.row_export_floats += q.row_export_floats; off.row_base_ints += q.row_base_ints; off.strip_export_doubles += q.strip_export_doubles;
+    off.strip_base_ints += q.strip_base_ints; off.row_partial_floats += q.row_partial_floats; off.strip_partial_doubles += q.strip_partial_doubles;
     sq_off += plan.nsquads;
   }
   {

@@ -150,9 +150,8 @@ int main(int argc, char** argv) {
     std::chrono::steady_clock::time_point t2 = std::chrono::steady_clock::now();
     batch_first_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
     batch_again_ms = std::chrono::duration<double, std::milli>(t2 - t1).count();
-    // A batch this large is spread over the grid with other squad sizes than a single alignment, so its fp32 sums are
-    // grouped differently: the answers agree to rounding, not bit for bit (the two- and three-pair batches above do);
-    // all alignments of the batch see the same inputs and the same plan and must agree exactly among themselves.
+    // A batch this large is spread over the grid with other squad sizes than a single alignment; sums are taken in an
+    // order fixed by the level geometry, so the answers are still those of the single alignment, bit for bit.
     for (int i = 0; i < nbatch; ++i) {
       const dvo::DenseTracker::Result& r = props[size_t(i)].TrackingResult;
       if (!same_pose(r, result)) batch_bitwise = 0;
