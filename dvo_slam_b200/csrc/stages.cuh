@@ -218,7 +218,7 @@ struct PipeTiming {};
 struct LevelGeom {
   int w, h, n, pitch;       // pixels, row pitch of the planes (float2)
   int nbands, nstrips;
-  int strip0, strip1;       // this CTA's strips [strip0, strip1)
+  int strip0, strip_step, nmine;   // this CTA's strips: strip0 + k * strip_step, k = 0 .. nmine-1
 };
 
 // ---- per pair-iteration constants ---------------------------------------------------------------
@@ -275,7 +275,7 @@ __device__ __noinline__ void produce_tiles(TilePipe& tp, const PairLevel& pl, co
     {
       const int ii = min(i0 + sub, ntiles - 1);
       const int sd = ii / g.nbands;
-      const int s = g.strip0 + sd, b = ii - sd * g.nbands;
+      const int s = g.strip0 + sd * g.strip_step, b = ii - sd * g.nbands;
       const int y0 = s * kTileH, rows = min(kTileH, g.h - y0);
       const int x0 = b * kTileW, bw = min(kTileW, g.w - x0);
       const float2 zr = __ldg(pl.rrange + (size_t)s * g.nbands + b);
@@ -329,7 +329,7 @@ __device__ __noinline__ void produce_tiles(TilePipe& tp, const PairLevel& pl, co
       StageBuf& sb = tp.buf[bufi];
       const unsigned wa = __shfl_sync(kFullMask, wordA, k * 8), wd = __shfl_sync(kFullMask, wordD, k * 8);
       const int s = s_issue, b = b_issue;
-      if (++b_issue == g.nbands) { b_issue = 0; ++s_issue; }
+      if (++b_issue == g.nbands) { b_issue = 0; s_issue += g.strip_step; }
       const int skip = (int)(wa & 1u), ncols = (int)((wa >> 2) & 0xffu), nrows = (int)(wa >> 10);
       const int win_bx0 = (int)(wd & 0xffffu), win_row_lo = (int)(wd >> 16) - 1;
       TileDesc d;
@@ -562,11 +562,6 @@ __device__ __forceinline__ SegT<double> load_seg_export(const float* e) {
   s.wf = v[7]; s.wl = v[8]; s.ol[0] = v[9]; s.ol[1] = v[10]; s.ol[2] = v[11];
   return s;
 }
-__device__ __forceinline__ void store_seg_export(const SegT<double>& s, float* e) {
-  e[0] = __int_as_float((int)s.n);
-  for (int k = 0; k < 3; ++k) { e[1 + k] = (float)s.S0[k]; e[4 + k] = (float)s.S1[k]; e[9 + k] = (float)s.ol[k]; }
-  e[7] = (float)s.wf; e[8] = (float)s.wl;
-}
 
 // Strip summaries.  Everything above a row is combined in an order that depends only on the level's geometry, never on how
 // the strips are spread over CTAs: the rows of a strip in order (one thread), the strips of the level by
@@ -606,46 +601,14 @@ __device__ __forceinline__ void combine_strip_rows(const float* row_exports, int
   store_strip_export(acc, strip_export);
 }
 
-// One warp combines `count` segment exports (kSegExportFloats floats each, in row-major pixel order) into one and
-// writes the exclusive prefix of their valid counts to base_out[0..count) (rank base of each segment).
+// scratch of one warp-wide in-order combine
 struct SegCombineSmem {
   SegT<double> lanes[32];
   long long lane_base[32];
 };
-__device__ __forceinline__ SegT<double> combine_exports_warp(const float* e, int count, int* base_out, SegCombineSmem& sm) {
-  const int lane = threadIdx.x & 31;
-  const int chunk = (count + 31) / 32;
-  const int t0 = min(lane * chunk, count), t1 = min(t0 + chunk, count);
-  SegT<double> acc;
-  acc.n = 0; acc.wf = acc.wl = 0;
-  for (int k = 0; k < 3; ++k) acc.S0[k] = acc.S1[k] = acc.ol[k] = 0;
-  for (int t = t0; t < t1; ++t) acc = combine_seg<double>(acc, load_seg_export(e + (size_t)t * kSegExportFloats));
-  sm.lanes[lane] = acc;
-  {   // exclusive prefix of the lane counts
-    long long incl = acc.n;
-#pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-      long long v = __shfl_up_sync(kFullMask, incl, off);
-      if (lane >= off) incl += v;
-    }
-    sm.lane_base[lane] = incl - acc.n;
-  }
-  __syncwarp();
-  for (int off = 1; off < 32; off <<= 1) {   // in-order tree combine
-    if ((lane & (2 * off - 1)) == 0) sm.lanes[lane] = combine_seg<double>(sm.lanes[lane], sm.lanes[lane + off]);
-    __syncwarp();
-  }
-  long long run = sm.lane_base[lane];
-  for (int t = t0; t < t1; ++t) {
-    base_out[t] = (int)run;
-    run += __float_as_int(__ldcg(e + (size_t)t * kSegExportFloats));
-  }
-  const SegT<double> all = sm.lanes[0];
-  __syncwarp();
-  return all;
-}
 
-// The same over the `count` strip summaries of a level; base_out[0 .. count] = exclusive prefix of the strips' valid counts
+// One warp combines the `count` strip summaries of a level, in order, into one; base_out[0 .. count] = exclusive prefix of the
+// strips' valid counts
 // (base_out[count] = all valid points).
 __device__ __forceinline__ SegT<double> combine_strip_exports_warp(const double* e, int count, int* base_out, SegCombineSmem& sm) {
   const int lane = threadIdx.x & 31;
@@ -789,7 +752,7 @@ __device__ __forceinline__ void stage_a_run(TilePipe& tp, const PairLevel& pl, c
                                             float* row_exports, unsigned& tile_count, int* error_flag, PipeTiming& tm) {
   const int lane = threadIdx.x & 31, q = threadIdx.x >> 5;
   const unsigned lt_mask = (1u << lane) - 1u;
-  const int ntiles = (g.strip1 - g.strip0) * g.nbands;
+  const int ntiles = g.nmine * g.nbands;
   const unsigned tbase = tile_count;
   tile_count += ntiles;
   if (q == kConsumerWarps) {   // the producer warp
@@ -802,7 +765,7 @@ __device__ __forceinline__ void stage_a_run(TilePipe& tp, const PairLevel& pl, c
   const unsigned my_ref = pin((unsigned)(offsetof(StageBuf, ref0) + (q * kTileW + lane) * 8));
   const unsigned my_tx = pin((unsigned)(offsetof(StageBuf, tx) + lane * 4));
   const int gw = pin(g.w), gh = pin(g.h), gnb = pin(g.nbands), gpitch = g.pitch;
-  for (int s = g.strip0; s < g.strip1; ++s) {
+  for (int sk = 0, s = g.strip0; sk < g.nmine; ++sk, s += g.strip_step) {
     const int y = s * kTileH + q;
     const bool row_ok = y < gh;
     const float ty = __ldg(pl.rtmpl + gw + min(y, gh - 1));
@@ -966,14 +929,13 @@ __device__ __noinline__ void dump_record(const RecordDump& dump, size_t i, bool 
 // computeCompleteDataLogLikelihood (dense_tracking_impl.cpp:413-422).
 template <bool kDump>
 __device__ __forceinline__ void stage_b_run(TilePipe& tp, const PairLevel& pl, const LevelGeom& g, const StageConsts& c,
-                                            const StageBConsts& cb, const int* row_base, const int* strip_base, long long cta_base,
-                                            long long n_keep, bool cta_has_tail, const RecordDump& dump, float* row_partial,
-                                            unsigned& tile_count, int* error_flag, PipeTiming& tm) {
+                                            const StageBConsts& cb, const int* row_base, const int* strip_base, long long n_keep,
+                                            const RecordDump& dump, float* row_partial, unsigned& tile_count, int* error_flag,
+                                            PipeTiming& tm) {
   const int lane = threadIdx.x & 31, q = threadIdx.x >> 5;
   const unsigned lt_mask = (1u << lane) - 1u;
-  const int ntiles = (g.strip1 - g.strip0) * g.nbands;
+  const int ntiles = g.nmine * g.nbands;
   const unsigned tbase = tile_count;
-  const int keep_rank = (int)max(min(n_keep - cta_base, (long long)0x7fffffff), (long long)-1);   // first dropped rank, CTA-relative
   tile_count += ntiles;
   if (q == kConsumerWarps) {   // the producer warp
     produce_tiles<true>(tp, pl, g, c, tbase, ntiles, error_flag, tm);
@@ -984,12 +946,16 @@ __device__ __forceinline__ void stage_b_run(TilePipe& tp, const PairLevel& pl, c
   const unsigned my_ref = (unsigned)(offsetof(StageBuf, ref0) + (q * kTileW + lane) * 8);
   const unsigned my_tx = (unsigned)(offsetof(StageBuf, tx) + lane * 4);
   const int gw = g.w, gh = g.h, gnb = g.nbands, gpitch = g.pitch;
-  for (int s = g.strip0; s < g.strip1; ++s) {
+  for (int sk = 0, s = g.strip0; sk < g.nmine; ++sk, s += g.strip_step) {
     const int y = s * kTileH + q;
     const bool row_ok = y < gh;
     const float ty = __ldg(pl.rtmpl + gw + min(y, gh - 1));
-    int rank = 0;              // rank of the row's first point inside this CTA (n < 2^31)
-    if (cta_has_tail && row_ok) rank = (__ldcg(strip_base + s) - (int)cta_base) + __ldcg(row_base + y);
+    // the dropped tail of the log-likelihood (points of rank >= n_keep): only the strip(s) that reach past n_keep look at ranks
+    const long long sbase = __ldcg(strip_base + s);
+    const bool cta_has_tail = (long long)__ldcg(strip_base + s + 1) > n_keep;                 // warp-uniform
+    const int keep_rank = (int)max(min(n_keep - sbase, (long long)0x7fffffff), (long long)-1);   // first dropped rank, strip-relative
+    int rank = 0;              // rank of the row's first point inside its strip
+    if (cta_has_tail && row_ok) rank = __ldcg(row_base + y);
     StageBAcc acc;             // one image row at a time: the row's sums leave the warp in a fixed order (flush_row_partial)
     stage_b_init(acc);
     for (int b = 0; b < gnb; ++b, ++i) {

@@ -344,7 +344,6 @@ struct SquadState {
 struct LevelTail {      // shared memory after the tile pipeline
   SegCombineSmem comb;
   PairEndSmem end;
-  float red[kConsumerWarps][kNormalValues];
   int s_flag[2];
 };
 constexpr size_t kLevelSmemBytes = sizeof(TilePipe) + sizeof(LevelTail);
@@ -367,6 +366,7 @@ struct Segment {
   int* ready;             // fused launch, segments >= 1: ring of (pair + 1) whose coarse levels are done, 0 = not yet written
   int* ready_tail;
   int* arrivals;          // CTAs that have entered this segment (squads of segments >= 1 form in order of arrival)
+  int cyclic;             // 1: CTA r of a squad takes strips r, r + g, ...; 0: contiguous ranges of strips_per_cta strips
   int pair_begin;         // segments >= 1 of a fused launch own the pairs [pair_begin, pair_begin + npairs_seg)
   int npairs_seg;         // pairs handed out by this segment's queue
   unsigned long long* dbg2;  // optional (timing build): {tiles, inexact tiles, skipped tiles, rounds, rounds of inexact tiles, max / min CTA lifetime}
@@ -525,9 +525,14 @@ k_level_persistent(const __grid_constant__ PersistentArgs a) {
     const PairLevel pl = S.pls[(size_t)li * a.npairs + pair];
     LevelGeom geo;
     geo.w = lp.w; geo.h = lp.h; geo.n = lp.n; geo.pitch = lp.pitch; geo.nbands = lp.nbands; geo.nstrips = lp.nstrips;
-    geo.strip0 = min(rank * S.strips_per_cta[li], lp.nstrips);
-    geo.strip1 = min(geo.strip0 + S.strips_per_cta[li], lp.nstrips);
-    const int row0 = min(geo.strip0 * kTileH, lp.h), row1 = min(geo.strip1 * kTileH, lp.h);
+    if (S.cyclic) {   // CTA r takes strips r, r + g, r + 2g, ...: every CTA of the squad samples the whole image
+      const int g_eff = min(S.g, lp.nstrips);
+      geo.strip0 = min(rank, lp.nstrips); geo.strip_step = g_eff;
+      geo.nmine = rank < g_eff ? (lp.nstrips - rank + g_eff - 1) / g_eff : 0;
+    } else {          // contiguous ranges
+      geo.strip0 = min(rank * S.strips_per_cta[li], lp.nstrips); geo.strip_step = 1;
+      geo.nmine = min(geo.strip0 + S.strips_per_cta[li], lp.nstrips) - geo.strip0;
+    }
     if (!a.skip_begin) {   // DenseTracker::match, start of a level: the last CTA to arrive initialises the pair's level state
       if (squad_arrive(sq, episode, S.g, lt.s_flag)) {
         if (threadIdx.x == 0) {
@@ -554,8 +559,8 @@ k_level_persistent(const __grid_constant__ PersistentArgs a) {
       __syncthreads();
       // this CTA's strips: the rows of a strip in order -> the strip's summary (one thread per strip); row_base: rank of each
       // row's first point inside its strip
-      for (int j = threadIdx.x; j < geo.strip1 - geo.strip0; j += kCtaThreads) {
-        const int sj = geo.strip0 + j;
+      for (int j = threadIdx.x; j < geo.nmine; j += kCtaThreads) {
+        const int sj = geo.strip0 + j * geo.strip_step;
         combine_strip_rows(row_exports, sj * kTileH, min(sj * kTileH + kTileH, lp.h), row_base, strip_exports + (size_t)sj * kStripExportDoubles);
       }
       DVO_TOCK(0);
@@ -582,20 +587,18 @@ k_level_persistent(const __grid_constant__ PersistentArgs a) {
         StageBConsts cb;
         load_stage_b_consts(st, cb);
         const long long n_keep = __ldcg(&st.n_keep);
-        const long long my_base = __ldcg(&strip_base[geo.strip0]);
-        const long long my_n = __ldcg(&strip_base[geo.strip1]) - my_base;
         RecordDump dump;
         dump.planes = a.dump; dump.n = lp.n;
         const long long ts0 = DVO_CLOCK(tm);
-        if (a.dump) stage_b_run<true>(tp, pl, geo, c, cb, row_base, strip_base, my_base, n_keep, my_base + my_n > n_keep, dump, row_partial, tile_count, a.error_flag, tm);
-        else stage_b_run<false>(tp, pl, geo, c, cb, row_base, strip_base, my_base, n_keep, my_base + my_n > n_keep, dump, row_partial, tile_count, a.error_flag, tm);
+        if (a.dump) stage_b_run<true>(tp, pl, geo, c, cb, row_base, strip_base, n_keep, dump, row_partial, tile_count, a.error_flag, tm);
+        else stage_b_run<false>(tp, pl, geo, c, cb, row_base, strip_base, n_keep, dump, row_partial, tile_count, a.error_flag, tm);
         DVO_ADD(tm, rounds_b, DVO_CLOCK(tm) - ts0);
       }
       __syncthreads();
       // the rows of each of this CTA's strips, in order, in fp64: one thread per (strip, value)
-      for (int it = threadIdx.x; it < (geo.strip1 - geo.strip0) * kNormalValues; it += kCtaThreads) {
+      for (int it = threadIdx.x; it < geo.nmine * kNormalValues; it += kCtaThreads) {
         const int j = it / kNormalValues, i = it - j * kNormalValues;
-        const int sj = geo.strip0 + j;
+        const int sj = geo.strip0 + j * geo.strip_step;
         const int nrow = min(kTileH, lp.h - sj * kTileH);
         const float* rp = row_partial + (size_t)sj * kTileH * kNormalValues + i;
         float r[kTileH];
@@ -959,6 +962,7 @@ int launch_segments(dvo_b200_ctx* ctx, int nseg, const LevelLaunch (*lps)[kMaxLe
     S.squads = squads + sq_off;
     S.queue = counters + s; S.ready_tail = counters + kMaxSeg + s; S.arrivals = counters + 2 * kMaxSeg + s;
     S.pair_begin = plan.pair_begin; S.npairs_seg = plan.npairs;
+    S.cyclic = getenv("DVO_B200_CONTIGUOUS") ? 0 : 1;          // developer switch (results are identical either way)
     S.ready = ring + plan.pair_begin;
     const int slot = std::min(group_index + s, 7);
     S.dbg = ctx->d_dbg ? ctx->d_dbg + 16 * slot : nullptr;
