@@ -258,7 +258,7 @@ def run_reference(args, rank, world):
             "note": "the reference's build system needs Eigen3/OpenCV2/Sophus/ROS (absent here); its hot-path translation units "
                     "compile unmodified against header-only container shims (oracle/ref_shim) and are what this arm executes"
                     if kind == "reference" else "oracle/_ref absent: timed arm is the oracle's scalar FAITHFUL port"}
-    print(json.dumps(line))
+    emit(json.dumps(line))
 
 
 # ---------------------------------------------------------------------------------------------
@@ -586,7 +586,7 @@ def run_ours(args, rank, local_rank, world):
                              "pair_step_ms_per_step": prof["pair_step"]["ms"] / args.steps},
                 "e2e_consecutive_frames": e2e_seq,
                 "cpu_baseline": cpu, "clocks": clocks, "single_pair_latency_ms": lat_ms}
-        print(json.dumps(line))
+        emit(json.dumps(line))
 
 
 def main():
@@ -614,5 +614,26 @@ def main():
             dist.destroy_process_group()
 
 
+_JSON_OUT = None
+
+
+def emit(text):
+    """The one JSON line of the contract, on the process's ORIGINAL stdout."""
+    out = _JSON_OUT or sys.stdout
+    out.write(text + "\n")
+    out.flush()
+
+
+def _reserve_stdout():
+    """Rank 0 prints exactly one line on stdout.  Libraries write there too (NCCL prints its version banner at
+    NCCL_DEBUG=VERSION and above, whatever this process sets later): keep a private handle on the original stdout for the JSON
+    line and point file descriptor 1 at stderr for everything else."""
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
 if __name__ == "__main__":
+    _reserve_stdout()
     main()
