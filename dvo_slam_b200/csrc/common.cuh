@@ -18,9 +18,10 @@ namespace dvo_b200 {
 constexpr int kMaxLevels = DVO_B200_MAX_LEVELS;
 
 // ---- device image layout --------------------------------------------------------------------
-// Per image, per level l: four float2 planes of h_l rows, row pitch = w_l rounded up to even (every row
-// starts 16-byte aligned, which the bulk-copy engine requires of its sources):
-//   P0 = (I, Z')   P1 = (Ix, Iy)   P2 = (I, Z)   P3 = (I, Zsel)
+// Per image, per level l: two float2 planes of h_l rows, row pitch = w_l rounded up to even (every row
+// starts 16-byte aligned, which the bulk-copy engine requires of its sources), for the role of CURRENT image:
+//   P0 = (I, Z')   P2 = (I, Z)
+// and the REFERENCE TILE RECORDS (below) for the role of reference image: (I, Zsel), tx and (Ix, Iy) per tile.
 // Z' is the depth with NaN wherever ANY of the six channels is NaN at that pixel: a bilinear tap
 // on such a pixel makes the reference reject the point (cmpunord over the 8-vector,
 // dense_tracking_impl.cpp:261) and a reference point there fails isPointOk (point_selection.h:63-66),
@@ -33,7 +34,7 @@ constexpr int kMaxLevels = DVO_B200_MAX_LEVELS;
 // gradient planes of the current image are never read (the depth gradients are not even stored).
 // Zsel is the depth where the pixel belongs to the reference point list of PointSelection::select
 // (point_selection.cpp:89-152; the odd last point that computeResidualsSse skips excluded) and NaN
-// elsewhere: the reference side of an alignment reads P3 and P1 and needs no mask lookup -- an
+// elsewhere: the reference side of an alignment reads the tile records and needs no mask lookup -- an
 // unselected point projects to NaN and fails the bounds test like any other rejected point.
 struct LevelInfo {
   int w, h, n, words;          // n = w*h pixels, words = ceil(n/32) selection-mask words (linear index y*w+x)

@@ -428,7 +428,7 @@ int pyramid_build_batch_input(dvo_b200_ctx* ctx, int n, const void* d_I, const v
   return 0;
 }
 
-// The selection (mask, {S, last}, the Zsel channel of P3) is state of the PYRAMID, shared by every context that aligns
+// The selection (mask, {S, last}, the Zsel channel of the reference tile records) is state of the PYRAMID, shared by every context that aligns
 // against it, while the reference keeps it per tracker (PointSelection, point_selection.cpp:100-113).  Contexts that use
 // the same thresholds -- every caller in dvo_slam: one configuration per tracker family -- never get here twice.  A context
 // that asks for other thresholds rewrites the selection on its stream; the host-side state is guarded by sel_mu and the

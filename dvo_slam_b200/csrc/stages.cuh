@@ -10,18 +10,25 @@
 // Data movement.  The reference image is cut into tiles of kTileW x kTileH pixels; a CTA owns whole
 // strips (kTileH full image rows) and walks their tiles band by band.  For every tile a producer warp
 // asks the bulk-copy engine (cp.async.bulk, the TMA unit) for
-//   * the tile's rows of the reference planes (P0; in stage B also P1), and
+//   * the tile's REFERENCE TILE RECORD (common.cuh): its rows of (I, Zsel), its slice of the point-cloud
+//     template and -- in stage B -- its rows of (Ix, Iy), contiguous in HBM: one copy, and
 //   * the WINDOW of the current image the tile's bilinear taps fall into: its bounding box follows from
 //     projecting the tile's four corner rays at the minimum and maximum depth of the tile (a projective map
-//     keeps the convex hull), plus the one-pixel halo the central differences need,
-// into one of kStages shared-memory stage buffers and arms an mbarrier with the byte count; the eight
+//     keeps the convex hull), plus the one-pixel halo the central differences need: one copy per window row,
+// into one of kStages shared-memory stage buffers and arms an mbarrier with the byte count; the seven
 // consumer warps (warp q <-> tile row q) wait on it, compute from shared memory and release the buffer
-// through a second mbarrier, on which the producer waits before it refills the buffer.  Nothing is written back: stage B recomputes the residual of stage A from the
-// staged tile (same operations, same bits) instead of reading a record, so per pixel and iteration the
-// kernel moves 8 (ref P0) + 8 x window overlap (cur P0) bytes in stage A and 16 + 8 x overlap in stage B.
+// through a second mbarrier, on which the producer waits before it refills the buffer.  Nothing per pixel is
+// written back: stage B recomputes the residual of stage A from the staged tile (same operations, same bits)
+// instead of reading a record, so per pixel and iteration the kernel moves 8 (reference) + 8 x window overlap
+// (current P0) bytes in stage A and 16 + 8 x overlap (current P2) in stage B.
 // A tap outside the staged window (window larger than the buffer, point behind the camera, ...) is
 // gathered from global memory by the same code through generic pointers: the window is a cache, never a
 // correctness condition.
+//
+// Sums.  A warp owns an image row: the pairwise scale sums of the row leave it as one 12-float summary, the 28
+// normal-equation values of the row through a fixed halving exchange (flush_row_partial).  Everything above a row is
+// combined by the level kernel in an order fixed by the level's geometry (rows of a strip in order, strips in order,
+// fp64), so results do not depend on how strips are spread over CTAs.
 //
 // The gradient channels of the current image are formed from the staged (I, Z) neighbours of each tap:
 // (P[x+1] - P[x-1]) * 0.5 with clamped indices is exactly calculateDerivativeX/Y (rgbd_image.cpp:419-472);
@@ -29,8 +36,8 @@
 // so every rounding step equals the one the precomputed gradient planes would give.
 //
 // All arithmetic that decides validity is explicit round-to-nearest fp32 in a fixed order (packed f32x2
-// where two channels share an operation), mirrored bit for bit by the oracle's MIRROR mode; sums use
-// whatever contraction the compiler picks.
+// where two channels share an operation), mirrored bit for bit by the oracle's MIRROR mode; the per-thread
+// accumulation along a row uses whatever contraction the compiler picks.
 #pragma once
 #include "common.cuh"
 #include "f32x2.cuh"

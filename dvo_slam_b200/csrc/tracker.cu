@@ -11,9 +11,11 @@
 // each followed by a small per-pair step (pair_mid_warp: P_k; pair_end_cta: accept test, 6x6 LDL^T
 // solve, SE(3) update, termination logic).  Both stages read their inputs from shared-memory tiles that a
 // producer warp fills with bulk asynchronous copies (TMA unit) through an mbarrier pipeline; nothing but
-// per-row / per-CTA summaries is written.  match() runs everything inside ONE persistent cooperative
-// kernel per pyramid level (k_level_persistent); the test hooks (residual image, linearize) run the same
-// kernel for one pair and one iteration.
+// per-row / per-strip summaries is written.  A batch that fills the GPU runs ALL levels inside ONE persistent
+// cooperative launch (k_level_persistent: a coarse segment with one CTA per pair, then slices of the fine levels
+// with squads of g, 2g and 4g CTAs); small batches use one launch per level; the test hooks (residual image,
+// linearize) run the same kernel for one pair and one iteration.  All sums above an image row are taken in an
+// order fixed by the level's geometry, so every plan returns the same bits.
 #include "common.cuh"
 #include "stages.cuh"
 
@@ -29,7 +31,7 @@ namespace dvo_b200 {
 namespace {
 
 constexpr unsigned kFull = 0xffffffffu;
-constexpr int kEndWarps = 4;   // warps that sum the CTA partials in pair_end_cta
+constexpr int kEndWarps = 4;   // warps that sum the level's strip partials in pair_end_cta
 
 struct LevelLaunch {
   int w, h, n, pitch;
@@ -169,7 +171,7 @@ __device__ __noinline__ void pair_mid_warp(PairState& st, int pair, const double
   __syncwarp();
 }
 
-// End of an iteration (dense_tracking.cpp:297-363): reduce the CTA partials, log-likelihood, accept test, solve,
+// End of an iteration (dense_tracking.cpp:297-363): add the level's strip partials, log-likelihood, accept test, solve,
 // pose update, termination.  Every thread of the CTA calls; thread 0 does the scalar part in two steps:
 //   critical : everything the other CTAs of the squad wait for -- the new K*T and iteration flag, or
 //              level_active = 0 -- followed by `release` (the squad barrier of the persistent kernel);
@@ -322,15 +324,15 @@ __device__ __noinline__ void pair_end_cta(PairState& st, const PairLevel& pl, in
 }
 
 // ------------------------------------------------------------------------------------------------
-// One persistent cooperative kernel per pyramid level.
+// The persistent cooperative level kernel.
 //
-// The grid is num_sms x C CTAs (C = resident CTAs per SM, 2 with ~98 KB of shared memory each) of 8 warps.  CTAs are grouped into squads of g CTAs; a squad owns ONE frame pair at a time, each CTA a
-// contiguous range of strips (kTileH image rows), and runs all its Gauss-Newton iterations on this level inside the
-// kernel:
-//   stage A over the CTA's tiles -> per-row scale summaries -> CTA summary -> squad barrier, the last CTA to
-//   arrive computes P_k (pair_mid_warp) -> stage B -> CTA partial sums -> squad barrier, the last CTA reduces
-//   the partials, tests the log-likelihood, solves the 6x6 system and updates the pose (pair_end_cta) -> next
-//   iteration,
+// The grid is num_sms x C CTAs (C = resident CTAs per SM, 2 with ~93 KB of shared memory each) of 8 warps.  CTAs are
+// grouped into squads of g CTAs; a squad owns ONE frame pair at a time, CTA r of the squad the strips r, r+g, r+2g, ...
+// (kTileH image rows each), and runs all its Gauss-Newton iterations on the segment's levels inside the kernel:
+//   stage A over the CTA's tiles -> per-row scale summaries -> per-strip summaries (fp64) -> squad barrier, the last
+//   CTA to arrive combines the level's strips and computes P_k (pair_mid_warp) -> stage B -> per-row sums -> per-strip
+//   sums (fp64) -> squad barrier, the last CTA adds the level's strips, tests the log-likelihood, solves the 6x6
+//   system and updates the pose (pair_end_cta) -> next iteration,
 // then takes the next pair from a global queue.  The two resident CTAs of an SM belong to different squads, so
 // one squad's barrier wait is hidden by the other.
 // ------------------------------------------------------------------------------------------------
