@@ -137,23 +137,23 @@ k_pyr_finish(const void* __restrict__ I0, const void* __restrict__ Z0, float zsc
   if ((threadIdx.x & 31) == 0 && idx < ((n + 31) / 32) * 32) masks[img * mask_words_per_image + mask_off + (idx >> 5)] = m;
 }
 
-// The parts of the reference tile records that no pixel owns: cells of border tiles outside the image (never selected)
-// and the tx[] slice of every tile.  One thread per record cell; runs after k_template.
+// The parts of the reference tile records that no pixel owns: the tx[] slice of every tile and, in border tiles, the cells
+// outside the image (never selected).  One thread per tile column; runs after k_template.
 __global__ void k_rec_fill(float2* __restrict__ planes, size_t planes_per_image, size_t rec_off, int nbands, int ntiles, int w, int h,
                            const float* __restrict__ tmpl, size_t tmpl_per_image, size_t tmpl_off) {
   const int img = blockIdx.y;
-  const int cell = blockIdx.x * blockDim.x + threadIdx.x;
-  if (cell >= ntiles * kTileH * kTileW) return;
-  const int tile = cell / (kTileH * kTileW), rcell = cell - tile * (kTileH * kTileW);
-  const int r = rcell / kTileW, cx = rcell - r * kTileW;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ntiles * kTileW) return;
+  const int tile = t / kTileW, cx = t - tile * kTileW;
   const int s = tile / nbands, b = tile - s * nbands;
-  const int x = b * kTileW + cx, y = s * kTileH + r;
+  const int x = b * kTileW + cx, y0 = s * kTileH;
   float2* rec = planes + img * planes_per_image + rec_off + (size_t)tile * kRecF2;
-  if (x >= w || y >= h) {
-    rec[rcell] = make_float2(0.f, __int_as_float(0x7fc00000));
-    rec[kRecP1 + rcell] = make_float2(0.f, 0.f);
+  reinterpret_cast<float*>(rec + kRecTx)[cx] = x < w ? tmpl[img * tmpl_per_image + tmpl_off + x] : 0.f;
+  const int r0 = x >= w ? 0 : min(max(h - y0, 0), kTileH);      // first row of this column that lies outside the image
+  for (int r = r0; r < kTileH; ++r) {
+    rec[r * kTileW + cx] = make_float2(0.f, __int_as_float(0x7fc00000));
+    rec[kRecP1 + r * kTileW + cx] = make_float2(0.f, 0.f);
   }
-  if (r == 0) reinterpret_cast<float*>(rec + kRecTx)[cx] = x < w ? tmpl[img * tmpl_per_image + tmpl_off + x] : 0.f;
 }
 
 // {min, max} of the non-NaN Z' of every tile of kTileW x kTileH pixels (one warp per tile).  The level kernel
@@ -400,7 +400,7 @@ int pyramid_build_batch_input(dvo_b200_ctx* ctx, int n, const void* d_I, const v
       k_sel_info<<<n, 32, 0, st>>>(masks, mask_words, q.mask_off, q.words, sel, sel_ints, l);
       k_drop_odd_last<<<(n + 127) / 128, 128, 0, st>>>(planes, plane_f2, q.rec_off, q.nbands, q.w, sel, sel_ints, l, n);
       const int ntiles = q.nbands * q.nstrips;
-      k_rec_fill<<<dim3((ntiles * kTileH * kTileW + T - 1) / T, n), T, 0, st>>>(planes, plane_f2, q.rec_off, q.nbands, ntiles, q.w, q.h,
+      k_rec_fill<<<dim3((ntiles * kTileW + T - 1) / T, n), T, 0, st>>>(planes, plane_f2, q.rec_off, q.nbands, ntiles, q.w, q.h,
                                                                               tmpl, tmpl_floats, q.tmpl_off);
       ctx->launches += 1;
       k_tile_range<<<dim3((ntiles + 7) / 8, n), 256, 0, st>>>(planes, plane_f2, q.plane_off, q.w, q.h, q.pitch, q.nbands, ntiles,
