@@ -143,3 +143,23 @@ def test_c_abi_shard_range_is_the_partition_of_the_multi_process_path():
     if not torch.cuda.is_available():
         with pytest.raises(RuntimeError, match="no usable CUDA device"):
             engine.ShardedEngine([0, 0])
+
+
+def test_scale_sum_segments_combine_like_the_reference_walk(tmp_path):
+    """The pairwise scale sum of computeScaleSse (dense_tracking_impl.cpp:590-638: (w_2j + w_2j+1) r_2j r_2j^T per pair of the
+    compacted list, odd tail alone) from the kernel's segment summaries: SegT / combine_seg of csrc/stages.cuh, compiled for
+    the HOST, combined left to right, through random parenthesisations and in the kernel's row -> strip -> level order,
+    against the sequential walk (tests/native/seg_monoid.cu)."""
+    import shutil
+    import subprocess
+    ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    exe = str(tmp_path / "seg_monoid")
+    r = subprocess.run([nvcc, "-std=c++17", "--expt-relaxed-constexpr", "-w", "-I", os.path.join(ROOT, "dvo_slam_b200", "csrc"),
+                        "-I", os.path.join(ROOT, "include"), "-o", exe, os.path.join(ROOT, "tests", "native", "seg_monoid.cu")],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stdout[-2000:]
